@@ -1,0 +1,522 @@
+// c4_net.cu -- fused residual value/policy network forward (oinkoink/neural/pytorch/model.py:20-134, eval mode).
+//
+// One launch evaluates a whole leaf batch: bitboards in (16 B/position), {prior[7], value} out (32 B/position);
+// every intermediate activation stays on chip.
+//
+// Kernel A (filters = 32, the default NetConfig): WARP-PER-BOARD fused tower.
+//   * all BN-folded bf16 conv weights (stem + 2R residual convs, 123 KB) and the fp32 head parameters stay resident
+//     in shared memory for the life of the CTA; a persistent grid of 148 CTAs x 8 warps strides over the batch.
+//   * a board is laid out as an 8-wide padded pixel strip (row stride 8 = 7 columns + one shared zero column), so a
+//     3x3 tap is a constant row offset and every conv is 9 shifted [48 x Cin] x [Cin x 32] bf16 GEMMs
+//     (mma.sync m16n8k16, fp32 accumulate, operands via ldmatrix from conflict-free padded rows).
+//   * the residual stream is kept in fp32 registers (same fragment layout for every layer); shared memory only holds
+//     the bf16 operand copy.  No block-level barrier anywhere: a warp only touches its own board.
+//   * heads are fused: 1x1 convs straight from the fp32 fragments (quad shuffles), the (pre-multiplied) value MLP,
+//     tanh, the policy linear and the 7-way softmax.
+// Kernel B (filters = 64, example_config): same math, but weights do not fit on chip (897 KB): the CTA walks the layers
+//   together and streams each layer's weights L2 -> shared memory; the residual is re-read from the bf16 copy.
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "c4_common.cuh"
+
+#define NPX 66            // padded pixel rows: q in [-1, 64], row index q + 1
+#define LEAKY 0.01f
+
+// offsets inside the fp32 head block
+#define HO_VW 0           // value conv weight [F] (max 64)
+#define HO_PW 64          // policy conv weight [2][F] (max 128)
+#define HO_VB 192         // value conv bias
+#define HO_PB 193         // policy conv bias [2]
+#define HO_FC1B 195
+#define HO_W1 196
+#define HO_W2 197
+#define HO_FCB 200        // [42]
+#define HO_FC1W 242       // [42]
+#define HO_POLB 284       // [7]
+#define HO_FCT 292        // [42][42] transposed: FCT[j*42+i] = W_eff[i][j]
+#define HO_POLW 2056      // [7][84]
+#define HEAD_FLOATS 2656  // fp32 head parameter block (2644 used)
+
+struct c4_net {
+    int device;
+    int F, R, n_fc;
+    void *image;          // device: smem image (kernel A) / per-layer weight images (kernel B)
+    size_t image_bytes;
+    double flops;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float *c, const uint32_t *a, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : LEAKY * x; }
+
+// One 3x3 convolution of one board as implicit GEMM: acc[t][j][.] (+)= sum over taps/channels.
+//   src: padded activation strip (row stride AS bytes), W: [F][9*CIN + 8] bf16 rows (stride WS bytes)
+template <int F, int CIN>
+__device__ __forceinline__ void conv3x3(float (&acc)[3][F / 8][4], uint32_t src, uint32_t W, int lane)
+{
+    constexpr int AS = F * 2 + 16;
+    constexpr int WS = (9 * CIN + 8) * 2;
+    constexpr int NT = F / 8;
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) acc[t][j][e] = 0.f;
+    // per-lane ldmatrix row addresses
+    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;       // A: matrices 0/1 = rows 0-7 / 8-15, 2/3 = k+8
+    const uint32_t a_base = src + (uint32_t)((8 + arow + 1) * AS + (lane >> 4) * 16);
+    const uint32_t b_base = W + (uint32_t)((((lane >> 4) & 1) * 8 + (lane & 7)) * WS + ((lane >> 3) & 1) * 16);
+#pragma unroll 1
+    for (int tap = 0; tap < 9; tap++) {
+        const int off = (tap / 3 - 1) * 8 + (tap % 3 - 1);
+#pragma unroll
+        for (int kc = 0; kc < CIN / 16; kc++) {
+            uint32_t a[3][4];
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+                ldsm4(a_base + (uint32_t)((16 * t + off) * AS + kc * 32), a[t][0], a[t][1], a[t][2], a[t][3]);
+#pragma unroll
+            for (int jp = 0; jp < NT / 2; jp++) {
+                uint32_t b0, b1, b2, b3;
+                ldsm4(b_base + (uint32_t)(jp * 16 * WS + (tap * CIN + kc * 16) * 2), b0, b1, b2, b3);
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    mma16816(acc[t][2 * jp], a[t], b0, b1);
+                    mma16816(acc[t][2 * jp + 1], a[t], b2, b3);
+                }
+            }
+        }
+    }
+}
+
+// board -> bf16 input planes (Board.to_array, oinkoink/board.py:147-154) in channels 0..15 of the strip
+template <int F>
+__device__ __forceinline__ void write_input(unsigned char *buf, u64 c0, u64 c1, int lane)
+{
+    constexpr int AS = F * 2 + 16;
+    const uint32_t tomove = ((__popcll(c0 | c1) & 1) == 0) ? 0x3F80u : 0u;
+    for (int px = lane; px < 42; px += 32) {
+        int r = px / 7, c = px - r * 7;
+        int bit = 7 * c + (5 - r);
+        uint32_t o = (uint32_t)((c0 >> bit) & 1ULL) * 0x3F80u, x = (uint32_t)((c1 >> bit) & 1ULL) * 0x3F80u;
+        uint4 v0 = make_uint4(tomove | (o << 16), x, 0u, 0u), v1 = make_uint4(0u, 0u, 0u, 0u);
+        unsigned char *row = buf + (size_t)(((r + 1) * 8 + (c + 1)) + 1) * AS;
+        *reinterpret_cast<uint4 *>(row) = v0;
+        *reinterpret_cast<uint4 *>(row + 16) = v1;
+    }
+}
+
+// store the activated fp32 fragments as the bf16 operand copy (valid pixels only: pad column rows stay zero)
+template <int F>
+__device__ __forceinline__ void store_act(unsigned char *buf, const float (&v)[3][F / 8][4], int lane)
+{
+    constexpr int AS = F * 2 + 16;
+    const int g = lane >> 2, tq = lane & 3;
+    if (g == 0) return;
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+#pragma unroll
+        for (int j = 0; j < F / 8; j++) {
+            unsigned char *p = buf + (size_t)((8 + 16 * t + g) + 1) * AS + (j * 8 + 2 * tq) * 2;
+            *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(v[t][j][0], v[t][j][1]);
+            *reinterpret_cast<__nv_bfloat162 *>(p + 8 * AS) = __floats2bfloat162_rn(v[t][j][2], v[t][j][3]);
+        }
+}
+
+// value + policy heads from the fp32 trunk fragments (model.py:77-91,107-117); scratch: >= 126 floats of shared memory
+template <int F>
+__device__ __forceinline__ void heads(const float (&x)[3][F / 8][4], const float *hp, float *scratch, float *out, int lane)
+{
+    const int g = lane >> 2, tq = lane & 3;
+    float pv[3][2], p0[3][2], p1[3][2];
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+            for (int j = 0; j < F / 8; j++) {
+                int co = j * 8 + 2 * tq;
+                float x0 = x[t][j][2 * h], x1 = x[t][j][2 * h + 1];
+                a = fmaf(x0, hp[HO_VW + co], a); a = fmaf(x1, hp[HO_VW + co + 1], a);
+                b = fmaf(x0, hp[HO_PW + co], b); b = fmaf(x1, hp[HO_PW + co + 1], b);
+                c = fmaf(x0, hp[HO_PW + F + co], c); c = fmaf(x1, hp[HO_PW + F + co + 1], c);
+            }
+            pv[t][h] = a; p0[t][h] = b; p1[t][h] = c;
+        }
+#pragma unroll
+    for (int t = 0; t < 3; t++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            pv[t][h] += __shfl_xor_sync(0xffffffffu, pv[t][h], 1); pv[t][h] += __shfl_xor_sync(0xffffffffu, pv[t][h], 2);
+            p0[t][h] += __shfl_xor_sync(0xffffffffu, p0[t][h], 1); p0[t][h] += __shfl_xor_sync(0xffffffffu, p0[t][h], 2);
+            p1[t][h] += __shfl_xor_sync(0xffffffffu, p1[t][h], 1); p1[t][h] += __shfl_xor_sync(0xffffffffu, p1[t][h], 2);
+        }
+    __syncwarp();
+    if (tq == 0 && g != 0) {
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int q = 8 + 16 * t + g + 8 * h;
+                int idx = ((q >> 3) - 1) * 7 + ((q & 7) - 1);
+                scratch[idx] = leaky(pv[t][h] + hp[HO_VB]);
+                scratch[42 + idx] = leaky(p0[t][h] + hp[HO_PB]);
+                scratch[84 + idx] = leaky(p1[t][h] + hp[HO_PB + 1]);
+            }
+    }
+    __syncwarp();
+    // value: (pre-multiplied) Linear(42,42) stack -> LeakyReLU -> Linear(42,1) -> tanh -> (x + w1) * w2
+    float part = 0.f;
+    for (int i = lane; i < 42; i += 32) {
+        float a = hp[HO_FCB + i];
+#pragma unroll 6
+        for (int j = 0; j < 42; j++) a = fmaf(hp[HO_FCT + j * 42 + i], scratch[j], a);
+        part = fmaf(hp[HO_FC1W + i], leaky(a), part);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    const float value = (tanhf(part + hp[HO_FC1B]) + hp[HO_W1]) * hp[HO_W2];
+    // policy: Linear(84,7) on the channel-major flatten -> softmax
+    float lg[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) lg[k] = 0.f;
+    for (int m = lane; m < 84; m += 32) {
+        float xv = scratch[42 + m];
+#pragma unroll
+        for (int k = 0; k < 7; k++) lg[k] = fmaf(hp[HO_POLW + k * 84 + m], xv, lg[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) lg[k] += __shfl_xor_sync(0xffffffffu, lg[k], off);
+        lg[k] += hp[HO_POLB + k];
+    }
+    float mx = lg[0];
+#pragma unroll
+    for (int k = 1; k < 7; k++) mx = fmaxf(mx, lg[k]);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 7; k++) { lg[k] = expf(lg[k] - mx); sum += lg[k]; }
+    float mine = value;
+#pragma unroll
+    for (int k = 0; k < 7; k++) if (lane == k) mine = lg[k] / sum;
+    if (lane < 8) out[lane] = mine;
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------ kernel A (F = 32)
+// shared-memory image: [stem W 32x(144+8) bf16][2R conv W 32x(288+8) bf16][biases (1+2R) x 32 f32][head f32]
+template <int F>
+struct ImageA {
+    static constexpr int WS_STEM = (9 * 16 + 8) * 2;
+    static constexpr int WS = (9 * F + 8) * 2;
+    __host__ __device__ static constexpr size_t stem_bytes() { return (size_t)F * WS_STEM; }
+    __host__ __device__ static constexpr size_t conv_bytes() { return (size_t)F * WS; }
+    __host__ __device__ static constexpr size_t bias_off(int R) { return stem_bytes() + 2 * R * conv_bytes(); }
+    __host__ __device__ static constexpr size_t head_off(int R) { return bias_off(R) + (size_t)(1 + 2 * R) * F * 4; }
+    __host__ __device__ static constexpr size_t total(int R) { return head_off(R) + HEAD_FLOATS * 4; }
+};
+
+template <int F, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_net_resident(const unsigned char *__restrict__ image, int image_bytes, int R, const u64 *__restrict__ c0,
+               const u64 *__restrict__ c1, int n, const int *__restrict__ count, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int AS = F * 2 + 16;
+    constexpr int ACT = NPX * AS;
+    if (count) { int m = *count; n = m < n ? m : n; }
+    if ((int)blockIdx.x * WARPS >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // resident parameters
+    for (int i = threadIdx.x; i < image_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(smem)[i] = reinterpret_cast<const uint4 *>(image)[i];
+    unsigned char *X = smem + image_bytes + (size_t)warp * 2 * ACT;
+    unsigned char *H = X + ACT;
+    for (int i = lane; i < 2 * ACT / 16; i += 32) reinterpret_cast<uint4 *>(X)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const uint32_t sX = smem_u32(X), sH = smem_u32(H), sW = smem_u32(smem);
+    const float *bias = reinterpret_cast<const float *>(smem + ImageA<F>::stem_bytes() + 2 * R * ImageA<F>::conv_bytes());
+    const float *hp = bias + (1 + 2 * R) * F;
+    const int tq = lane & 3;
+
+    for (int b = blockIdx.x * WARPS + warp; b < n; b += gridDim.x * WARPS) {
+        const u64 bc0 = c0[b], bc1 = c1[b];
+        write_input<F>(H, bc0, bc1, lane);
+        __syncwarp();
+        float acc[3][F / 8][4], res[3][F / 8][4];
+        // stem: conv3x3(3->F) + BN + LeakyReLU (model.py:20-31)
+        conv3x3<F, 16>(acc, sH, sW, lane);
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+#pragma unroll
+            for (int j = 0; j < F / 8; j++) {
+                float b0 = bias[j * 8 + 2 * tq], b1 = bias[j * 8 + 2 * tq + 1];
+                res[t][j][0] = leaky(acc[t][j][0] + b0); res[t][j][1] = leaky(acc[t][j][1] + b1);
+                res[t][j][2] = leaky(acc[t][j][2] + b0); res[t][j][3] = leaky(acc[t][j][3] + b1);
+            }
+        store_act<F>(X, res, lane);
+        __syncwarp();
+        // residual tower (model.py:45-55)
+#pragma unroll 1
+        for (int r = 0; r < R; r++) {
+            const uint32_t w1 = sW + (uint32_t)(ImageA<F>::stem_bytes() + (size_t)(2 * r) * ImageA<F>::conv_bytes());
+            const uint32_t w2 = w1 + (uint32_t)ImageA<F>::conv_bytes();
+            const float *bb1 = bias + (1 + 2 * r) * F, *bb2 = bb1 + F;
+            conv3x3<F, F>(acc, sX, w1, lane);
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int j = 0; j < F / 8; j++) {
+                    float b0 = bb1[j * 8 + 2 * tq], b1 = bb1[j * 8 + 2 * tq + 1];
+                    acc[t][j][0] = leaky(acc[t][j][0] + b0); acc[t][j][1] = leaky(acc[t][j][1] + b1);
+                    acc[t][j][2] = leaky(acc[t][j][2] + b0); acc[t][j][3] = leaky(acc[t][j][3] + b1);
+                }
+            store_act<F>(H, acc, lane);
+            __syncwarp();
+            conv3x3<F, F>(acc, sH, w2, lane);
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int j = 0; j < F / 8; j++) {
+                    float b0 = bb2[j * 8 + 2 * tq], b1 = bb2[j * 8 + 2 * tq + 1];
+                    res[t][j][0] = leaky(acc[t][j][0] + b0 + res[t][j][0]); res[t][j][1] = leaky(acc[t][j][1] + b1 + res[t][j][1]);
+                    res[t][j][2] = leaky(acc[t][j][2] + b0 + res[t][j][2]); res[t][j][3] = leaky(acc[t][j][3] + b1 + res[t][j][3]);
+                }
+            if (r + 1 < R) store_act<F>(X, res, lane);
+            __syncwarp();
+        }
+        heads<F>(res, hp, reinterpret_cast<float *>(H), out + (size_t)b * 8, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel B (F = 64)
+// global image: [stem W][2R conv W][biases][head]; shared: one layer's weights + biases + head + per-warp strips
+template <int F, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__restrict__ c0, const u64 *__restrict__ c1,
+               int n, const int *__restrict__ count, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int AS = F * 2 + 16;
+    constexpr int ACT = NPX * AS;
+    constexpr int NT = F / 8;
+    if (count) { int m = *count; n = m < n ? m : n; }
+    if ((int)blockIdx.x * WARPS >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tq = lane & 3, g = lane >> 2;
+    const size_t conv_b = ImageA<F>::conv_bytes(), stem_b = ImageA<F>::stem_bytes();
+    unsigned char *Wbuf = smem;                                               // conv_b bytes
+    float *small = reinterpret_cast<float *>(smem + conv_b);                  // biases + head
+    const int small_bytes = (1 + 2 * R) * F * 4 + HEAD_FLOATS * 4;
+    unsigned char *X = smem + conv_b + small_bytes + (size_t)warp * 2 * ACT;
+    unsigned char *H = X + ACT;
+    {
+        const unsigned char *src = image + ImageA<F>::bias_off(R);
+        for (int i = threadIdx.x; i < small_bytes / 16; i += blockDim.x)
+            reinterpret_cast<uint4 *>(small)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    }
+    for (int i = lane; i < 2 * ACT / 16; i += 32) reinterpret_cast<uint4 *>(X)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const float *bias = small, *hp = small + (1 + 2 * R) * F;
+    const uint32_t sX = smem_u32(X), sH = smem_u32(H), sW = smem_u32(Wbuf);
+
+    const int per_round = gridDim.x * WARPS;
+    for (int base = 0; base < n; base += per_round) {                         // CTA-uniform trip count
+        const int b = base + blockIdx.x * WARPS + warp;
+        const bool active = b < n;
+        float acc[3][NT][4];
+        // layer 0: stem
+        __syncthreads();
+        for (int i = threadIdx.x; i < (int)(stem_b / 16); i += blockDim.x)
+            reinterpret_cast<uint4 *>(Wbuf)[i] = reinterpret_cast<const uint4 *>(image)[i];
+        if (active) write_input<F>(H, c0[b], c1[b], lane);
+        __syncthreads();
+        if (active) {
+            conv3x3<F, 16>(acc, sH, sW, lane);
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) {
+                    float b0 = bias[j * 8 + 2 * tq], b1 = bias[j * 8 + 2 * tq + 1];
+                    acc[t][j][0] = leaky(acc[t][j][0] + b0); acc[t][j][1] = leaky(acc[t][j][1] + b1);
+                    acc[t][j][2] = leaky(acc[t][j][2] + b0); acc[t][j][3] = leaky(acc[t][j][3] + b1);
+                }
+            store_act<F>(X, acc, lane);
+        }
+#pragma unroll 1
+        for (int l = 0; l < 2 * R; l++) {
+            __syncthreads();
+            const unsigned char *src = image + stem_b + (size_t)l * conv_b;
+            for (int i = threadIdx.x; i < (int)(conv_b / 16); i += blockDim.x)
+                reinterpret_cast<uint4 *>(Wbuf)[i] = reinterpret_cast<const uint4 *>(src)[i];
+            __syncthreads();
+            if (!active) continue;
+            const float *bb = bias + (1 + l) * F;
+            const bool second = (l & 1);
+            conv3x3<F, F>(acc, second ? sH : sX, sW, lane);
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int j = 0; j < NT; j++) {
+                    float b0 = bb[j * 8 + 2 * tq], b1 = bb[j * 8 + 2 * tq + 1];
+                    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+                    if (second && g != 0) {                                      // residual from the bf16 copy
+                        const unsigned char *p = X + (size_t)((8 + 16 * t + g) + 1) * AS + (j * 8 + 2 * tq) * 2;
+                        float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p));
+                        float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p + 8 * AS));
+                        r0 = lo.x; r1 = lo.y; r2 = hi.x; r3 = hi.y;
+                    }
+                    acc[t][j][0] = leaky(acc[t][j][0] + b0 + r0); acc[t][j][1] = leaky(acc[t][j][1] + b1 + r1);
+                    acc[t][j][2] = leaky(acc[t][j][2] + b0 + r2); acc[t][j][3] = leaky(acc[t][j][3] + b1 + r3);
+                }
+            __syncwarp();
+            if (l + 1 < 2 * R) store_act<F>(second ? X : H, acc, lane);
+            __syncwarp();
+        }
+        if (active) heads<F>(acc, hp, reinterpret_cast<float *>(H), out + (size_t)b * 8, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static uint16_t f2bf(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)((u + r) >> 16);
+}
+
+// pack W[co][ci][ky][kx] (fp32) into [co][k = (ky*3+kx)*CINP + ci] bf16 rows of (9*CINP + 8) elements
+static void pack_conv(const float *W, int F, int cin, int cinp, uint16_t *dst)
+{
+    const int ws = 9 * cinp + 8;
+    for (int co = 0; co < F; co++)
+        for (int ci = 0; ci < cin; ci++)
+            for (int ky = 0; ky < 3; ky++)
+                for (int kx = 0; kx < 3; kx++)
+                    dst[(size_t)co * ws + (ky * 3 + kx) * cinp + ci] = f2bf(W[((co * cin + ci) * 3 + ky) * 3 + kx]);
+}
+
+template <int F, int WARPS>
+static size_t smem_resident(int R) { return ImageA<F>::total(R) + (size_t)WARPS * 2 * NPX * (F * 2 + 16); }
+template <int F, int WARPS>
+static size_t smem_streamed(int R)
+{
+    return ImageA<F>::conv_bytes() + (size_t)(1 + 2 * R) * F * 4 + HEAD_FLOATS * 4 + (size_t)WARPS * 2 * NPX * (F * 2 + 16);
+}
+
+#define WARPS_A 8
+#define WARPS_B 6
+
+extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4_net **out)
+{
+    C4_REQUIRE(blob && out, "c4_net_create: null pointer");
+    C4_REQUIRE(n_floats >= 4 && (int)blob[0] == 0xC4B2, "c4_net_create: bad blob magic");
+    const int F = (int)blob[1], R = (int)blob[2], n_fc = (int)blob[3];
+    C4_REQUIRE(F == 32 || F == 64, "c4_net_create: filters must be 32 or 64");
+    C4_REQUIRE(R >= 1 && R <= 16, "c4_net_create: n_residuals out of range");
+    const int64_t expect = 4 + (int64_t)F * 27 + F + (int64_t)2 * R * ((int64_t)F * F * 9 + F) + F + 1 + 42 * 42 + 42 +
+                           42 + 1 + 2 + 2 * F + 2 + 7 * 84 + 7;
+    C4_REQUIRE(n_floats == expect, "c4_net_create: blob size does not match its header");
+    int ndev = 0;
+    C4_CUDA(cudaGetDeviceCount(&ndev));
+    C4_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (there is no CPU fallback)");
+    C4_CUDA(cudaSetDevice(device));
+
+    const size_t total = (F == 32) ? ImageA<32>::total(R) : ImageA<64>::total(R);
+    const size_t stem_b = (F == 32) ? ImageA<32>::stem_bytes() : ImageA<64>::stem_bytes();
+    const size_t conv_b = (F == 32) ? ImageA<32>::conv_bytes() : ImageA<64>::conv_bytes();
+    std::vector<unsigned char> img(total, 0);
+    const float *p = blob + 4;
+    float *bias = reinterpret_cast<float *>(img.data() + stem_b + 2 * R * conv_b);
+    float *hp = bias + (1 + 2 * R) * F;
+    pack_conv(p, F, 3, 16, reinterpret_cast<uint16_t *>(img.data()));
+    p += F * 27;
+    memcpy(bias, p, F * 4);
+    p += F;
+    for (int l = 0; l < 2 * R; l++) {
+        pack_conv(p, F, F, F, reinterpret_cast<uint16_t *>(img.data() + stem_b + l * conv_b));
+        p += (size_t)F * F * 9;
+        memcpy(bias + (1 + l) * F, p, F * 4);
+        p += F;
+    }
+    memcpy(hp + HO_VW, p, F * 4); p += F;
+    hp[HO_VB] = *p++;
+    for (int i = 0; i < 42; i++)
+        for (int j = 0; j < 42; j++) hp[HO_FCT + j * 42 + i] = p[i * 42 + j];
+    p += 42 * 42;
+    memcpy(hp + HO_FCB, p, 42 * 4); p += 42;
+    memcpy(hp + HO_FC1W, p, 42 * 4); p += 42;
+    hp[HO_FC1B] = *p++;
+    hp[HO_W1] = *p++; hp[HO_W2] = *p++;
+    memcpy(hp + HO_PW, p, F * 4); memcpy(hp + HO_PW + F, p + F, F * 4); p += 2 * F;
+    hp[HO_PB] = *p++; hp[HO_PB + 1] = *p++;
+    memcpy(hp + HO_POLW, p, 7 * 84 * 4); p += 7 * 84;
+    memcpy(hp + HO_POLB, p, 7 * 4); p += 7;
+
+    c4_net *net = new c4_net();
+    net->device = device; net->F = F; net->R = R; net->n_fc = n_fc;
+    net->image_bytes = total;
+    net->flops = 2.0 * (42.0 * 27 * F + 2.0 * R * 42 * 9 * F * F + 42.0 * F + (double)n_fc * 42 * 42 + 42 + 42.0 * F * 2 +
+                        84.0 * 7);
+    if (cudaMalloc(&net->image, total) != cudaSuccess) { delete net; c4_set_error("cudaMalloc failed"); return -2; }
+    C4_CUDA(cudaMemcpy(net->image, img.data(), total, cudaMemcpyHostToDevice));
+    if (F == 32) {
+        C4_REQUIRE((smem_resident<32, WARPS_A>(R)) <= 227 * 1024, "c4_net_create: F=32 network too deep for the resident kernel");
+        C4_CUDA(cudaFuncSetAttribute(k_net_resident<32, WARPS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_resident<32, WARPS_A>(R)));
+    } else {
+        C4_CUDA(cudaFuncSetAttribute(k_net_streamed<64, WARPS_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_streamed<64, WARPS_B>(R)));
+    }
+    *out = net;
+    return 0;
+}
+
+extern "C" int c4_net_destroy(c4_net *net)
+{
+    if (!net) return 0;
+    cudaSetDevice(net->device);
+    cudaFree(net->image);
+    delete net;
+    return 0;
+}
+
+extern "C" double c4_net_flops_per_position(const c4_net *net) { return net ? net->flops : 0.0; }
+
+extern "C" int c4_net_forward(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count,
+                              float *out, void *stream)
+{
+    C4_REQUIRE(net && (n == 0 || (c0 && c1 && out)), "c4_net_forward: null pointer");
+    C4_REQUIRE(n >= 0 && n < (1LL << 31), "c4_net_forward: n out of range");
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (net->F == 32) {
+        int grid = (int)std::min<int64_t>(148, (n + WARPS_A - 1) / WARPS_A);
+        k_net_resident<32, WARPS_A><<<grid, WARPS_A * 32, smem_resident<32, WARPS_A>(net->R), s>>>(
+            (const unsigned char *)net->image, (int)net->image_bytes, net->R, (const u64 *)c0, (const u64 *)c1, (int)n,
+            count, out);
+    } else {
+        int grid = (int)std::min<int64_t>(148, (n + WARPS_B - 1) / WARPS_B);
+        k_net_streamed<64, WARPS_B><<<grid, WARPS_B * 32, smem_streamed<64, WARPS_B>(net->R), s>>>(
+            (const unsigned char *)net->image, net->R, (const u64 *)c0, (const u64 *)c1, (int)n, count, out);
+    }
+    C4_CUDA(cudaGetLastError());
+    return 0;
+}

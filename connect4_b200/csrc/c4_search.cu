@@ -1,0 +1,1132 @@
+// c4_search.cu -- warp-per-game MCTS engine: select / expand / evaluate / backup and the self-play state machine.
+//
+// Reference semantics reproduced bit-for-bit (deterministic evaluator): oinkoink/mcts.py:94-202 (search,
+// evaluate_node, select_child, ucb_score, backpropagate, add_exploration_noise, normalise), oinkoink/tree.py:18-147
+// (NodeData.value, best_move, sample_value_fn, get_values_policy), oinkoink/neural/training_game.py:8-19.
+//
+// B200 design (NOT the reference's structure):
+//  * one warp owns one game for the whole kernel; lanes 0..6 are the seven columns.  One descent level = lanes 0..6
+//    each reading their 32-byte child record (two 128-bit loads, two fully used 128-byte lines per level), fp64 PUCT
+//    per lane, warp-shuffle argmax on (score, column).
+//  * children are allocated EAGERLY when a node is evaluated (one 8-slot block), which is observably identical to the
+//    reference's lazy expand-on-second-visit (a node's children cannot be reached before its second visit) but lets
+//    the evaluation result (prior) be scattered straight into the child records.
+//  * boards are not stored per node: the descent replays the moves on the root bitboards held in registers; only the
+//    terminal result of each child is stored (2 bits), computed by the drop + 4-in-a-row test at block creation.
+//  * a game advances until it needs an evaluator answer; pending leaves of all games are compacted into one batch
+//    (atomic slot counter), evaluated by the network kernel (c4_net.cu) or the host, and consumed by the next pass.
+//    Terminal revisits need no evaluator and are played through inside the same pass (bounded by `budget`).
+//  * all PUCT arithmetic uses explicit round-to-nearest intrinsics (__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn) so no
+//    FMA contraction can change the reference's two-rounding  pb_c*prior + value ; log() comes from a host-built
+//    table (glibc, the same libm Python's math.log calls).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "c4_common.cuh"
+
+enum { ST_IDLE = 0, ST_READY = 1, ST_WAIT = 2, ST_DONE = 3, ST_NEWROOT = 4 };
+#define PATH_CAP 48
+#define MAX_PLY 42
+#define FULL 0xffffffffu
+
+struct C4Counters {
+    unsigned long long next_game;       // next local game number to seed
+    unsigned long long games_finished;
+    unsigned long long n_records;
+    unsigned long long n_done;          // stand-alone searches finished
+    unsigned long long overflow;        // records dropped (records_out too small)
+    int leaf_count[2];                  // ping-pong leaf batch counters
+    int pad[2];
+};
+
+struct C4Dev {
+    C4Node *pool;
+    int blocks_per_game;
+    const double *pbc;                  // pbc[N] = log((N + base + 1)/base) + init
+    int sims;
+    double frac, one_minus_frac;
+    float one_minus_frac_f;
+    double alpha;
+    int noise_on;                       // alpha != 0 && frac != 0   (oinkoink/mcts.py:174)
+    int n_sampling;
+    int rng_mode;
+    int rng_record;
+    u64 seed;
+    double *noise;                      // [G][42][7]
+    double *uniform;                    // [G][42]
+    // per game slot
+    u64 *root_c0, *root_c1;
+    int *status, *sims_done, *n_blocks, *pending_node, *pending_slot, *path_len, *ply;
+    u64 *pend_c0, *pend_c1;
+    uint32_t *path;                     // [G][PATH_CAP]
+    long long *game_id;
+    unsigned long long *stat_evals, *stat_positions;
+    c4_record *staging;                 // [G][42]
+    // leaf batch
+    u64 *leaf_c0, *leaf_c1;
+    int *leaf_game;
+    // evaluator answers
+    const float *net_out;               // [G][8] {prior[7], value}
+    const double *ext_value;            // [G]
+    const void *ext_prior;              // [G][7] fp64 or fp32
+    int ext_prior_dtype;
+    // self-play control
+    C4Counters *ctr;
+    long long n_games_target;
+    long long game_id_base, game_id_stride;
+    const u64 *start_c0, *start_c1;
+    c4_record *records_out;
+    long long max_records;
+};
+
+// ------------------------------------------------------------------------------------------------ device pieces
+__device__ __forceinline__ C4NodeA ld_a(const C4Node *n)
+{
+    C4NodeA a;
+    uint4 v = *reinterpret_cast<const uint4 *>(&n->a);
+    a.vsum = __hiloint2double((int)v.y, (int)v.x);
+    a.visits = v.z; a.meta = v.w;
+    return a;
+}
+__device__ __forceinline__ C4NodeB ld_b(const C4Node *n)
+{
+    C4NodeB b;
+    uint4 v = *reinterpret_cast<const uint4 *>(&n->b);
+    b.prior = __hiloint2double((int)v.y, (int)v.x);
+    b.child_block = v.z; b.parent = v.w;
+    return b;
+}
+__device__ __forceinline__ void st_a(C4Node *n, double vsum, uint32_t visits, uint32_t meta)
+{
+    uint4 v;
+    v.x = (uint32_t)__double2loint(vsum); v.y = (uint32_t)__double2hiint(vsum); v.z = visits; v.w = meta;
+    *reinterpret_cast<uint4 *>(&n->a) = v;
+}
+__device__ __forceinline__ void st_b(C4Node *n, double prior, uint32_t child_block, uint32_t parent)
+{
+    uint4 v;
+    v.x = (uint32_t)__double2loint(prior); v.y = (uint32_t)__double2hiint(prior); v.z = child_block; v.w = parent;
+    *reinterpret_cast<uint4 *>(&n->b) = v;
+}
+
+// sequential sum of the 7 per-lane values, left to right from 0.0 (numpy's add.reduce for n < 8)
+__device__ __forceinline__ double seq_sum7(double v)
+{
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) s = __dadd_rn(s, shfl_d(v, i));
+    return s;
+}
+__device__ __forceinline__ float seq_sum7f(float v)
+{
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) s = __fadd_rn(s, __shfl_sync(FULL, v, i));
+    return s;
+}
+
+// gamma(alpha, 1) variate (Marsaglia-Tsang, with the U^(1/alpha) boost for alpha < 1); replaces np.random.gamma of
+// oinkoink/mcts.py:175 -- distributionally, not draw-for-draw (the reference's global MT19937 stream is not
+// reproducible across threads anyway).
+__device__ double c4_gamma(Philox &ph, double alpha)
+{
+    double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+    double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    double x, v, u3, u4;
+    for (int it = 0; it < 64; it++) {
+        uint32_t r[4], q[4];
+        ph.next(r);
+        ph.next(q);
+        double u1 = ph.uniform_from(r[0], r[1]), u2 = ph.uniform_from(r[2], r[3]);
+        u3 = ph.uniform_from(q[0], q[1]);
+        u4 = ph.uniform_from(q[2], q[3]);
+        x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(u3) < 0.5 * x * x + d - d * v + d * log(v)) break;
+    }
+    double g = d * v;
+    if (alpha < 1.0) g *= pow(u4, 1.0 / alpha);
+    return g;
+}
+
+struct Game {
+    C4Node *gp;          // this game's node pool
+    int g;               // slot
+    int lane;
+    int n_blocks;
+    int sims_done;
+    u64 c0, c1;          // root board
+    int age;             // root age
+};
+
+// Evaluate node `node` (board c0,c1 at `age`): store the value, normalise the prior over the legal moves in its own
+// dtype (oinkoink/mcts.py:129-135,197-202), optionally mix root noise (mcts.py:171-181) and create the child block
+// (oinkoink/tree.py:119-132 -- one child per legal move, each with its terminal result).
+// p64 / p32: lane c (<7) holds the raw prior of column c.
+template <bool F32>
+__device__ __forceinline__ void apply_eval(const C4Dev &d, Game &G, uint32_t node, u64 c0, u64 c1, int age, double value,
+                                           double p64, float p32, bool is_root, int ply)
+{
+    const int lane = G.lane;
+    const int legal = c4_legal_mask(c0, c1);
+    const bool mine = lane < 7 && ((legal >> lane) & 1);
+    double p;
+    float pf = 0.f;
+    if (F32) {
+        pf = (lane < 7) ? p32 : 0.f;
+        if (legal != 127 && !mine) pf = 0.f;
+        float s = seq_sum7f(pf);
+        pf = __fdiv_rn(pf, s);
+        p = (double)pf;
+    } else {
+        p = (lane < 7) ? p64 : 0.0;
+        if (legal != 127 && !mine) p = 0.0;
+        double s = seq_sum7(p);
+        p = __ddiv_rn(p, s);
+    }
+    if (is_root && d.noise_on) {
+        double nz = 0.0;
+        if (d.rng_mode == C4_RNG_PHILOX) {
+            if (lane < 7) {
+                Philox ph(d.seed, (u64)d.game_id[G.g], (u64)(ply * 8 + lane));
+                nz = c4_gamma(ph, d.alpha);
+            }
+            if (d.rng_record && d.noise && lane < 7) d.noise[((size_t)G.g * MAX_PLY + ply) * 7 + lane] = nz;
+        } else if (d.rng_mode == C4_RNG_INJECTED) {
+            if (lane < 7) nz = d.noise[((size_t)G.g * MAX_PLY + ply) * 7 + lane];
+        }
+        if (d.rng_mode != C4_RNG_NONE) {
+            __syncwarp();
+            if (legal != 127 && !mine) nz = 0.0;
+            double s = seq_sum7(nz);
+            nz = __ddiv_rn(nz, s);
+            // prior * (1 - frac) + noise * frac ; a float32 prior times the python float stays float32
+            double a = F32 ? (double)__fmul_rn(pf, d.one_minus_frac_f) : __dmul_rn(p, d.one_minus_frac);
+            p = __dadd_rn(a, __dmul_rn(nz, d.frac));
+        }
+    }
+    const uint32_t blk = (uint32_t)G.n_blocks;
+    G.n_blocks++;
+    C4Node *slot = G.gp + (size_t)blk * C4_SLOTS + lane;
+    if (lane < 7) {
+        int res = C4_RES_NONE;
+        if (mine) { u64 a = c0, b = c1; res = c4_drop(a, b, age, lane); }
+        st_a(slot, 0.0, 0u, c4_make_meta(mine, res));
+        st_b(slot, mine ? p : 0.0, 0u, node);
+    } else if (lane == 7) {
+        st_a(slot, value, 0u, 0u);                                    // block header: position value, parent id, #children
+        st_b(slot, 0.0, (uint32_t)__popc(legal), node);
+    }
+    if (lane == 0) {
+        C4Node *n = G.gp + node;
+        st_a(n, __dadd_rn(0.0, value), 1u, C4_META_EXISTS);          // SearchEvaluation(): 0.0 + value, count 1
+        n->b.child_block = blk;
+    }
+    __syncwarp();
+}
+
+// add `value` to the first `count` path nodes (lane i owns path entry i / i+32): oinkoink/mcts.py:164-168
+__device__ __forceinline__ void backup(Game &G, uint32_t path_lo, uint32_t path_hi, int count, double value)
+{
+    if (G.lane < count) {
+        C4Node *n = G.gp + path_lo;
+        C4NodeA a = ld_a(n);
+        st_a(n, __dadd_rn(a.vsum, value), a.visits + 1u, a.meta);
+    }
+    if (G.lane + 32 < count) {
+        C4Node *n = G.gp + path_hi;
+        C4NodeA a = ld_a(n);
+        st_a(n, __dadd_rn(a.vsum, value), a.visits + 1u, a.meta);
+    }
+    __syncwarp();
+}
+
+struct Leaf {
+    uint32_t node;
+    uint32_t meta;
+    u64 c0, c1;
+    int age;
+    int depth;            // number of moves below the root; path has depth+1 entries
+    uint32_t path_lo, path_hi;
+};
+
+// One descent from the root to a leaf: oinkoink/mcts.py:108-116 (the `while node.children` loop plus the
+// expand-then-select step, merged by eager expansion) with select_child / ucb_score (mcts.py:138-161).
+__device__ __forceinline__ Leaf descend(const C4Dev &d, const Game &G)
+{
+    const int lane = G.lane;
+    Leaf L;
+    L.c0 = G.c0; L.c1 = G.c1; L.age = G.age; L.depth = 0;
+    L.path_lo = 0u; L.path_hi = 0u; L.node = 0u;
+    C4NodeA ra = ld_a(G.gp);
+    uint32_t visits = ra.visits, meta = ra.meta;
+    uint32_t child_block = G.gp->b.child_block;
+    while (!(meta & C4_META_TERMINAL) && visits > 0u) {
+        const uint32_t blk = child_block;
+        const C4Node *cn = G.gp + (size_t)blk * C4_SLOTS + (lane & 7);
+        C4NodeA a = ld_a(cn);
+        C4NodeB b = ld_b(cn);
+        const bool exists = (lane < 7) && (a.meta & C4_META_EXISTS);
+        // ucb_score: pb_c = (log((N+base+1)/base)+init) * (sqrt(N)/(n+1)); score = pb_c*prior + value
+        const double pbc = d.pbc[visits];
+        const double sq = __dsqrt_rn((double)visits);
+        double score = -1.0;
+        if (exists) {
+            double pb = __dmul_rn(pbc, __ddiv_rn(sq, (double)(a.visits + 1u)));
+            double ps = __dmul_rn(pb, b.prior);
+            double v;
+            if (a.meta & C4_META_TERMINAL) {
+                double av = c4_meta_value(a.meta);
+                v = (L.age & 1) ? __dsub_rn(1.0, av) : av;
+            } else if (a.visits > 0u) {
+                double av = __ddiv_rn(a.vsum, (double)a.visits);
+                v = (L.age & 1) ? __dsub_rn(1.0, av) : av;
+            } else {
+                v = 0.0;                                   // "position is unknown - assume lost" (tree.py:42-44)
+            }
+            score = __dadd_rn(ps, v);
+        }
+        // argmax over (score, column); equal scores -> highest column (Node.__gt__ on names, tree.py:11-15)
+        int col = lane & 7;
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) {
+            double os = __shfl_xor_sync(FULL, score, off);
+            int oc = __shfl_xor_sync(FULL, col, off);
+            if (os > score || (os == score && oc > col)) { score = os; col = oc; }
+        }
+        col = __shfl_sync(FULL, col, 0);
+        visits = __shfl_sync(FULL, a.visits, col);
+        meta = __shfl_sync(FULL, a.meta, col);
+        child_block = __shfl_sync(FULL, b.child_block, col);
+        // replay the move on the register-resident board
+        u64 bit = 1ULL << c4_drop_bit(L.c0 | L.c1, col);
+        if (L.age & 1) L.c1 |= bit; else L.c0 |= bit;
+        L.age++;
+        L.depth++;
+        uint32_t nid = blk * C4_SLOTS + (uint32_t)col;
+        L.node = nid;
+        if (lane == L.depth) L.path_lo = nid;
+        if (lane + 32 == L.depth) L.path_hi = nid;
+    }
+    L.meta = meta;
+    return L;
+}
+
+// side-relative value and absolute value of root child in lane c (oinkoink/tree.py:27-44, utils.py:33-34)
+__device__ __forceinline__ void child_values(const C4NodeA &a, bool exists, int side, double &v_side, double &v_abs)
+{
+    v_side = 0.0;
+    v_abs = nan("");
+    if (!exists) return;
+    if (a.meta & C4_META_TERMINAL) v_abs = c4_meta_value(a.meta);
+    else if (a.visits > 0u) v_abs = __ddiv_rn(a.vsum, (double)a.visits);
+    else return;
+    v_side = side ? __dsub_rn(1.0, v_abs) : v_abs;
+}
+
+// Tree._normalise_policy (oinkoink/tree.py:139-147) on the per-lane raw policy entries
+__device__ __forceinline__ double normalise_policy(double v, bool exists)
+{
+    double s = seq_sum7(v);
+    unsigned m = __ballot_sync(FULL, exists) & 127u;
+    if (s == 0.0) return exists ? __ddiv_rn(1.0, (double)__popc(m)) : __ddiv_rn(0.0, (double)__popc(m));
+    return __ddiv_rn(v, s);
+}
+
+// argmax of (value, column) over existing children, ties -> highest column (Tree.best_move, tree.py:69-73)
+__device__ __forceinline__ int best_child(double v, bool exists, int lane)
+{
+    double s = exists ? v : -1.0;
+    int col = lane & 7;
+    if (lane >= 7) s = -1.0;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) {
+        double os = __shfl_xor_sync(FULL, s, off);
+        int oc = __shfl_xor_sync(FULL, col, off);
+        if (os > s || (os == s && oc > col)) { s = os; col = oc; }
+    }
+    return __shfl_sync(FULL, col, 0);
+}
+
+// Tree.sample_value_fn(lambda x: x**2) (oinkoink/tree.py:75-82) with np.random.choice's inverse-cdf draw
+__device__ __forceinline__ int sample_child(double v, bool exists, int lane, double u)
+{
+    double w = exists ? __dmul_rn(v, v) : 0.0;
+    if (lane >= 7) w = 0.0;
+    double s = seq_sum7(w);
+    if (!(s > 0.0)) return best_child(v, exists, lane);   // reference raises here (NaN probabilities)
+    double p = __ddiv_rn(w, s);
+    const unsigned m = __ballot_sync(FULL, lane < 7 && exists) & 127u;
+    double cdf = 0.0, mine = 0.0, last = 0.0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        cdf = __dadd_rn(cdf, shfl_d(p, i));
+        if (i == lane) mine = cdf;
+        if ((m >> i) & 1u) last = cdf;
+    }
+    mine = __ddiv_rn(mine, last);
+    unsigned hit = __ballot_sync(FULL, lane < 7 && exists && mine > u) & 127u;
+    if (hit) return __ffs(hit) - 1;
+    return 31 - __clz(m);
+}
+
+__device__ __forceinline__ void emit_request(const C4Dev &d, Game &G, int parity, u64 c0, u64 c1, uint32_t node,
+                                             int path_len, uint32_t path_lo, uint32_t path_hi)
+{
+    int slot = 0;
+    if (G.lane == 0) slot = atomicAdd(&d.ctr->leaf_count[parity], 1);
+    slot = __shfl_sync(FULL, slot, 0);
+    if (G.lane == 0) {
+        d.leaf_c0[slot] = c0; d.leaf_c1[slot] = c1; d.leaf_game[slot] = G.g;
+        d.pend_c0[G.g] = c0; d.pend_c1[G.g] = c1;
+        d.pending_node[G.g] = (int)node; d.pending_slot[G.g] = slot; d.path_len[G.g] = path_len;
+        d.stat_evals[G.g] += 1ULL;
+    }
+    if (G.lane < path_len) d.path[(size_t)G.g * PATH_CAP + G.lane] = path_lo;
+    if (G.lane + 32 < path_len) d.path[(size_t)G.g * PATH_CAP + G.lane + 32] = path_hi;
+}
+
+// End of a search inside a self-play game: pick the move, log the position, play it, finish / re-seed the game.
+// oinkoink/mcts.py:78-88 (MCTS.make_move) + neural/training_game.py:8-19 (training_game).  Returns the new status.
+__device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
+{
+    const int lane = G.lane;
+    const int side = G.age & 1;
+    const uint32_t blk = G.gp->b.child_block;
+    C4NodeA a = ld_a(G.gp + (size_t)blk * C4_SLOTS + (lane & 7));
+    const bool exists = lane < 7 && (a.meta & C4_META_EXISTS);
+    double v_side, v_abs;
+    child_values(a, exists, side, v_side, v_abs);
+    double pol = normalise_policy(lane < 7 ? v_side : 0.0, exists);
+    int ply = d.ply[G.g];
+    int mv;
+    if (G.age < d.n_sampling && d.rng_mode != C4_RNG_NONE) {
+        double u;
+        if (d.rng_mode == C4_RNG_PHILOX) {
+            Philox ph(d.seed, (u64)d.game_id[G.g], (u64)(ply * 8 + 7));
+            uint32_t r[4];
+            ph.next(r);
+            u = ph.uniform_from(r[0], r[1]);
+            if (d.rng_record && d.uniform && lane == 0) d.uniform[(size_t)G.g * MAX_PLY + ply] = u;
+        } else {
+            u = d.uniform[(size_t)G.g * MAX_PLY + ply];
+        }
+        mv = sample_child(v_side, exists, lane, u);
+    } else {
+        mv = best_child(v_side, exists, lane);
+    }
+    double mv_abs = shfl_d(v_abs, mv);
+    c4_record *rec = d.staging + (size_t)G.g * MAX_PLY + ply;
+    if (lane < 7) rec->policy[lane] = (float)pol;
+    if (lane == 0) {
+        rec->c0 = G.c0; rec->c1 = G.c1;
+        rec->result_value = 0.f;
+        rec->search_value = (float)mv_abs;
+        rec->game_id = (int32_t)d.game_id[G.g];
+        rec->move = (int8_t)mv; rec->ply = (int8_t)ply; rec->n_moves = 0; rec->result = C4_RES_NONE;
+        d.stat_positions[G.g] += 1ULL;
+    }
+    int res = c4_drop(G.c0, G.c1, G.age, mv);
+    G.age++;
+    ply++;
+    __syncwarp();
+    if (res == C4_RES_NONE) {
+        if (lane == 0) d.ply[G.g] = ply;
+        return ST_NEWROOT;
+    }
+    // game over: flush the staged records with the final result, then re-seed the slot
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&d.ctr->n_records, (unsigned long long)ply);
+    base = shfl_u64(base, 0);
+    if (d.records_out) {
+        if ((long long)(base + ply) <= d.max_records) {
+            for (int r = lane; r < ply; r += 32) {
+                c4_record t = d.staging[(size_t)G.g * MAX_PLY + r];
+                t.result_value = (float)(res * 0.5);
+                t.n_moves = (int8_t)ply;
+                t.result = (int8_t)res;
+                d.records_out[base + r] = t;
+            }
+        } else if (lane == 0) {
+            atomicAdd(&d.ctr->overflow, 1ULL);
+        }
+    }
+    unsigned long long nxt = 0;
+    if (lane == 0) {
+        atomicAdd(&d.ctr->games_finished, 1ULL);
+        nxt = atomicAdd(&d.ctr->next_game, 1ULL);
+    }
+    nxt = shfl_u64(nxt, 0);
+    if ((long long)nxt >= d.n_games_target) return ST_IDLE;
+    G.c0 = d.start_c0 ? d.start_c0[nxt] : 0ULL;
+    G.c1 = d.start_c1 ? d.start_c1[nxt] : 0ULL;
+    G.age = c4_age(G.c0, G.c1);
+    if (lane == 0) {
+        d.game_id[G.g] = d.game_id_base + (long long)nxt * d.game_id_stride;
+        d.ply[G.g] = 0;
+    }
+    __syncwarp();
+    return ST_NEWROOT;
+}
+
+// ------------------------------------------------------------------------------------------------ the pass kernel
+// MODE: C4_EVAL_EXTERNAL / C4_EVAL_CENTRE / C4_EVAL_NET.  One warp per game slot.
+template <int MODE, bool SELFPLAY>
+__global__ void __launch_bounds__(128) k_advance(C4Dev d, int n_games, int parity, int budget)
+{
+    const int g = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.ctr->leaf_count[parity ^ 1] = 0;
+    if (g >= n_games) return;
+    int st = d.status[g];
+    if (st == ST_IDLE || st == ST_DONE) return;
+
+    Game G;
+    G.g = g; G.lane = lane;
+    G.gp = d.pool + (size_t)g * d.blocks_per_game * C4_SLOTS;
+    G.n_blocks = d.n_blocks[g];
+    G.sims_done = d.sims_done[g];
+    G.c0 = d.root_c0[g]; G.c1 = d.root_c1[g];
+    G.age = c4_age(G.c0, G.c1);
+
+    if (st == ST_WAIT) {
+        // consume the evaluator's answer for the pending leaf (oinkoink/mcts.py:129-135), then backpropagate
+        const int slot = d.pending_slot[g];
+        const uint32_t node = (uint32_t)d.pending_node[g];
+        const int plen = d.path_len[g];
+        const u64 lc0 = d.pend_c0[g], lc1 = d.pend_c1[g];
+        const int lage = c4_age(lc0, lc1);
+        const bool is_root = (plen == 0);
+        const int ply = SELFPLAY ? d.ply[g] : 0;
+        if (MODE == C4_EVAL_NET) {
+            const float *o = d.net_out + (size_t)slot * 8;
+            float pf = (lane < 7) ? o[lane] : 0.f;
+            double value = (double)o[7];
+            apply_eval<true>(d, G, node, lc0, lc1, lage, value, 0.0, pf, is_root, ply);
+            if (!is_root) {
+                uint32_t plo = (lane < plen) ? d.path[(size_t)g * PATH_CAP + lane] : 0u;
+                uint32_t phi = (lane + 32 < plen) ? d.path[(size_t)g * PATH_CAP + lane + 32] : 0u;
+                backup(G, plo, phi, plen - 1, value);
+                G.sims_done++;
+            }
+        } else if (MODE == C4_EVAL_EXTERNAL) {
+            double value = d.ext_value[slot];
+            if (d.ext_prior_dtype == 1) {
+                float pf = (lane < 7) ? ((const float *)d.ext_prior)[(size_t)slot * 7 + lane] : 0.f;
+                apply_eval<true>(d, G, node, lc0, lc1, lage, value, 0.0, pf, is_root, ply);
+            } else {
+                double p = (lane < 7) ? ((const double *)d.ext_prior)[(size_t)slot * 7 + lane] : 0.0;
+                apply_eval<false>(d, G, node, lc0, lc1, lage, value, p, 0.f, is_root, ply);
+            }
+            if (!is_root) {
+                uint32_t plo = (lane < plen) ? d.path[(size_t)g * PATH_CAP + lane] : 0u;
+                uint32_t phi = (lane + 32 < plen) ? d.path[(size_t)g * PATH_CAP + lane + 32] : 0u;
+                backup(G, plo, phi, plen - 1, value);
+                G.sims_done++;
+            }
+        }
+        st = ST_READY;
+    }
+
+    for (;;) {
+        if (st == ST_NEWROOT) {
+            // Tree(board) + evaluate root (oinkoink/mcts.py:98-105): fresh pool, root = node 0 of block 0
+            G.n_blocks = 1;
+            G.sims_done = 0;
+            if (lane == 0) { st_a(G.gp, 0.0, 0u, C4_META_EXISTS); st_b(G.gp, 0.0, 0u, 0u); }
+            __syncwarp();
+            if (MODE == C4_EVAL_CENTRE) {
+                const int ply = SELFPLAY ? d.ply[g] : 0;
+                apply_eval<false>(d, G, 0u, G.c0, G.c1, G.age, c4_evaluate_centre(G.c0, G.c1), __ddiv_rn(1.0, 7.0),
+                                  0.f, true, ply);
+                if (lane == 0) d.stat_evals[g] += 1ULL;
+                st = ST_READY;
+            } else {
+                emit_request(d, G, parity, G.c0, G.c1, 0u, 0, 0u, 0u);
+                st = ST_WAIT;
+                break;
+            }
+        }
+        if (G.sims_done >= d.sims) {
+            if (!SELFPLAY) {
+                st = ST_DONE;
+                if (lane == 0) atomicAdd(&d.ctr->n_done, 1ULL);
+                break;
+            }
+            st = finalize_move(d, G);
+            if (st == ST_IDLE) break;
+            continue;
+        }
+        if (budget-- <= 0) break;
+        Leaf L = descend(d, G);
+        if (L.meta & C4_META_TERMINAL) {
+            // terminal branch of evaluate_node (mcts.py:125-128) + backpropagate: leaf and all ancestors get the result
+            backup(G, L.path_lo, L.path_hi, L.depth + 1, c4_meta_value(L.meta));
+            G.sims_done++;
+            continue;
+        }
+        if (MODE == C4_EVAL_CENTRE) {
+            double value = c4_evaluate_centre(L.c0, L.c1);
+            apply_eval<false>(d, G, L.node, L.c0, L.c1, L.age, value, __ddiv_rn(1.0, 7.0), 0.f, false, 0);
+            backup(G, L.path_lo, L.path_hi, L.depth, value);
+            if (lane == 0) d.stat_evals[g] += 1ULL;
+            G.sims_done++;
+            continue;
+        }
+        emit_request(d, G, parity, L.c0, L.c1, L.node, L.depth + 1, L.path_lo, L.path_hi);
+        st = ST_WAIT;
+        break;
+    }
+    if (lane == 0) {
+        d.status[g] = st;
+        d.n_blocks[g] = G.n_blocks;
+        d.sims_done[g] = G.sims_done;
+        d.root_c0[g] = G.c0; d.root_c1[g] = G.c1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+__global__ void k_search_begin(C4Dev d, const u64 *c0, const u64 *c1, int n, int max_games)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) {
+        d.ctr->leaf_count[0] = 0; d.ctr->leaf_count[1] = 0;
+        d.ctr->n_done = 0;
+    }
+    if (g >= max_games) return;
+    if (g < n) {
+        d.root_c0[g] = c0[g]; d.root_c1[g] = c1[g];
+        d.status[g] = ST_NEWROOT;
+        d.game_id[g] = g;
+    } else {
+        d.status[g] = ST_IDLE;
+    }
+    d.sims_done[g] = 0; d.n_blocks[g] = 1; d.ply[g] = 0; d.path_len[g] = 0;
+}
+
+__global__ void k_selfplay_init(C4Dev d, int max_games)
+{
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) {
+        d.ctr->leaf_count[0] = 0; d.ctr->leaf_count[1] = 0;
+        d.ctr->games_finished = 0; d.ctr->n_records = 0; d.ctr->overflow = 0; d.ctr->n_done = 0;
+        long long first = d.n_games_target < (long long)max_games ? d.n_games_target : (long long)max_games;
+        d.ctr->next_game = (unsigned long long)first;
+    }
+    if (g >= max_games) return;
+    d.sims_done[g] = 0; d.n_blocks[g] = 1; d.ply[g] = 0; d.path_len[g] = 0;
+    d.stat_evals[g] = 0; d.stat_positions[g] = 0;
+    if ((long long)g < d.n_games_target) {
+        d.root_c0[g] = d.start_c0 ? d.start_c0[g] : 0ULL;
+        d.root_c1[g] = d.start_c1 ? d.start_c1[g] : 0ULL;
+        d.game_id[g] = d.game_id_base + (long long)g * d.game_id_stride;
+        d.status[g] = ST_NEWROOT;
+    } else {
+        d.status[g] = ST_IDLE;
+    }
+}
+
+// root read-out: one warp per game (Tree.get_values_policy / get_visit_count_policy / best_move + reference node count)
+__global__ void k_readout(C4Dev d, int n, int32_t *visits, double *value_sum, int8_t *child_result,
+                          int32_t *root_visits, double *root_value_sum, double *root_prior, double *values_policy,
+                          double *visit_policy, int8_t *best_move, double *best_value, int32_t *n_nodes)
+{
+    const int g = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= n) return;
+    C4Node *gp = d.pool + (size_t)g * d.blocks_per_game * C4_SLOTS;
+    const u64 c0 = d.root_c0[g], c1 = d.root_c1[g];
+    const int side = c4_age(c0, c1) & 1;
+    C4NodeA ra = ld_a(gp);
+    const uint32_t blk = gp->b.child_block;
+    C4NodeA a; a.vsum = 0.0; a.visits = 0; a.meta = 0;
+    C4NodeB b; b.prior = 0.0; b.child_block = 0; b.parent = 0;
+    if (blk != 0u) { a = ld_a(gp + (size_t)blk * C4_SLOTS + (lane & 7)); b = ld_b(gp + (size_t)blk * C4_SLOTS + (lane & 7)); }
+    const bool exists = lane < 7 && (a.meta & C4_META_EXISTS);
+    // the reference creates the root's children during the first simulation only
+    const bool expanded = ra.visits >= 2u;
+    const bool ex = exists && expanded;
+    double v_side, v_abs;
+    child_values(a, ex, side, v_side, v_abs);
+    double vp = normalise_policy(lane < 7 ? v_side : 0.0, ex);
+    double cnt = (ex && a.visits > 0u) ? (double)a.visits : 0.0;
+    double cp = normalise_policy(lane < 7 ? cnt : 0.0, ex);
+    int bm = best_child(v_side, ex, lane);
+    double bv = shfl_d(v_abs, bm);
+    if (lane < 7) {
+        size_t o = (size_t)g * 7 + lane;
+        if (visits) visits[o] = ex ? (int32_t)a.visits : 0;
+        if (value_sum) value_sum[o] = ex ? a.vsum : 0.0;
+        if (child_result) child_result[o] = ex ? (int8_t)c4_meta_result(a.meta) : (int8_t)-2;
+        if (root_prior) root_prior[o] = exists ? b.prior : 0.0;
+        if (values_policy) values_policy[o] = vp;
+        if (visit_policy) visit_policy[o] = cp;
+    }
+    if (lane == 0) {
+        if (root_visits) root_visits[g] = (int32_t)ra.visits;
+        if (root_value_sum) root_value_sum[g] = ra.vsum;
+        if (best_move) best_move[g] = expanded ? (int8_t)bm : (int8_t)-1;
+        if (best_value) best_value[g] = bv;
+    }
+    if (n_nodes) {
+        // nodes of the reference's lazily expanded tree: root + children of every node visited at least twice
+        int nb = d.n_blocks[g], total = 0;
+        for (int bI = 1 + lane; bI < nb; bI += 32) {
+            C4NodeB h = ld_b(gp + (size_t)bI * C4_SLOTS + 7);
+            C4NodeA pa = ld_a(gp + h.parent);
+            if (pa.visits >= 2u) total += (int)h.child_block;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) total += __shfl_xor_sync(FULL, total, off);
+        if (lane == 0) n_nodes[g] = total + 1;
+    }
+}
+
+__global__ void k_sum_stats(const unsigned long long *evals, const unsigned long long *positions, int n,
+                            unsigned long long *out)
+{
+    unsigned long long e = 0, p = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { e += evals[i]; p += positions[i]; }
+    __shared__ unsigned long long se[256], sp[256];
+    se[threadIdx.x] = e; sp[threadIdx.x] = p;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { se[threadIdx.x] += se[threadIdx.x + s]; sp[threadIdx.x] += sp[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = se[0]; out[1] = sp[0]; }
+}
+
+// generation sink: native_to_pytorch(add_fliplr=True) (oinkoink/neural/pytorch/data.py:78-105); one thread per
+// output float of the board planes, originals first then mirrors.
+__global__ void k_augment_pack(const c4_record *__restrict__ rec, long long n, float *__restrict__ boards,
+                               float *__restrict__ values, float *__restrict__ priors)
+{
+    const long long total = 2 * n * 126;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long row = e / 126;
+        int k = (int)(e - row * 126);
+        bool flip = row >= n;
+        const c4_record &r = rec[flip ? row - n : row];
+        u64 a = r.c0, b = r.c1;
+        if (flip) { a = c4_fliplr(a); b = c4_fliplr(b); }
+        int ch = k / 42, px = k - ch * 42, rr = px / 7, c = px - rr * 7;
+        int bit = 7 * c + (5 - rr);
+        float v;
+        if (ch == 0) v = ((__popcll(a | b) & 1) == 0) ? 1.f : 0.f;
+        else v = (float)(((ch == 1 ? a : b) >> bit) & 1ULL);
+        boards[e] = v;
+        if (k < 7) priors[row * 7 + k] = flip ? r.policy[6 - k] : r.policy[k];
+        if (k == 7) values[row] = r.result_value;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct c4_ctx {
+    int device;
+    int max_games;
+    int sims_cap;
+    c4_mcts_config cfg;
+    C4Dev d;
+    c4_net *net;
+    std::vector<void *> allocs;
+    double *pbc_dev;
+    float *net_out;
+    double *ext_value;
+    void *ext_prior;
+    unsigned long long *stats_dev;      // [2]
+    unsigned long long *pinned;         // host pinned scratch (8 words)
+    int parity;
+    int n_search;                       // searches started by the last c4_search_begin
+    int budget_net;                     // terminal re-visits a game may play through per pass (NET / EXTERNAL)
+    int last_pending;
+    bool supplied;
+    bool pool_fresh;                    // bench pool initialised
+    cudaEvent_t ev0, ev1, evn0, evn1;
+};
+
+template <typename T>
+static int dev_alloc(c4_ctx *ctx, T **p, size_t n)
+{
+    void *q = nullptr;
+    C4_CUDA(cudaMalloc(&q, n * sizeof(T)));
+    C4_CUDA(cudaMemset(q, 0, n * sizeof(T)));
+    ctx->allocs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+
+static int upload_config(c4_ctx *ctx, const c4_mcts_config *cfg)
+{
+    C4_REQUIRE(cfg->simulations >= 0 && cfg->simulations <= ctx->sims_cap, "simulations exceeds the context capacity");
+    C4_REQUIRE(cfg->pb_c_base > 0, "pb_c_base must be positive");
+    ctx->cfg = *cfg;
+    std::vector<double> t(ctx->sims_cap + 2);
+    for (int n = 0; n < (int)t.size(); n++)                    // oinkoink/mcts.py:150-152, host libm log
+        t[n] = log(((double)n + cfg->pb_c_base + 1.0) / cfg->pb_c_base) + cfg->pb_c_init;
+    C4_CUDA(cudaMemcpy(ctx->pbc_dev, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->d.sims = cfg->simulations;
+    ctx->d.alpha = cfg->root_dirichlet_alpha;
+    ctx->d.frac = cfg->root_exploration_fraction;
+    ctx->d.one_minus_frac = 1.0 - cfg->root_exploration_fraction;
+    ctx->d.one_minus_frac_f = (float)(1.0 - cfg->root_exploration_fraction);
+    ctx->d.noise_on = (cfg->root_dirichlet_alpha != 0.0 && cfg->root_exploration_fraction != 0.0) ? 1 : 0;
+    ctx->d.n_sampling = cfg->num_sampling_moves;
+    return 0;
+}
+
+extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config *cfg, c4_ctx **out)
+{
+    C4_REQUIRE(out && cfg, "c4_ctx_create: null pointer");
+    C4_REQUIRE(max_games > 0 && max_games <= (1 << 20), "max_games out of range");
+    C4_REQUIRE(cfg->simulations >= 0 && cfg->simulations <= (1 << 20), "simulations out of range");
+    int ndev = 0;
+    C4_CUDA(cudaGetDeviceCount(&ndev));
+    C4_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (there is no CPU fallback)");
+    C4_CUDA(cudaSetDevice(device));
+    c4_ctx *ctx = new c4_ctx();
+    ctx->device = device;
+    ctx->max_games = max_games;
+    ctx->sims_cap = cfg->simulations;
+    ctx->net = nullptr;
+    ctx->parity = 0;
+    ctx->n_search = 0;
+    ctx->budget_net = getenv("C4_BUDGET") ? atoi(getenv("C4_BUDGET")) : 8;
+    ctx->last_pending = 0;
+    ctx->supplied = true;
+    ctx->pool_fresh = false;
+    memset(&ctx->d, 0, sizeof(ctx->d));
+    C4Dev &d = ctx->d;
+    const size_t G = (size_t)max_games;
+    d.blocks_per_game = cfg->simulations + 2;
+    int rc = 0;
+#define A(ptr, n) if ((rc = dev_alloc(ctx, &(ptr), (n))) != 0) { c4_ctx_destroy(ctx); return rc; }
+    A(d.pool, G * d.blocks_per_game * C4_SLOTS);
+    A(ctx->pbc_dev, (size_t)cfg->simulations + 2);
+    d.pbc = ctx->pbc_dev;
+    A(d.root_c0, G); A(d.root_c1, G); A(d.status, G); A(d.sims_done, G); A(d.n_blocks, G);
+    A(d.pending_node, G); A(d.pending_slot, G); A(d.path_len, G); A(d.ply, G);
+    A(d.pend_c0, G); A(d.pend_c1, G); A(d.path, G * PATH_CAP); A(d.game_id, G);
+    A(d.stat_evals, G); A(d.stat_positions, G); A(d.staging, G * MAX_PLY);
+    A(d.leaf_c0, G); A(d.leaf_c1, G); A(d.leaf_game, G);
+    A(ctx->net_out, G * 8); A(ctx->ext_value, G);
+    double *extp = nullptr;
+    A(extp, G * 7);
+    ctx->ext_prior = extp;
+    A(d.ctr, 1); A(ctx->stats_dev, 2);
+#undef A
+    d.net_out = ctx->net_out;
+    d.ext_value = ctx->ext_value;
+    d.ext_prior = ctx->ext_prior;
+    d.rng_mode = C4_RNG_NONE;
+    if (cudaMallocHost((void **)&ctx->pinned, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+        c4_set_error("cudaMallocHost failed");
+        c4_ctx_destroy(ctx);
+        return -2;
+    }
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evn0); cudaEventCreate(&ctx->evn1);
+    rc = upload_config(ctx, cfg);
+    if (rc) { c4_ctx_destroy(ctx); return rc; }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int c4_ctx_destroy(c4_ctx *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1); }
+    delete ctx;
+    return 0;
+}
+
+extern "C" int c4_ctx_set_config(c4_ctx *ctx, const c4_mcts_config *cfg)
+{
+    C4_REQUIRE(ctx && cfg, "c4_ctx_set_config: null pointer");
+    C4_CUDA(cudaSetDevice(ctx->device));
+    return upload_config(ctx, cfg);
+}
+
+extern "C" int c4_ctx_set_net(c4_ctx *ctx, c4_net *net)
+{
+    C4_REQUIRE(ctx, "c4_ctx_set_net: null context");
+    ctx->net = net;
+    return 0;
+}
+
+extern "C" int c4_ctx_set_rng(c4_ctx *ctx, int mode, uint64_t seed, double *noise, double *uniform, int record)
+{
+    C4_REQUIRE(ctx, "c4_ctx_set_rng: null context");
+    C4_REQUIRE(mode >= 0 && mode <= 2, "rng mode must be 0 (none), 1 (philox) or 2 (injected)");
+    C4_REQUIRE(mode != C4_RNG_INJECTED || (noise && uniform), "injected rng needs noise and uniform buffers");
+    C4_REQUIRE(!record || (noise && uniform), "recording needs noise and uniform buffers");
+    ctx->d.rng_mode = mode; ctx->d.seed = seed; ctx->d.noise = noise; ctx->d.uniform = uniform;
+    ctx->d.rng_record = record;
+    return 0;
+}
+
+template <bool SP>
+static int launch_advance(c4_ctx *ctx, int mode, int n_games, int budget, cudaStream_t s)
+{
+    ctx->parity ^= 1;
+    const int threads = 128, wpb = threads / 32;
+    const int blocks = (n_games + wpb - 1) / wpb;
+    switch (mode) {
+    case C4_EVAL_EXTERNAL: k_advance<C4_EVAL_EXTERNAL, SP><<<blocks, threads, 0, s>>>(ctx->d, n_games, ctx->parity, budget); break;
+    case C4_EVAL_CENTRE: k_advance<C4_EVAL_CENTRE, SP><<<blocks, threads, 0, s>>>(ctx->d, n_games, ctx->parity, budget); break;
+    case C4_EVAL_NET: k_advance<C4_EVAL_NET, SP><<<blocks, threads, 0, s>>>(ctx->d, n_games, ctx->parity, budget); break;
+    default: c4_set_error("bad eval kind"); return -1;
+    }
+    C4_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int run_net(c4_ctx *ctx, cudaStream_t s)
+{
+    return c4_net_forward(ctx->net, (const uint64_t *)ctx->d.leaf_c0, (const uint64_t *)ctx->d.leaf_c1, ctx->max_games,
+                          &ctx->d.ctr->leaf_count[ctx->parity], ctx->net_out, s);
+}
+
+extern "C" int c4_search_begin(c4_ctx *ctx, const uint64_t *c0, const uint64_t *c1, int32_t n, void *stream)
+{
+    C4_REQUIRE(ctx && c0 && c1, "c4_search_begin: null pointer");
+    C4_REQUIRE(n >= 0 && n <= ctx->max_games, "c4_search_begin: n exceeds max_games");
+    C4_CUDA(cudaSetDevice(ctx->device));
+    ctx->d.n_games_target = 0;
+    ctx->d.records_out = nullptr;
+    ctx->pool_fresh = false;
+    k_search_begin<<<(ctx->max_games + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d, (const u64 *)c0,
+                                                                                   (const u64 *)c1, n, ctx->max_games);
+    C4_CUDA(cudaGetLastError());
+    ctx->parity = 0;
+    ctx->n_search = n;
+    ctx->last_pending = 0;
+    ctx->supplied = true;
+    return 0;
+}
+
+extern "C" int c4_search_pending(c4_ctx *ctx, uint64_t *leaf_c0, uint64_t *leaf_c1, int32_t *leaf_game,
+                                 int32_t *n_pending, void *stream)
+{
+    C4_REQUIRE(ctx && n_pending, "c4_search_pending: null pointer");
+    C4_REQUIRE(ctx->supplied || ctx->last_pending == 0, "c4_search_pending: previous leaves were not supplied");
+    cudaStream_t s = (cudaStream_t)stream;
+    C4_CUDA(cudaSetDevice(ctx->device));
+    int rc = launch_advance<false>(ctx, C4_EVAL_EXTERNAL, ctx->max_games, 0x7fffffff, s);
+    if (rc) return rc;
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned, &ctx->d.ctr->leaf_count[ctx->parity], sizeof(int), cudaMemcpyDeviceToHost, s));
+    C4_CUDA(cudaStreamSynchronize(s));
+    int m = *(int *)ctx->pinned;
+    if (m > 0) {
+        if (leaf_c0) C4_CUDA(cudaMemcpyAsync(leaf_c0, ctx->d.leaf_c0, m * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        if (leaf_c1) C4_CUDA(cudaMemcpyAsync(leaf_c1, ctx->d.leaf_c1, m * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        if (leaf_game) C4_CUDA(cudaMemcpyAsync(leaf_game, ctx->d.leaf_game, m * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    }
+    *n_pending = m;
+    ctx->last_pending = m;
+    ctx->supplied = (m == 0);
+    return 0;
+}
+
+extern "C" int c4_search_supply(c4_ctx *ctx, const double *value, const void *prior, int prior_dtype, int32_t m,
+                                void *stream)
+{
+    C4_REQUIRE(ctx && value && prior, "c4_search_supply: null pointer");
+    C4_REQUIRE(m == ctx->last_pending, "c4_search_supply: m must equal the last pending count");
+    C4_REQUIRE(prior_dtype == 0 || prior_dtype == 1, "prior_dtype must be 0 (fp64) or 1 (fp32)");
+    cudaStream_t s = (cudaStream_t)stream;
+    C4_CUDA(cudaSetDevice(ctx->device));
+    C4_CUDA(cudaMemcpyAsync(ctx->ext_value, value, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    C4_CUDA(cudaMemcpyAsync(ctx->ext_prior, prior, (size_t)m * 7 * (prior_dtype ? 4 : 8), cudaMemcpyDeviceToDevice, s));
+    ctx->d.ext_prior_dtype = prior_dtype;
+    ctx->supplied = true;
+    return 0;
+}
+
+static int read_counters(c4_ctx *ctx, C4Counters *host, cudaStream_t s)
+{
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned, ctx->d.ctr, sizeof(C4Counters), cudaMemcpyDeviceToHost, s));
+    C4_CUDA(cudaStreamSynchronize(s));
+    memcpy(host, ctx->pinned, sizeof(C4Counters));
+    return 0;
+}
+
+extern "C" int c4_search_run(c4_ctx *ctx, int eval_kind, void *stream)
+{
+    C4_REQUIRE(ctx, "c4_search_run: null context");
+    C4_REQUIRE(eval_kind == C4_EVAL_CENTRE || eval_kind == C4_EVAL_NET, "c4_search_run: eval_kind must be CENTRE or NET");
+    C4_REQUIRE(eval_kind != C4_EVAL_NET || ctx->net, "c4_search_run: no network attached (c4_ctx_set_net)");
+    cudaStream_t s = (cudaStream_t)stream;
+    C4_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if (eval_kind == C4_EVAL_CENTRE) {
+        // the whole search of every game in one launch: evaluator fused into the tree kernel
+        if ((rc = launch_advance<false>(ctx, C4_EVAL_CENTRE, ctx->max_games, 0x7fffffff, s))) return rc;
+        C4_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    }
+    const int chunk = 32;
+    for (long long it = 0;; it++) {
+        for (int k = 0; k < chunk; k++) {
+            if ((rc = launch_advance<false>(ctx, C4_EVAL_NET, ctx->max_games, ctx->budget_net, s))) return rc;
+            if ((rc = run_net(ctx, s))) return rc;
+        }
+        C4Counters c;
+        if ((rc = read_counters(ctx, &c, s))) return rc;
+        if ((long long)c.n_done >= ctx->n_search) break;
+        C4_REQUIRE(it < (1 << 20), "c4_search_run: did not terminate");
+    }
+    return 0;
+}
+
+extern "C" int c4_search_readout(c4_ctx *ctx, int32_t n, int32_t *visits, double *value_sum, int8_t *child_result,
+                                 int32_t *root_visits, double *root_value_sum, double *root_prior,
+                                 double *values_policy, double *visit_policy, int8_t *best_move, double *best_value,
+                                 int32_t *n_nodes, void *stream)
+{
+    C4_REQUIRE(ctx, "c4_search_readout: null context");
+    C4_REQUIRE(n >= 0 && n <= ctx->max_games, "c4_search_readout: n exceeds max_games");
+    if (n == 0) return 0;
+    C4_CUDA(cudaSetDevice(ctx->device));
+    k_readout<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(ctx->d, n, visits, value_sum, child_result, root_visits,
+                                                            root_value_sum, root_prior, values_policy, visit_policy,
+                                                            best_move, best_value, n_nodes);
+    C4_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int c4_search_export_tree(c4_ctx *ctx, int32_t game, void *nodes_out, int64_t capacity_slots,
+                                     int64_t *n_slots, void *stream)
+{
+    C4_REQUIRE(ctx && nodes_out && n_slots, "c4_search_export_tree: null pointer");
+    C4_REQUIRE(game >= 0 && game < ctx->max_games, "c4_search_export_tree: bad game index");
+    cudaStream_t s = (cudaStream_t)stream;
+    C4_CUDA(cudaSetDevice(ctx->device));
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned, ctx->d.n_blocks + game, sizeof(int), cudaMemcpyDeviceToHost, s));
+    C4_CUDA(cudaStreamSynchronize(s));
+    int64_t slots = (int64_t)(*(int *)ctx->pinned) * C4_SLOTS;
+    C4_REQUIRE(slots <= capacity_slots, "c4_search_export_tree: output buffer too small");
+    C4_CUDA(cudaMemcpyAsync(nodes_out, ctx->d.pool + (size_t)game * ctx->d.blocks_per_game * C4_SLOTS,
+                            (size_t)slots * sizeof(C4Node), cudaMemcpyDeviceToHost, s));
+    C4_CUDA(cudaStreamSynchronize(s));
+    *n_slots = slots;
+    return 0;
+}
+
+static int selfplay_passes(c4_ctx *ctx, int eval_kind, int n_passes, cudaStream_t s)
+{
+    int rc;
+    for (int k = 0; k < n_passes; k++) {
+        if (eval_kind == C4_EVAL_CENTRE) {
+            if ((rc = launch_advance<true>(ctx, C4_EVAL_CENTRE, ctx->max_games, 512, s))) return rc;
+        } else {
+            if ((rc = launch_advance<true>(ctx, C4_EVAL_NET, ctx->max_games, ctx->budget_net, s))) return rc;
+            if ((rc = run_net(ctx, s))) return rc;
+        }
+    }
+    return 0;
+}
+
+extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int64_t game_id_base,
+                               int64_t game_id_stride, const uint64_t *start_c0, const uint64_t *start_c1,
+                               c4_record *records_out, int64_t max_records, int64_t *n_records_out, void *stream)
+{
+    C4_REQUIRE(ctx && records_out && n_records_out, "c4_selfplay_run: null pointer");
+    C4_REQUIRE(eval_kind == C4_EVAL_CENTRE || eval_kind == C4_EVAL_NET, "c4_selfplay_run: eval_kind must be CENTRE or NET");
+    C4_REQUIRE(eval_kind != C4_EVAL_NET || ctx->net, "c4_selfplay_run: no network attached (c4_ctx_set_net)");
+    C4_REQUIRE(n_games >= 0 && max_records >= 0, "c4_selfplay_run: negative size");
+    cudaStream_t s = (cudaStream_t)stream;
+    C4_CUDA(cudaSetDevice(ctx->device));
+    C4Dev &d = ctx->d;
+    d.n_games_target = n_games;
+    d.game_id_base = game_id_base; d.game_id_stride = game_id_stride;
+    d.start_c0 = (const u64 *)start_c0; d.start_c1 = (const u64 *)start_c1;
+    d.records_out = records_out; d.max_records = max_records;
+    ctx->pool_fresh = false;
+    k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
+    C4_CUDA(cudaGetLastError());
+    ctx->parity = 0;
+    int rc;
+    C4Counters c;
+    for (long long it = 0;; it++) {
+        if ((rc = selfplay_passes(ctx, eval_kind, 64, s))) return rc;
+        if ((rc = read_counters(ctx, &c, s))) return rc;
+        if ((long long)c.games_finished >= n_games) break;
+        C4_REQUIRE(it < (1LL << 24), "c4_selfplay_run: did not terminate");
+    }
+    C4_REQUIRE(c.overflow == 0, "c4_selfplay_run: records_out too small");
+    *n_records_out = (int64_t)c.n_records;
+    return 0;
+}
+
+extern "C" int c4_selfplay_reset(c4_ctx *ctx, void *stream)
+{
+    C4_REQUIRE(ctx, "c4_selfplay_reset: null context");
+    ctx->pool_fresh = false;
+    return 0;
+}
+
+extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations, int64_t *positions, int64_t *evals,
+                                 int64_t *sims, int64_t *games, float *device_ms, float *net_ms, void *stream)
+{
+    C4_REQUIRE(ctx, "c4_selfplay_bench: null context");
+    C4_REQUIRE(eval_kind == C4_EVAL_CENTRE || eval_kind == C4_EVAL_NET, "c4_selfplay_bench: eval_kind must be CENTRE or NET");
+    C4_REQUIRE(eval_kind != C4_EVAL_NET || ctx->net, "c4_selfplay_bench: no network attached (c4_ctx_set_net)");
+    cudaStream_t s = (cudaStream_t)stream;
+    C4_CUDA(cudaSetDevice(ctx->device));
+    C4Dev &d = ctx->d;
+    int rc;
+    if (!ctx->pool_fresh) {
+        d.n_games_target = (long long)1 << 60;
+        d.game_id_base = 0; d.game_id_stride = 1;
+        d.start_c0 = nullptr; d.start_c1 = nullptr;
+        d.records_out = nullptr; d.max_records = 0;
+        k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
+        C4_CUDA(cudaGetLastError());
+        ctx->parity = 0;
+        ctx->pool_fresh = true;
+    }
+    unsigned long long before[3], after[3];
+    C4Counters c;
+    k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, ctx->max_games, ctx->stats_dev);
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if ((rc = read_counters(ctx, &c, s))) return rc;
+    before[0] = ctx->pinned[8]; before[1] = ctx->pinned[9]; before[2] = c.games_finished;
+    C4_CUDA(cudaEventRecord(ctx->ev0, s));
+    if ((rc = selfplay_passes(ctx, eval_kind, (int)iterations, s))) return rc;
+    C4_CUDA(cudaEventRecord(ctx->ev1, s));
+    k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, ctx->max_games, ctx->stats_dev);
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if ((rc = read_counters(ctx, &c, s))) return rc;
+    after[0] = ctx->pinned[8]; after[1] = ctx->pinned[9]; after[2] = c.games_finished;
+    float ms = 0.f;
+    C4_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (evals) *evals = (int64_t)(after[0] - before[0]);
+    if (positions) *positions = (int64_t)(after[1] - before[1]);
+    if (sims) *sims = (int64_t)(after[1] - before[1]) * ctx->cfg.simulations;
+    if (games) *games = (int64_t)(after[2] - before[2]);
+    if (device_ms) *device_ms = ms;
+    if (net_ms) *net_ms = 0.f;
+    return 0;
+}
+
+extern "C" int c4_records_augment_pack(const c4_record *records, int64_t n, float *boards, float *values,
+                                       float *priors, void *stream)
+{
+    C4_REQUIRE(n >= 0 && (n == 0 || (records && boards && values && priors)), "c4_records_augment_pack: null pointer");
+    if (n == 0) return 0;
+    long long total = 2 * n * 126;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_augment_pack<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(records, n, boards, values, priors);
+    C4_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,201 @@
+"""`Engine`: thin Python owner of one c4_ctx (include/c4b200.h) -- the GPU-resident game pool that replaces the
+reference's process x thread x pipe runtime (oinkoink/neural/game_pool.py:15-49, inference_server.py:15-76) and runs
+mcts.search (oinkoink/mcts.py:94-121) for many positions at once.  PyTorch is used for device buffers and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EVAL_CENTRE, EVAL_EXTERNAL, EVAL_NET, RNG_INJECTED, RNG_NONE, RNG_PHILOX, MCTSConfigC, ptr
+
+RECORD_DTYPE = np.dtype({"names": ["c0", "c1", "policy", "result_value", "search_value", "game_id", "move", "ply",
+                                   "n_moves", "result"],
+                         "formats": ["<u8", "<u8", ("<f4", (7,)), "<f4", "<f4", "<i4", "i1", "i1", "i1", "i1"],
+                         "offsets": [0, 8, 16, 44, 48, 52, 56, 57, 58, 59], "itemsize": 64})
+assert RECORD_DTYPE.itemsize == 64
+
+NODE_DTYPE = np.dtype([("vsum", "<f8"), ("visits", "<u4"), ("meta", "<u4"), ("prior", "<f8"), ("child_block", "<u4"),
+                       ("parent", "<u4")])
+assert NODE_DTYPE.itemsize == 32
+
+
+def _cfg_struct(cfg):
+    return MCTSConfigC(int(cfg.simulations), float(cfg.pb_c_base), float(cfg.pb_c_init),
+                       float(cfg.root_dirichlet_alpha), float(cfg.root_exploration_fraction),
+                       int(cfg.num_sampling_moves))
+
+
+def _u64_tensor(a):
+    import torch
+    if torch.is_tensor(a):
+        return a.to(device="cuda", dtype=torch.int64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.uint64)).view(np.int64)).cuda()
+
+
+class Engine():
+    def __init__(self, max_games, config, device=None):
+        import torch
+        _lib.require_gpu()
+        self.torch = torch
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.max_games = int(max_games)
+        self.config = config
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        cs = _cfg_struct(config)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c4_ctx_create(self.device, self.max_games, C.byref(cs), C.byref(h)))
+        self.h = h
+        self.net = None
+        self._rng_bufs = None
+        self.n_started = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.c4_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ configuration
+    def set_config(self, config):
+        cs = _cfg_struct(config)
+        _lib.check(self.lib.c4_ctx_set_config(self.h, C.byref(cs)))
+        self.config = config
+
+    def set_net(self, model):
+        """model: connect4_b200.neural.model.ModelWrapper (owns a c4_net)"""
+        self.net = model
+        _lib.check(self.lib.c4_ctx_set_net(self.h, model.c4_net))
+
+    def set_rng(self, mode="none", seed=0, noise=None, uniform=None, record=False):
+        """mode: 'none' | 'philox' | 'injected'. noise [G,42,7] / uniform [G,42] float64 (numpy or CUDA tensors)."""
+        torch = self.torch
+        m = {"none": RNG_NONE, "philox": RNG_PHILOX, "injected": RNG_INJECTED}[mode]
+        nz = un = None
+        if m == RNG_INJECTED or record:
+            G = self.max_games
+            nz = torch.zeros((G, 42, 7), dtype=torch.float64, device="cuda")
+            un = torch.zeros((G, 42), dtype=torch.float64, device="cuda")
+            if noise is not None:
+                a = torch.as_tensor(np.asarray(noise, dtype=np.float64))
+                nz[:a.shape[0], :a.shape[1]] = a.cuda()
+            if uniform is not None:
+                a = torch.as_tensor(np.asarray(uniform, dtype=np.float64))
+                un[:a.shape[0], :a.shape[1]] = a.cuda()
+        self._rng_bufs = (nz, un)
+        _lib.check(self.lib.c4_ctx_set_rng(self.h, m, int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(nz), ptr(un), int(bool(record))))
+
+    def recorded_rng(self):
+        nz, un = self._rng_bufs
+        return nz.cpu().numpy(), un.cpu().numpy()
+
+    # ------------------------------------------------------------------ stand-alone searches
+    def begin(self, c0, c1):
+        t0, t1 = _u64_tensor(c0), _u64_tensor(c1)
+        n = int(t0.numel())
+        _lib.check(self.lib.c4_search_begin(self.h, ptr(t0), ptr(t1), n, _lib.stream_ptr()))
+        self.n_started = n
+        self._roots = (t0, t1)
+
+    def run(self, kind):
+        k = {"centre": EVAL_CENTRE, "net": EVAL_NET}[kind]
+        _lib.check(self.lib.c4_search_run(self.h, k, _lib.stream_ptr()))
+
+    def run_external(self, evaluate_batch):
+        """evaluate_batch(c0 uint64[m], c1 uint64[m]) -> (values float64[m], priors [m,7] float64 or float32).
+        GPU does select / expand / backup; the callable is the reference's evaluator protocol, batched."""
+        torch = self.torch
+        G = self.max_games
+        l0 = torch.empty(G, dtype=torch.int64, device="cuda")
+        l1 = torch.empty(G, dtype=torch.int64, device="cuda")
+        lg = torch.empty(G, dtype=torch.int32, device="cuda")
+        m = C.c_int32(0)
+        while True:
+            _lib.check(self.lib.c4_search_pending(self.h, ptr(l0), ptr(l1), ptr(lg), C.byref(m), _lib.stream_ptr()))
+            if m.value == 0:
+                break
+            a = l0[:m.value].cpu().numpy().view(np.uint64)
+            b = l1[:m.value].cpu().numpy().view(np.uint64)
+            values, priors = evaluate_batch(a, b)
+            v = torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64)).cuda()
+            pr = np.ascontiguousarray(priors)
+            dt = 1 if pr.dtype == np.float32 else 0
+            if dt == 0:
+                pr = pr.astype(np.float64)
+            p = torch.as_tensor(pr).cuda()
+            _lib.check(self.lib.c4_search_supply(self.h, ptr(v), ptr(p), dt, m.value, _lib.stream_ptr()))
+
+    def readout(self, n=None):
+        torch = self.torch
+        n = self.n_started if n is None else n
+        dev = "cuda"
+        out = dict(visits=torch.zeros((n, 7), dtype=torch.int32, device=dev),
+                   vsum=torch.zeros((n, 7), dtype=torch.float64, device=dev),
+                   cres=torch.zeros((n, 7), dtype=torch.int8, device=dev),
+                   root_visits=torch.zeros(n, dtype=torch.int32, device=dev),
+                   root_vsum=torch.zeros(n, dtype=torch.float64, device=dev),
+                   root_prior=torch.zeros((n, 7), dtype=torch.float64, device=dev),
+                   vpolicy=torch.zeros((n, 7), dtype=torch.float64, device=dev),
+                   cpolicy=torch.zeros((n, 7), dtype=torch.float64, device=dev),
+                   best=torch.zeros(n, dtype=torch.int8, device=dev),
+                   best_value=torch.zeros(n, dtype=torch.float64, device=dev),
+                   nodes=torch.zeros(n, dtype=torch.int32, device=dev))
+        order = ["visits", "vsum", "cres", "root_visits", "root_vsum", "root_prior", "vpolicy", "cpolicy", "best",
+                 "best_value", "nodes"]
+        _lib.check(self.lib.c4_search_readout(self.h, n, *[ptr(out[k]) for k in order], _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
+    def export_tree(self, game):
+        cap = (int(self.config.simulations) + 2) * 8
+        buf = np.zeros(cap, dtype=NODE_DTYPE)
+        n = C.c_int64(0)
+        _lib.check(self.lib.c4_search_export_tree(self.h, int(game), buf.ctypes.data_as(C.c_void_p), cap, C.byref(n),
+                                                  _lib.stream_ptr()))
+        return buf[:n.value]
+
+    # ------------------------------------------------------------------ self-play
+    def selfplay(self, n_games, kind, game_id_base=0, game_id_stride=1, start=None):
+        """Play n_games complete games; returns the position records (numpy structured array, RECORD_DTYPE)."""
+        torch = self.torch
+        k = {"centre": EVAL_CENTRE, "net": EVAL_NET}[kind]
+        cap = int(n_games) * 42
+        rec = torch.zeros((max(cap, 1), 64), dtype=torch.uint8, device="cuda")
+        s0 = s1 = None
+        if start is not None:
+            s0, s1 = _u64_tensor(start[0]), _u64_tensor(start[1])
+        n = C.c_int64(0)
+        _lib.check(self.lib.c4_selfplay_run(self.h, k, int(n_games), int(game_id_base), int(game_id_stride),
+                                            ptr(s0), ptr(s1), ptr(rec), cap, C.byref(n), _lib.stream_ptr()))
+        self.last_records_device = rec[:n.value]
+        return rec[:n.value].cpu().numpy().view(RECORD_DTYPE).reshape(-1)
+
+    def bench(self, iterations, kind):
+        k = {"centre": EVAL_CENTRE, "net": EVAL_NET}[kind]
+        pos, ev, sims, games = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        ms, nms = C.c_float(0), C.c_float(0)
+        _lib.check(self.lib.c4_selfplay_bench(self.h, k, int(iterations), C.byref(pos), C.byref(ev), C.byref(sims),
+                                              C.byref(games), C.byref(ms), C.byref(nms), _lib.stream_ptr()))
+        return dict(positions=pos.value, evals=ev.value, sims=sims.value, games=games.value, device_ms=ms.value)
+
+    def reset_pool(self):
+        _lib.check(self.lib.c4_selfplay_reset(self.h, _lib.stream_ptr()))
+
+
+def augment_pack(records_device):
+    """records (CUDA uint8 [n,64]) -> (boards f32 [2n,3,6,7], values f32 [2n], priors f32 [2n,7]) with the reference's
+    left-right flip augmentation (oinkoink/neural/pytorch/data.py:78-105)."""
+    import torch
+    n = int(records_device.shape[0])
+    boards = torch.empty((2 * n, 3, 6, 7), dtype=torch.float32, device="cuda")
+    values = torch.empty(2 * n, dtype=torch.float32, device="cuda")
+    priors = torch.empty((2 * n, 7), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().c4_records_augment_pack(ptr(records_device), n, ptr(boards), ptr(values), ptr(priors),
+                                                   _lib.stream_ptr()))
+    return boards, values, priors

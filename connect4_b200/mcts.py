@@ -1,0 +1,113 @@
+"""`MCTSConfig`, `MCTS`, `search` with the reference's surface (oinkoink/mcts.py:13-121); the search itself runs in
+the CUDA engine (csrc/c4_search.cu).  There is no host implementation of the search: without the CUDA library or a
+GPU these calls raise.
+
+Evaluator dispatch (see evaluators.Evaluator.device_kind):
+  Evaluator(evaluate_centre_with_prior)            -> evaluator fused into the tree kernel, one launch per search
+  Evaluator(partial(evaluate_nn, model=ModelWrapper)) -> tree kernel + CUDA network kernel, all on the device
+  any other callable `evaluator(board) -> (value, prior)` -> tree kernels on the device, the callable on the host
+"""
+from typing import Callable, List, Tuple
+
+import numpy as np
+
+from .board import Board
+from .evaluators import Evaluator
+from .player import BasePlayer
+from .tree import PositionEvaluation, SearchEvaluation, Tree  # noqa: F401  (re-exported like the reference)
+from .utils import Connect4Stats as info
+
+
+class MCTSConfig():
+    def __init__(self, simulations: int, pb_c_base: int = 19652, pb_c_init: float = 1.25,
+                 root_dirichlet_alpha: float = 0.0, root_exploration_fraction: float = 0.0, num_sampling_moves=0):
+        self.simulations = simulations
+        self.pb_c_base = pb_c_base
+        self.pb_c_init = pb_c_init
+        self.root_dirichlet_alpha = root_dirichlet_alpha
+        self.root_exploration_fraction = root_exploration_fraction
+        self.num_sampling_moves = num_sampling_moves
+
+
+_ENGINES = {}
+
+
+def _engine(config, n):
+    """engines are cached per (capacity, simulations): creating one allocates the node pool"""
+    from .engine import Engine
+    cap = 1
+    while cap < n:
+        cap *= 2
+    key = (cap, int(config.simulations))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = Engine(cap, config)
+        _ENGINES[key] = eng
+    eng.set_config(config)
+    return eng
+
+
+def _host_evaluator(evaluator):
+    def batch(c0, c1):
+        values, priors = [], []
+        for a, b in zip(c0, c1):
+            v, p = evaluator(Board.from_bitboards(int(a), int(b)))
+            values.append(float(np.asarray(v).reshape(-1)[0]))
+            priors.append(np.asarray(p))
+        pr = np.stack(priors)
+        return np.array(values, np.float64), (pr if pr.dtype == np.float32 else pr.astype(np.float64))
+    return batch
+
+
+def search_batch(config: MCTSConfig, boards: List[Board], evaluator, noise=None):
+    """search() for many root positions at once (one GPU warp per tree). Returns (engine, trees-as-readout dict)."""
+    eng = _engine(config, len(boards))
+    c0 = np.array([int(b.color[0]) for b in boards], np.uint64)
+    c1 = np.array([int(b.color[1]) for b in boards], np.uint64)
+    if noise is not None:
+        eng.set_rng("injected", noise=np.asarray(noise, np.float64).reshape(len(boards), 1, 7),
+                    uniform=np.zeros((len(boards), 1)))
+    else:
+        eng.set_rng("none")
+    kind, model = evaluator.device_kind() if isinstance(evaluator, Evaluator) else ("external", None)
+    eng.begin(c0, c1)
+    if kind == "centre":
+        eng.run("centre")
+    elif kind == "net":
+        eng.set_net(model)
+        eng.run("net")
+    else:
+        eng.run_external(_host_evaluator(evaluator))
+    return eng
+
+
+def search(config: MCTSConfig, board: Board, evaluator: Callable[[Board], Tuple[float, List[float]]]):
+    """oinkoink/mcts.py:94-121. Root noise (mcts.py:171-181) is drawn here with np.random.gamma -- the same call, on
+    the same global numpy stream, as the reference -- and injected into the device search."""
+    if board.result is not None:
+        raise ValueError("search() on a finished game (the reference fails here too: mcts.py:102)")
+    noise = None
+    if config.root_dirichlet_alpha and config.root_exploration_fraction:
+        noise = np.random.gamma(config.root_dirichlet_alpha, 1, info.width)
+    eng = search_batch(config, [board], evaluator, None if noise is None else noise[None, :])
+    return Tree(board, eng.export_tree(0))
+
+
+class MCTS(BasePlayer):
+    def __init__(self, name: str, config: MCTSConfig, evaluator: Evaluator):
+        super().__init__(name)
+        self.config = config
+        self.evaluator = evaluator
+
+    def make_move(self, board):
+        """oinkoink/mcts.py:78-88: search, choose (sample v^2 in the opening, else best value), play it on `board`."""
+        tree = search(self.config, board, self.evaluator)
+        if board.age < self.config.num_sampling_moves:
+            child = tree.sample_value_fn(lambda x: x ** 2)
+        else:
+            child = tree.best_move()
+        board.make_move(child.name)
+        return child.name, child.data.absolute_value, tree
+
+    def __str__(self):
+        return super().__str__() + ", type: Computer"

@@ -1,0 +1,139 @@
+"""`ModelWrapper`: the evaluator-side surface of oinkoink/neural/pytorch/model.py:137-282 on the CUDA network kernel.
+
+  model(Board)        -> (value ndarray (1,), prior ndarray (7,))      float32   (model.py:252-267)
+  model([Board, ...]) -> (values ndarray (N,), priors ndarray (N,7))   float32   (model.py:269-282)
+  anything else       -> TypeError                                               (model.py:176-178)
+
+Training (model.py:199-240) is outside this path and raises NotImplementedError.  Checkpoints use the reference's
+format (`net_state_dict` / `optimiser_state_dict` / `scheduler_state_dict`, model.py:242-250).
+"""
+import ctypes as C
+from typing import List, Optional, Union
+
+import numpy as np
+
+from .. import _lib
+from ..board import Board
+from .config import ModelConfig, NetConfig
+from .weights import fold_state_dict
+
+
+def _init_state_dict(nc: NetConfig):
+    """Freshly initialised parameters with the reference's module construction order (model.py:120-128), so that
+    torch.manual_seed(s) gives the same network as `Net(config)` does in the reference."""
+    import torch.nn as nn
+    import torch
+
+    class Res(nn.Module):
+        def __init__(s, f):
+            super().__init__()
+            s.conv1 = nn.Conv2d(f, f, 3, padding=1, bias=False)
+            s.conv2 = nn.Conv2d(f, f, 3, padding=1, bias=False)
+            s.batch_norm1 = nn.BatchNorm2d(f)
+            s.batch_norm2 = nn.BatchNorm2d(f)
+
+    class VH(nn.Module):
+        def __init__(s, f, n):
+            super().__init__()
+            s.conv1 = nn.Conv2d(f, 1, 1)
+            s.batch_norm = nn.BatchNorm2d(1)
+            s.fcN = nn.Sequential(*[nn.Linear(42, 42) for _ in range(n)])
+            s.fc1 = nn.Linear(42, 1)
+            s.w1 = nn.Parameter(torch.tensor(1.0), requires_grad=False)
+            s.w2 = nn.Parameter(torch.tensor(0.5), requires_grad=False)
+
+    class PH(nn.Module):
+        def __init__(s, f):
+            super().__init__()
+            s.conv1 = nn.Conv2d(f, 2, 1)
+            s.batch_norm = nn.BatchNorm2d(2)
+            s.fc1 = nn.Linear(84, 7)
+
+    class Params(nn.Module):
+        def __init__(s):
+            super().__init__()
+            s.body = nn.Sequential(
+                nn.Sequential(nn.Conv2d(nc.channels, nc.filters, 3, padding=1, bias=False),
+                              nn.BatchNorm2d(nc.filters)),
+                nn.Sequential(*[Res(nc.filters) for _ in range(nc.n_residuals)]))
+            s.value_head = VH(nc.filters, nc.n_fc_layers)
+            s.policy_head = PH(nc.filters)
+
+    return {k: v.detach().clone() for k, v in Params().state_dict().items()}
+
+
+class ModelWrapper():
+    def __init__(self, config: Optional[ModelConfig] = None, file_name: Optional[str] = None, state_dict=None,
+                 device: Optional[int] = None):
+        import torch
+        _lib.require_gpu()
+        self.config = config if config is not None else ModelConfig()
+        self._extra = {}
+        if state_dict is not None:
+            sd = state_dict
+        elif file_name is not None:
+            checkpoint = torch.load(file_name, map_location="cpu", weights_only=False)
+            sd = checkpoint['net_state_dict']
+            self._extra = {k: v for k, v in checkpoint.items() if k != 'net_state_dict'}
+        else:
+            sd = _init_state_dict(self.config.net_config)
+        self.state_dict = {k: (v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))) for k, v in sd.items()}
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        blob = fold_state_dict(self.state_dict)
+        h = C.c_void_p()
+        _lib.check(_lib.load().c4_net_create(self.device.index, blob.ctypes.data_as(C.c_void_p), blob.size, C.byref(h)))
+        self.c4_net = h
+        self.n_parameters = sum(int(v.numel()) for k, v in self.state_dict.items()
+                                if "running_" not in k and "num_batches" not in k and not k.endswith((".w1", ".w2")))
+        print("Constructed NN with {} parameters".format(self.n_parameters))
+
+    def __del__(self):
+        try:
+            if getattr(self, "c4_net", None):
+                _lib.load().c4_net_destroy(self.c4_net)
+                self.c4_net = None
+        except Exception:
+            pass
+
+    @property
+    def flops_per_position(self):
+        return float(_lib.load().c4_net_flops_per_position(self.c4_net))
+
+    # ---- evaluator protocol
+    def __call__(self, input_: Union[Board, List[Board]]):
+        if isinstance(input_, Board):
+            v, p = self._call_list([input_])
+            return v.reshape(-1), p.reshape(-1)
+        elif isinstance(input_, list):
+            return self._call_list(input_)
+        raise TypeError('ModelWrapper called with {}. It accepts either a Board nor a list(Board)'.format(type(input_)))
+
+    def _call_list(self, board_list: List[Board]):
+        c0 = np.array([int(b.color[0]) for b in board_list], np.uint64)
+        c1 = np.array([int(b.color[1]) for b in board_list], np.uint64)
+        values, priors = self.evaluate_bitboards(c0, c1)
+        values, priors = values.cpu().numpy(), priors.cpu().numpy()
+        assert not np.isnan(values).any()
+        assert not np.isnan(priors).any()
+        return values, priors
+
+    def evaluate_bitboards(self, c0, c1):
+        """uint64 bitboards (numpy or CUDA int64 tensors) -> (values f32 [n], priors f32 [n,7]) CUDA tensors."""
+        import torch
+        from ..engine import _u64_tensor
+        t0, t1 = _u64_tensor(c0), _u64_tensor(c1)
+        n = int(t0.numel())
+        out = torch.empty((n, 8), dtype=torch.float32, device="cuda")
+        _lib.check(_lib.load().c4_net_forward(self.c4_net, _lib.ptr(t0), _lib.ptr(t1), n, None, _lib.ptr(out),
+                                              _lib.stream_ptr()))
+        return out[:, 7].contiguous(), out[:, :7].contiguous()
+
+    # ---- checkpoints (reference format)
+    def save(self, folder_path: str):
+        import torch
+        d = {'net_state_dict': self.state_dict, 'optimiser_state_dict': self._extra.get('optimiser_state_dict', {}),
+             'scheduler_state_dict': self._extra.get('scheduler_state_dict', {})}
+        torch.save(d, folder_path + '/net.pth')
+
+    def train(self, *a, **k):
+        raise NotImplementedError("training is outside the self-play hot path this package accelerates")

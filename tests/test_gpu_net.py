@@ -1,0 +1,123 @@
+"""CUDA network kernel vs the fp32 torch restatement / the reference's own outputs (tolerance 1e-2 absolute on
+values and priors, the bound BASELINE.json's north_star states for the bf16 path)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden, random_positions
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _golden_model():
+    from oracle import net_ref as nr
+    from connect4_b200.neural.model import ModelWrapper
+    sd = nr.load_golden_state(os.path.join(GOLDEN, "example_net_state.npz"))
+    return ModelWrapper(state_dict=sd), sd
+
+
+def test_example_net_vs_reference_outputs():
+    """the reference's trained checkpoint on 1536 positions: outputs recorded from the reference's ModelWrapper"""
+    g = golden("net_outputs.npz")
+    model, _ = _golden_model()
+    v, p = model.evaluate_bitboards(g["c0"], g["c1"])
+    v, p = v.cpu().numpy(), p.cpu().numpy()
+    dv, dp = np.abs(v - g["value"]).max(), np.abs(p - g["prior"]).max()
+    print("example_net max|dvalue| %.2e max|dprior| %.2e" % (dv, dp))
+    assert dv < TOL and dp < TOL
+    assert np.abs(p.sum(axis=1) - 1).max() < 1e-5
+    assert model.flops_per_position == 4740876.0
+
+
+def test_model_wrapper_call_protocol():
+    """model(Board) -> ((1,), (7,)); model([Board]) -> ((N,), (N,7)); TypeError otherwise (model.py:171-178)"""
+    from connect4_b200.board import Board
+    model, _ = _golden_model()
+    v, p = model(Board())
+    assert v.shape == (1,) and p.shape == (7,) and v.dtype == np.float32 and p.dtype == np.float32
+    assert abs(float(v[0]) - 0.5381826) < TOL
+    b2 = Board()
+    b2.make_move(3)
+    vs, ps = model([Board(), b2])
+    assert vs.shape == (2,) and ps.shape == (2, 7)
+    assert np.array_equal(vs[:1], v) and np.array_equal(ps[0], p)      # batch composition does not change a row
+    with pytest.raises(TypeError):
+        model("board")
+
+
+def test_random_init_nets_vs_torch_fp32():
+    """seeded random-init default net and the example_config net (64 filters / 6 residual / 6 fc)"""
+    import torch
+    from oracle import net_ref as nr
+    from connect4_b200.neural.config import ModelConfig, NetConfig
+    from connect4_b200.neural.model import ModelWrapper
+    g = golden("net_outputs.npz")
+    torch.manual_seed(0)
+    small = ModelWrapper(ModelConfig())
+    v, p = small.evaluate_bitboards(g["c0"][:256], g["c1"][:256])
+    assert np.abs(v.cpu().numpy() - g["rand_value"]).max() < TOL and np.abs(p.cpu().numpy() - g["rand_prior"]).max() < TOL
+    torch.manual_seed(0)
+    big = ModelWrapper(ModelConfig(net_config=NetConfig(filters=64, n_fc_layers=6, n_residuals=6)))
+    v, p = big.evaluate_bitboards(g["c0"][:256], g["c1"][:256])
+    dv, dp = np.abs(v.cpu().numpy() - g["big_value"]).max(), np.abs(p.cpu().numpy() - g["big_prior"]).max()
+    print("64f/6r net max|dvalue| %.2e max|dprior| %.2e" % (dv, dp))
+    assert dv < TOL and dp < TOL
+    assert big.flops_per_position == 37342620.0
+
+
+def test_8ply_shaped_set_67557_positions():
+    """BASELINE.json configs[4]: 67,557 synthetic 8-ply positions, value 'RMSE' (mean MSE, stats.py:14-16) parity"""
+    import random
+    import torch
+    from oracle import c4oracle as o
+    from oracle import net_ref as nr
+    rng = random.Random(8)
+    pos = []
+    while len(pos) < 67557:
+        c0 = c1 = 0
+        ok = True
+        for _ in range(8):
+            m = o.legal_mask(c0, c1)
+            c0, c1, res = o.drop(c0, c1, rng.choice([c for c in range(7) if m >> c & 1]))
+            if res != -1:
+                ok = False
+                break
+        if ok:
+            pos.append((c0, c1))
+    a = np.array(pos, np.uint64)
+    model, sd = _golden_model()
+    v, p = model.evaluate_bitboards(a[:, 0].copy(), a[:, 1].copy())
+    v, p = v.cpu().numpy(), p.cpu().numpy()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    rv, rp = nr.evaluate(sd, a[:, 0], a[:, 1])
+    dv, dp = np.abs(v - rv), np.abs(p - rp)
+    print("8ply set: value max %.2e mean %.2e | prior max %.2e mean %.2e" % (dv.max(), dv.mean(), dp.max(), dp.mean()))
+    assert dv.max() < TOL and dp.max() < TOL
+    labels = np.round(rv * 2) / 2                                 # synthetic {0, 0.5, 1} labels
+    mse_ref, mse_gpu = float(np.mean((rv - labels) ** 2)), float(np.mean((v - labels) ** 2))
+    assert abs(mse_ref - mse_gpu) < 1e-3
+
+
+def test_device_count_argument_and_ragged_sizes():
+    """c4_net_forward honours a device-side count and any batch size (empty, 1, not a multiple of the tile)"""
+    import ctypes as C
+    import torch
+    from connect4_b200 import _lib
+    g = golden("net_outputs.npz")
+    model, _ = _golden_model()
+    full_v, full_p = model.evaluate_bitboards(g["c0"], g["c1"])
+    for n in (1, 7, 8, 9, 1183, 1185):
+        v, p = model.evaluate_bitboards(g["c0"][:n], g["c1"][:n])
+        assert torch.equal(v, full_v[:n]) and torch.equal(p, full_p[:n])
+    t0 = torch.as_tensor(g["c0"].view(np.int64)).cuda()
+    t1 = torch.as_tensor(g["c1"].view(np.int64)).cuda()
+    out = torch.full((len(g["c0"]), 8), -7.0, dtype=torch.float32, device="cuda")
+    cnt = torch.tensor([100], dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().c4_net_forward(model.c4_net, _lib.ptr(t0), _lib.ptr(t1), len(g["c0"]), _lib.ptr(cnt),
+                                          _lib.ptr(out), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out[:100, 7], full_v[:100]) and (out[100:] == -7.0).all()
+    v, p = model.evaluate_bitboards(np.zeros(0, np.uint64), np.zeros(0, np.uint64))
+    assert v.numel() == 0

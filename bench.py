@@ -1,0 +1,281 @@
+#!/usr/bin/env python3
+"""bench.py -- self-play positions/sec at 800 sims/move (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (ours): BASELINE.json configs[2] -- 4096 concurrent self-play games per GPU, default NetConfig ResNet
+(32 filters / 3 residual / 4 fc; the reference's example_net weights), 800 simulations per move, AlphaZero root noise +
+6 sampled moves, bf16 batched leaf evaluation.  Games never interact, so with N GPUs every rank runs its own pool
+(weak scaling, no data-path collective).
+
+A "step" = `--passes` lock-step passes of the pool in steady state (finished games re-seeded at once); every pass
+advances each game to its next leaf, evaluates all leaves in one network launch and backs the answers up.
+  value = positions (root moves played) of all ranks / device time (CUDA events, max over ranks), inputs resident.
+  e2e   = the same metric through the public API with HOST buffers: SelfPlayPool.generate_records() plays a whole
+          generation from host-resident start positions and returns the position records to host memory.
+  roofline = the network kernel (dominant): algorithmic FLOPs per launch / its mean CUDA-event duration sampled inside
+          the timed region, against the measured sustained bf16 peak (MEASURED_PEAKS.json).
+  cpu_baseline = the oracle port (oracle/selfplay_port.py) on the box's host cores, bounded sample (rank 0, N=1 only).
+--impl reference: the CPU port alone, all host cores, same metric / config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "selfplay_positions_per_sec_at_800_sims_per_move"
+UNIT = "positions/s"
+SIMS = 800
+STATE = os.path.join(ROOT, "tests", "golden", "example_net_state.npz")
+WORKLOAD = ("BASELINE.json configs[2]: 4096 concurrent self-play games per GPU, default NetConfig 32f/3r/4fc "
+            "(example_net weights), 800 sims/move, AlphaZero noise alpha=0.3 frac=0.25, 6 sampled moves, 16-bit (fp16 operand / fp32 accumulate) tensor-core leaf eval")
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port(seconds, warm=2.0, procs=None):
+    from oracle.selfplay_port import PortPool
+    pp = PortPool(procs, SIMS, games_per_worker=32, state_path=STATE)
+    try:
+        pp.step(warm)
+        r = pp.step(seconds)
+    finally:
+        pp.close()
+    return r, pp.procs
+
+
+def run_reference(args, rank):
+    """the reference arm: the CPU port of the reference path on all host cores (the reference itself is pure Python
+    and is not present on the GPU box)."""
+    if rank != 0:
+        return
+    from oracle.selfplay_port import PortPool
+    procs = os.cpu_count() or 1
+    pp = PortPool(procs, SIMS, games_per_worker=32, state_path=STATE)
+    try:
+        budget = args.ref_seconds
+        for _ in range(args.warmup):
+            pp.step(min(budget, 3.0))
+        pos = secs = evals = 0
+        for _ in range(args.steps):
+            r = pp.step(budget)
+            pos += r["positions"]
+            secs += r["seconds"]
+            evals += r["evals"]
+    finally:
+        pp.close()
+    v = pos / secs
+    sample = "%d single-threaded workers x 32 games in flight, %d steps x %.0f s of self-play at 800 sims/move" % (
+        procs, args.steps, budget)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "host": "CPU port of the reference path (oracle/selfplay_port.py)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "evals_per_sec": evals / secs, "gpu_launches": 0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
+    ap.add_argument("--passes", type=int, default=4000, help="lock-step passes per step")
+    ap.add_argument("--preroll", type=int, default=36000, help="untimed passes that bring the pool to steady state")
+    ap.add_argument("--e2e-games", type=int, default=4096)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from connect4_b200.mcts import MCTSConfig
+    from connect4_b200.neural.game_pool import SelfPlayPool
+    from connect4_b200.neural.model import ModelWrapper
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    z = np.load(STATE)
+    model = ModelWrapper(state_dict={k: z[k] for k in z.files})
+    cfg = MCTSConfig(SIMS, 19652, 1.25, 0.3, 0.25, 6)
+    pool = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=1000 + rank)
+
+    # untimed: bring the pool to steady state (games at all plies), then W warm-up steps
+    done = 0
+    while done < args.preroll:
+        n = min(4000, args.preroll - done)
+        pool.throughput(n)
+        done += n
+    for _ in range(args.warmup):
+        pool.throughput(args.passes)
+
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    tot = dict(positions=0, evals=0, device_ms=0.0, net_ms=0.0, tree_ms=0.0, games=0)
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        r = pool.throughput(args.passes)
+        for k in ("positions", "evals", "device_ms", "games"):
+            tot[k] += r[k]
+        tot["net_ms"] += r["net_ms"]
+        tot["tree_ms"] += r["tree_ms"]
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if sampler else None
+
+    # whole-job aggregate: sum of units over ranks / max device time over ranks
+    stats = torch.tensor([tot["positions"], tot["evals"], tot["games"]], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([tot["device_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    positions, evals, games = [float(x) for x in stats.tolist()]
+    secs = float(tmax.item()) / 1000.0
+    value = positions / secs
+
+    # end to end through the public API with host buffers: one whole generation, records back on the host
+    e2e = None
+    if not args.no_e2e:
+        start = (np.zeros(args.e2e_games, np.uint64), np.zeros(args.e2e_games, np.uint64))   # host-resident inputs
+        pool2 = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=5000 + rank)
+        pool2.generate_records(min(64, args.e2e_games), start=(start[0][:64], start[1][:64]))   # warm the path
+        barrier()
+        t0 = time.perf_counter()
+        rec = pool2.generate_records(args.e2e_games, start=start)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e = torch.tensor([float(len(rec))], dtype=torch.float64, device="cuda")
+        tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(e.item()) / float(tm.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * 8 * args.e2e_games), "d2h_bytes_per_step": int(len(rec) * 64),
+               "what": "SelfPlayPool.generate_records(%d games from host start positions) -> host records, "
+                       "wall clock incl. pool drain" % args.e2e_games}
+        pool2.engine.close()
+
+    if rank == 0:
+        peak_tf, peak_hbm, peak_src = peaks()
+        flops = model.flops_per_position
+        n_pass = args.steps * args.passes
+        evals_per_pass = tot["evals"] / n_pass
+        net_ms = tot["net_ms"] / args.steps
+        tree_ms = tot["tree_ms"] / args.steps
+        achieved = (evals_per_pass * flops) / (net_ms * 1e-3) / 1e12 if net_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "games_per_gpu": args.games, "passes_per_step": args.passes,
+                       "preroll_passes": args.preroll, "simulations": SIMS,
+                       "l2": "node pool working set (%.0f MB/GPU) exceeds L2; fresh leaves every pass" %
+                             (args.games * (SIMS + 2) * 256 / 1e6)},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(2 * n_pass + 4 * args.steps),
+            "roofline": {"kernel": "k_net_resident<OpFP16,32,8>", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                         "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals_per_pass,
+                         "net_ms_per_launch": net_ms, "tree_ms_per_launch": tree_ms,
+                         "net_share_of_step": (net_ms * n_pass / args.steps) / (1000.0 * secs / args.steps) if secs else None},
+            "sims_per_sec": value * SIMS, "evals_per_sec": evals / secs, "games_finished": games,
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu:
+            r, cores = cpu_port(args.cpu_seconds)
+            line["cpu_baseline"] = {
+                "value": r["positions_per_sec"], "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d single-threaded workers x 32 games in flight, %.0f s of self-play at 800 sims/move "
+                          "(C oracle tree + torch fp32 net); the unmodified Python reference measured 13 positions/s on "
+                          "8 cores (BASELINE.md)" % (cores, args.cpu_seconds),
+                "evals_per_sec": r["evals_per_sec"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -60,7 +60,7 @@ SIGNATURES = {
     "c4_selfplay_run": (C.c_int, [vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, C.c_int64,
                                   C.POINTER(C.c_int64), vp]),
     "c4_selfplay_bench": (C.c_int, [vp, C.c_int, C.c_int64] + [C.POINTER(C.c_int64)] * 4 +
-                          [C.POINTER(C.c_float)] * 2 + [vp]),
+                          [C.POINTER(C.c_float)] * 3 + [vp]),
     "c4_selfplay_reset": (C.c_int, [vp, vp]),
     "c4_records_augment_pack": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp]),
 }

@@ -16,6 +16,7 @@
 // Kernel B (filters = 64, example_config): same math, but weights do not fit on chip (897 KB): the CTA walks the layers
 //   together and streams each layer's weights L2 -> shared memory; the residual is re-read from the bf16 copy.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
 
@@ -25,6 +26,7 @@
 
 #define NPX 66            // padded pixel rows: q in [-1, 64], row index q + 1
 #define LEAKY 0.01f
+#define SCRATCH_BYTES 512 // per-warp head scratch (126 floats)
 
 // offsets inside the fp32 head block
 #define HO_VW 0           // value conv weight [F] (max 64)
@@ -44,6 +46,7 @@
 struct c4_net {
     int device;
     int F, R, n_fc;
+    bool fp16;            // operand element type of the conv GEMMs (false: bf16)
     void *image;          // device: smem image (kernel A) / per-layer weight images (kernel B)
     size_t image_bytes;
     double flops;
@@ -61,11 +64,44 @@ __device__ __forceinline__ void mma16816(float *c, const uint32_t *a, uint32_t b
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma16816h(float *c, const uint32_t *a, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : LEAKY * x; }
+
+// operand element type of the tensor-core GEMMs (accumulation is always fp32).  fp16 is the default: on the
+// reference's trained checkpoint bf16 operands give max |dvalue| 5.4e-2 (> the 1e-2 parity bound), fp16 6.6e-3, at the
+// same tensor-core rate ("operand precision").
+struct OpBF16 {
+    static constexpr uint32_t ONE = 0x3F80u;
+    __device__ static __forceinline__ void mma(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) { mma16816(c, a, b0, b1); }
+    __device__ static __forceinline__ uint32_t pack(float lo, float hi)
+    {
+        __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t *>(&v);
+    }
+    __device__ static __forceinline__ float2 unpack(uint32_t u)
+    {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&u));
+    }
+};
+struct OpFP16 {
+    static constexpr uint32_t ONE = 0x3C00u;
+    __device__ static __forceinline__ void mma(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) { mma16816h(c, a, b0, b1); }
+    __device__ static __forceinline__ uint32_t pack(float lo, float hi)
+    {
+        __half2 v = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t *>(&v);
+    }
+    __device__ static __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2 *>(&u)); }
+};
 
 // One 3x3 convolution of one board as implicit GEMM: acc[t][j][.] (+)= sum over taps/channels.
 //   src: padded activation strip (row stride AS bytes), W: [F][9*CIN + 8] bf16 rows (stride WS bytes)
-template <int F, int CIN>
+template <typename OP, int F, int CIN>
 __device__ __forceinline__ void conv3x3(float (&acc)[3][F / 8][4], uint32_t src, uint32_t W, int lane)
 {
     constexpr int AS = F * 2 + 16;
@@ -96,8 +132,8 @@ __device__ __forceinline__ void conv3x3(float (&acc)[3][F / 8][4], uint32_t src,
                 ldsm4(b_base + (uint32_t)(jp * 16 * WS + (tap * CIN + kc * 16) * 2), b0, b1, b2, b3);
 #pragma unroll
                 for (int t = 0; t < 3; t++) {
-                    mma16816(acc[t][2 * jp], a[t], b0, b1);
-                    mma16816(acc[t][2 * jp + 1], a[t], b2, b3);
+                    OP::mma(acc[t][2 * jp], a[t], b0, b1);
+                    OP::mma(acc[t][2 * jp + 1], a[t], b2, b3);
                 }
             }
         }
@@ -105,15 +141,15 @@ __device__ __forceinline__ void conv3x3(float (&acc)[3][F / 8][4], uint32_t src,
 }
 
 // board -> bf16 input planes (Board.to_array, oinkoink/board.py:147-154) in channels 0..15 of the strip
-template <int F>
+template <typename OP, int F>
 __device__ __forceinline__ void write_input(unsigned char *buf, u64 c0, u64 c1, int lane)
 {
     constexpr int AS = F * 2 + 16;
-    const uint32_t tomove = ((__popcll(c0 | c1) & 1) == 0) ? 0x3F80u : 0u;
+    const uint32_t tomove = ((__popcll(c0 | c1) & 1) == 0) ? OP::ONE : 0u;
     for (int px = lane; px < 42; px += 32) {
         int r = px / 7, c = px - r * 7;
         int bit = 7 * c + (5 - r);
-        uint32_t o = (uint32_t)((c0 >> bit) & 1ULL) * 0x3F80u, x = (uint32_t)((c1 >> bit) & 1ULL) * 0x3F80u;
+        uint32_t o = (uint32_t)((c0 >> bit) & 1ULL) * OP::ONE, x = (uint32_t)((c1 >> bit) & 1ULL) * OP::ONE;
         uint4 v0 = make_uint4(tomove | (o << 16), x, 0u, 0u), v1 = make_uint4(0u, 0u, 0u, 0u);
         unsigned char *row = buf + (size_t)(((r + 1) * 8 + (c + 1)) + 1) * AS;
         *reinterpret_cast<uint4 *>(row) = v0;
@@ -122,7 +158,7 @@ __device__ __forceinline__ void write_input(unsigned char *buf, u64 c0, u64 c1, 
 }
 
 // store the activated fp32 fragments as the bf16 operand copy (valid pixels only: pad column rows stay zero)
-template <int F>
+template <typename OP, int F>
 __device__ __forceinline__ void store_act(unsigned char *buf, const float (&v)[3][F / 8][4], int lane)
 {
     constexpr int AS = F * 2 + 16;
@@ -133,8 +169,8 @@ __device__ __forceinline__ void store_act(unsigned char *buf, const float (&v)[3
 #pragma unroll
         for (int j = 0; j < F / 8; j++) {
             unsigned char *p = buf + (size_t)((8 + 16 * t + g) + 1) * AS + (j * 8 + 2 * tq) * 2;
-            *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(v[t][j][0], v[t][j][1]);
-            *reinterpret_cast<__nv_bfloat162 *>(p + 8 * AS) = __floats2bfloat162_rn(v[t][j][2], v[t][j][3]);
+            *reinterpret_cast<uint32_t *>(p) = OP::pack(v[t][j][0], v[t][j][1]);
+            *reinterpret_cast<uint32_t *>(p + 8 * AS) = OP::pack(v[t][j][2], v[t][j][3]);
         }
 }
 
@@ -233,7 +269,7 @@ struct ImageA {
     __host__ __device__ static constexpr size_t total(int R) { return head_off(R) + HEAD_FLOATS * 4; }
 };
 
-template <int F, int WARPS>
+template <typename OP, int F, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_net_resident(const unsigned char *__restrict__ image, int image_bytes, int R, const u64 *__restrict__ c0,
                const u64 *__restrict__ c1, int n, const int *__restrict__ count, float *__restrict__ out)
@@ -247,8 +283,9 @@ k_net_resident(const unsigned char *__restrict__ image, int image_bytes, int R, 
     // resident parameters
     for (int i = threadIdx.x; i < image_bytes / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(smem)[i] = reinterpret_cast<const uint4 *>(image)[i];
-    unsigned char *X = smem + image_bytes + (size_t)warp * 2 * ACT;
+    unsigned char *X = smem + image_bytes + (size_t)warp * (2 * ACT + SCRATCH_BYTES);
     unsigned char *H = X + ACT;
+    float *scratch = reinterpret_cast<float *>(H + ACT);   // NOT inside the strips: their pad rows must stay zero
     for (int i = lane; i < 2 * ACT / 16; i += 32) reinterpret_cast<uint4 *>(X)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const uint32_t sX = smem_u32(X), sH = smem_u32(H), sW = smem_u32(smem);
@@ -258,11 +295,11 @@ k_net_resident(const unsigned char *__restrict__ image, int image_bytes, int R, 
 
     for (int b = blockIdx.x * WARPS + warp; b < n; b += gridDim.x * WARPS) {
         const u64 bc0 = c0[b], bc1 = c1[b];
-        write_input<F>(H, bc0, bc1, lane);
+        write_input<OP, F>(H, bc0, bc1, lane);
         __syncwarp();
         float acc[3][F / 8][4], res[3][F / 8][4];
         // stem: conv3x3(3->F) + BN + LeakyReLU (model.py:20-31)
-        conv3x3<F, 16>(acc, sH, sW, lane);
+        conv3x3<OP, F, 16>(acc, sH, sW, lane);
 #pragma unroll
         for (int t = 0; t < 3; t++)
 #pragma unroll
@@ -271,7 +308,7 @@ k_net_resident(const unsigned char *__restrict__ image, int image_bytes, int R, 
                 res[t][j][0] = leaky(acc[t][j][0] + b0); res[t][j][1] = leaky(acc[t][j][1] + b1);
                 res[t][j][2] = leaky(acc[t][j][2] + b0); res[t][j][3] = leaky(acc[t][j][3] + b1);
             }
-        store_act<F>(X, res, lane);
+        store_act<OP, F>(X, res, lane);
         __syncwarp();
         // residual tower (model.py:45-55)
 #pragma unroll 1
@@ -279,7 +316,7 @@ k_net_resident(const unsigned char *__restrict__ image, int image_bytes, int R, 
             const uint32_t w1 = sW + (uint32_t)(ImageA<F>::stem_bytes() + (size_t)(2 * r) * ImageA<F>::conv_bytes());
             const uint32_t w2 = w1 + (uint32_t)ImageA<F>::conv_bytes();
             const float *bb1 = bias + (1 + 2 * r) * F, *bb2 = bb1 + F;
-            conv3x3<F, F>(acc, sX, w1, lane);
+            conv3x3<OP, F, F>(acc, sX, w1, lane);
 #pragma unroll
             for (int t = 0; t < 3; t++)
 #pragma unroll
@@ -288,9 +325,9 @@ k_net_resident(const unsigned char *__restrict__ image, int image_bytes, int R, 
                     acc[t][j][0] = leaky(acc[t][j][0] + b0); acc[t][j][1] = leaky(acc[t][j][1] + b1);
                     acc[t][j][2] = leaky(acc[t][j][2] + b0); acc[t][j][3] = leaky(acc[t][j][3] + b1);
                 }
-            store_act<F>(H, acc, lane);
+            store_act<OP, F>(H, acc, lane);
             __syncwarp();
-            conv3x3<F, F>(acc, sH, w2, lane);
+            conv3x3<OP, F, F>(acc, sH, w2, lane);
 #pragma unroll
             for (int t = 0; t < 3; t++)
 #pragma unroll
@@ -299,16 +336,16 @@ k_net_resident(const unsigned char *__restrict__ image, int image_bytes, int R, 
                     res[t][j][0] = leaky(acc[t][j][0] + b0 + res[t][j][0]); res[t][j][1] = leaky(acc[t][j][1] + b1 + res[t][j][1]);
                     res[t][j][2] = leaky(acc[t][j][2] + b0 + res[t][j][2]); res[t][j][3] = leaky(acc[t][j][3] + b1 + res[t][j][3]);
                 }
-            if (r + 1 < R) store_act<F>(X, res, lane);
+            if (r + 1 < R) store_act<OP, F>(X, res, lane);
             __syncwarp();
         }
-        heads<F>(res, hp, reinterpret_cast<float *>(H), out + (size_t)b * 8, lane);
+        heads<F>(res, hp, scratch, out + (size_t)b * 8, lane);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ kernel B (F = 64)
 // global image: [stem W][2R conv W][biases][head]; shared: one layer's weights + biases + head + per-warp strips
-template <int F, int WARPS>
+template <typename OP, int F, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__restrict__ c0, const u64 *__restrict__ c1,
                int n, const int *__restrict__ count, float *__restrict__ out)
@@ -324,8 +361,9 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
     unsigned char *Wbuf = smem;                                               // conv_b bytes
     float *small = reinterpret_cast<float *>(smem + conv_b);                  // biases + head
     const int small_bytes = (1 + 2 * R) * F * 4 + HEAD_FLOATS * 4;
-    unsigned char *X = smem + conv_b + small_bytes + (size_t)warp * 2 * ACT;
+    unsigned char *X = smem + conv_b + small_bytes + (size_t)warp * (2 * ACT + SCRATCH_BYTES);
     unsigned char *H = X + ACT;
+    float *scratch = reinterpret_cast<float *>(H + ACT);
     {
         const unsigned char *src = image + ImageA<F>::bias_off(R);
         for (int i = threadIdx.x; i < small_bytes / 16; i += blockDim.x)
@@ -344,10 +382,10 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
         __syncthreads();
         for (int i = threadIdx.x; i < (int)(stem_b / 16); i += blockDim.x)
             reinterpret_cast<uint4 *>(Wbuf)[i] = reinterpret_cast<const uint4 *>(image)[i];
-        if (active) write_input<F>(H, c0[b], c1[b], lane);
+        if (active) write_input<OP, F>(H, c0[b], c1[b], lane);
         __syncthreads();
         if (active) {
-            conv3x3<F, 16>(acc, sH, sW, lane);
+            conv3x3<OP, F, 16>(acc, sH, sW, lane);
 #pragma unroll
             for (int t = 0; t < 3; t++)
 #pragma unroll
@@ -356,7 +394,7 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
                     acc[t][j][0] = leaky(acc[t][j][0] + b0); acc[t][j][1] = leaky(acc[t][j][1] + b1);
                     acc[t][j][2] = leaky(acc[t][j][2] + b0); acc[t][j][3] = leaky(acc[t][j][3] + b1);
                 }
-            store_act<F>(X, acc, lane);
+            store_act<OP, F>(X, acc, lane);
         }
 #pragma unroll 1
         for (int l = 0; l < 2 * R; l++) {
@@ -368,7 +406,7 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
             if (!active) continue;
             const float *bb = bias + (1 + l) * F;
             const bool second = (l & 1);
-            conv3x3<F, F>(acc, second ? sH : sX, sW, lane);
+            conv3x3<OP, F, F>(acc, second ? sH : sX, sW, lane);
 #pragma unroll
             for (int t = 0; t < 3; t++)
 #pragma unroll
@@ -377,18 +415,18 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
                     float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
                     if (second && g != 0) {                                      // residual from the bf16 copy
                         const unsigned char *p = X + (size_t)((8 + 16 * t + g) + 1) * AS + (j * 8 + 2 * tq) * 2;
-                        float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p));
-                        float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p + 8 * AS));
+                        float2 lo = OP::unpack(*reinterpret_cast<const uint32_t *>(p));
+                        float2 hi = OP::unpack(*reinterpret_cast<const uint32_t *>(p + 8 * AS));
                         r0 = lo.x; r1 = lo.y; r2 = hi.x; r3 = hi.y;
                     }
                     acc[t][j][0] = leaky(acc[t][j][0] + b0 + r0); acc[t][j][1] = leaky(acc[t][j][1] + b1 + r1);
                     acc[t][j][2] = leaky(acc[t][j][2] + b0 + r2); acc[t][j][3] = leaky(acc[t][j][3] + b1 + r3);
                 }
             __syncwarp();
-            if (l + 1 < 2 * R) store_act<F>(second ? X : H, acc, lane);
+            if (l + 1 < 2 * R) store_act<OP, F>(second ? X : H, acc, lane);
             __syncwarp();
         }
-        if (active) heads<F>(acc, hp, reinterpret_cast<float *>(H), out + (size_t)b * 8, lane);
+        if (active) heads<F>(acc, hp, scratch, out + (size_t)b * 8, lane);
     }
 }
 
@@ -402,23 +440,35 @@ static uint16_t f2bf(float f)
     return (uint16_t)((u + r) >> 16);
 }
 
-// pack W[co][ci][ky][kx] (fp32) into [co][k = (ky*3+kx)*CINP + ci] bf16 rows of (9*CINP + 8) elements
-static void pack_conv(const float *W, int F, int cin, int cinp, uint16_t *dst)
+static uint16_t f2h(float f)
+{
+    __half h = __float2half_rn(f);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+
+// pack W[co][ci][ky][kx] (fp32) into [co][k = (ky*3+kx)*CINP + ci] 16-bit rows of (9*CINP + 8) elements
+static void pack_conv(const float *W, int F, int cin, int cinp, uint16_t *dst, bool fp16)
 {
     const int ws = 9 * cinp + 8;
     for (int co = 0; co < F; co++)
         for (int ci = 0; ci < cin; ci++)
             for (int ky = 0; ky < 3; ky++)
                 for (int kx = 0; kx < 3; kx++)
-                    dst[(size_t)co * ws + (ky * 3 + kx) * cinp + ci] = f2bf(W[((co * cin + ci) * 3 + ky) * 3 + kx]);
+                {
+                    float w = W[((co * cin + ci) * 3 + ky) * 3 + kx];
+                    dst[(size_t)co * ws + (ky * 3 + kx) * cinp + ci] = fp16 ? f2h(w) : f2bf(w);
+                }
 }
 
 template <int F, int WARPS>
-static size_t smem_resident(int R) { return ImageA<F>::total(R) + (size_t)WARPS * 2 * NPX * (F * 2 + 16); }
+static size_t smem_resident(int R) { return ImageA<F>::total(R) + (size_t)WARPS * (2 * NPX * (F * 2 + 16) + SCRATCH_BYTES); }
 template <int F, int WARPS>
 static size_t smem_streamed(int R)
 {
-    return ImageA<F>::conv_bytes() + (size_t)(1 + 2 * R) * F * 4 + HEAD_FLOATS * 4 + (size_t)WARPS * 2 * NPX * (F * 2 + 16);
+    return ImageA<F>::conv_bytes() + (size_t)(1 + 2 * R) * F * 4 + HEAD_FLOATS * 4 +
+           (size_t)WARPS * (2 * NPX * (F * 2 + 16) + SCRATCH_BYTES);
 }
 
 #define WARPS_A 8
@@ -428,7 +478,8 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
 {
     C4_REQUIRE(blob && out, "c4_net_create: null pointer");
     C4_REQUIRE(n_floats >= 4 && (int)blob[0] == 0xC4B2, "c4_net_create: bad blob magic");
-    const int F = (int)blob[1], R = (int)blob[2], n_fc = (int)blob[3];
+    const int F = (int)blob[1], R = (int)blob[2], n_fc = (int)blob[3] & 0xff;
+    const bool fp16 = ((int)blob[3] >> 8) != 1;                 // header[3] = n_fc | (operand dtype << 8): 0 fp16, 1 bf16
     C4_REQUIRE(F == 32 || F == 64, "c4_net_create: filters must be 32 or 64");
     C4_REQUIRE(R >= 1 && R <= 16, "c4_net_create: n_residuals out of range");
     const int64_t expect = 4 + (int64_t)F * 27 + F + (int64_t)2 * R * ((int64_t)F * F * 9 + F) + F + 1 + 42 * 42 + 42 +
@@ -446,12 +497,12 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
     const float *p = blob + 4;
     float *bias = reinterpret_cast<float *>(img.data() + stem_b + 2 * R * conv_b);
     float *hp = bias + (1 + 2 * R) * F;
-    pack_conv(p, F, 3, 16, reinterpret_cast<uint16_t *>(img.data()));
+    pack_conv(p, F, 3, 16, reinterpret_cast<uint16_t *>(img.data()), fp16);
     p += F * 27;
     memcpy(bias, p, F * 4);
     p += F;
     for (int l = 0; l < 2 * R; l++) {
-        pack_conv(p, F, F, F, reinterpret_cast<uint16_t *>(img.data() + stem_b + l * conv_b));
+        pack_conv(p, F, F, F, reinterpret_cast<uint16_t *>(img.data() + stem_b + l * conv_b), fp16);
         p += (size_t)F * F * 9;
         memcpy(bias + (1 + l) * F, p, F * 4);
         p += F;
@@ -471,7 +522,7 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
     memcpy(hp + HO_POLB, p, 7 * 4); p += 7;
 
     c4_net *net = new c4_net();
-    net->device = device; net->F = F; net->R = R; net->n_fc = n_fc;
+    net->device = device; net->F = F; net->R = R; net->n_fc = n_fc; net->fp16 = fp16;
     net->image_bytes = total;
     net->flops = 2.0 * (42.0 * 27 * F + 2.0 * R * 42 * 9 * F * F + 42.0 * F + (double)n_fc * 42 * 42 + 42 + 42.0 * F * 2 +
                         84.0 * 7);
@@ -479,10 +530,14 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
     C4_CUDA(cudaMemcpy(net->image, img.data(), total, cudaMemcpyHostToDevice));
     if (F == 32) {
         C4_REQUIRE((smem_resident<32, WARPS_A>(R)) <= 227 * 1024, "c4_net_create: F=32 network too deep for the resident kernel");
-        C4_CUDA(cudaFuncSetAttribute(k_net_resident<32, WARPS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        C4_CUDA(cudaFuncSetAttribute(k_net_resident<OpFP16, 32, WARPS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_resident<32, WARPS_A>(R)));
+        C4_CUDA(cudaFuncSetAttribute(k_net_resident<OpBF16, 32, WARPS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_resident<32, WARPS_A>(R)));
     } else {
-        C4_CUDA(cudaFuncSetAttribute(k_net_streamed<64, WARPS_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        C4_CUDA(cudaFuncSetAttribute(k_net_streamed<OpFP16, 64, WARPS_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_streamed<64, WARPS_B>(R)));
+        C4_CUDA(cudaFuncSetAttribute(k_net_streamed<OpBF16, 64, WARPS_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_streamed<64, WARPS_B>(R)));
     }
     *out = net;
@@ -509,12 +564,14 @@ extern "C" int c4_net_forward(c4_net *net, const uint64_t *c0, const uint64_t *c
     cudaStream_t s = (cudaStream_t)stream;
     if (net->F == 32) {
         int grid = (int)std::min<int64_t>(148, (n + WARPS_A - 1) / WARPS_A);
-        k_net_resident<32, WARPS_A><<<grid, WARPS_A * 32, smem_resident<32, WARPS_A>(net->R), s>>>(
+        auto k = net->fp16 ? k_net_resident<OpFP16, 32, WARPS_A> : k_net_resident<OpBF16, 32, WARPS_A>;
+        k<<<grid, WARPS_A * 32, smem_resident<32, WARPS_A>(net->R), s>>>(
             (const unsigned char *)net->image, (int)net->image_bytes, net->R, (const u64 *)c0, (const u64 *)c1, (int)n,
             count, out);
     } else {
         int grid = (int)std::min<int64_t>(148, (n + WARPS_B - 1) / WARPS_B);
-        k_net_streamed<64, WARPS_B><<<grid, WARPS_B * 32, smem_streamed<64, WARPS_B>(net->R), s>>>(
+        auto k = net->fp16 ? k_net_streamed<OpFP16, 64, WARPS_B> : k_net_streamed<OpBF16, 64, WARPS_B>;
+        k<<<grid, WARPS_B * 32, smem_streamed<64, WARPS_B>(net->R), s>>>(
             (const unsigned char *)net->image, net->R, (const u64 *)c0, (const u64 *)c1, (int)n, count, out);
     }
     C4_CUDA(cudaGetLastError());

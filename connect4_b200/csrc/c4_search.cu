@@ -748,8 +748,11 @@ struct c4_ctx {
     int last_pending;
     bool supplied;
     bool pool_fresh;                    // bench pool initialised
-    cudaEvent_t ev0, ev1, evn0, evn1;
+    cudaEvent_t ev0, ev1;
+    cudaEvent_t evs[2 * 64];            // sampled (start, stop) pairs around network launches
+    cudaEvent_t eva[2 * 64];            // sampled (start, stop) pairs around tree-pass launches
 };
+#define N_SAMPLES 64
 
 template <typename T>
 static int dev_alloc(c4_ctx *ctx, T **p, size_t n)
@@ -797,7 +800,7 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     ctx->net = nullptr;
     ctx->parity = 0;
     ctx->n_search = 0;
-    ctx->budget_net = getenv("C4_BUDGET") ? atoi(getenv("C4_BUDGET")) : 8;
+    ctx->budget_net = getenv("C4_BUDGET") ? atoi(getenv("C4_BUDGET")) : 2;
     ctx->last_pending = 0;
     ctx->supplied = true;
     ctx->pool_fresh = false;
@@ -830,7 +833,8 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
         c4_ctx_destroy(ctx);
         return -2;
     }
-    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->evn0); cudaEventCreate(&ctx->evn1);
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    for (int i = 0; i < 2 * N_SAMPLES; i++) { cudaEventCreate(&ctx->evs[i]); cudaEventCreate(&ctx->eva[i]); }
     rc = upload_config(ctx, cfg);
     if (rc) { c4_ctx_destroy(ctx); return rc; }
     *out = ctx;
@@ -843,7 +847,10 @@ extern "C" int c4_ctx_destroy(c4_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1); }
+    if (ctx->ev0) {
+        cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+        for (int i = 0; i < 2 * N_SAMPLES; i++) { cudaEventDestroy(ctx->evs[i]); cudaEventDestroy(ctx->eva[i]); }
+    }
     delete ctx;
     return 0;
 }
@@ -1021,17 +1028,26 @@ extern "C" int c4_search_export_tree(c4_ctx *ctx, int32_t game, void *nodes_out,
     return 0;
 }
 
-static int selfplay_passes(c4_ctx *ctx, int eval_kind, int n_passes, cudaStream_t s)
+// `sample_every` > 0: bracket every sample_every-th pass's two launches with CUDA events (at most N_SAMPLES samples)
+static int selfplay_passes(c4_ctx *ctx, int eval_kind, int n_passes, cudaStream_t s, int sample_every = 0,
+                           int *n_sampled = nullptr)
 {
-    int rc;
+    int rc, ns = 0;
     for (int k = 0; k < n_passes; k++) {
+        const bool sample = sample_every > 0 && (k % sample_every) == sample_every / 2 && ns < N_SAMPLES;
+        if (sample) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns], s));
         if (eval_kind == C4_EVAL_CENTRE) {
             if ((rc = launch_advance<true>(ctx, C4_EVAL_CENTRE, ctx->max_games, 512, s))) return rc;
+            if (sample) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], s));
         } else {
             if ((rc = launch_advance<true>(ctx, C4_EVAL_NET, ctx->max_games, ctx->budget_net, s))) return rc;
+            if (sample) { C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], s)); C4_CUDA(cudaEventRecord(ctx->evs[2 * ns], s)); }
             if ((rc = run_net(ctx, s))) return rc;
+            if (sample) C4_CUDA(cudaEventRecord(ctx->evs[2 * ns + 1], s));
         }
+        if (sample) ns++;
     }
+    if (n_sampled) *n_sampled = ns;
     return 0;
 }
 
@@ -1075,7 +1091,8 @@ extern "C" int c4_selfplay_reset(c4_ctx *ctx, void *stream)
 }
 
 extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations, int64_t *positions, int64_t *evals,
-                                 int64_t *sims, int64_t *games, float *device_ms, float *net_ms, void *stream)
+                                 int64_t *sims, int64_t *games, float *device_ms, float *net_ms, float *tree_ms,
+                                 void *stream)
 {
     C4_REQUIRE(ctx, "c4_selfplay_bench: null context");
     C4_REQUIRE(eval_kind == C4_EVAL_CENTRE || eval_kind == C4_EVAL_NET, "c4_selfplay_bench: eval_kind must be CENTRE or NET");
@@ -1100,8 +1117,10 @@ extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations,
     C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if ((rc = read_counters(ctx, &c, s))) return rc;
     before[0] = ctx->pinned[8]; before[1] = ctx->pinned[9]; before[2] = c.games_finished;
+    int n_sampled = 0;
+    const int sample_every = (net_ms || tree_ms) ? (int)std::max<int64_t>(1, iterations / N_SAMPLES) : 0;
     C4_CUDA(cudaEventRecord(ctx->ev0, s));
-    if ((rc = selfplay_passes(ctx, eval_kind, (int)iterations, s))) return rc;
+    if ((rc = selfplay_passes(ctx, eval_kind, (int)iterations, s, sample_every, &n_sampled))) return rc;
     C4_CUDA(cudaEventRecord(ctx->ev1, s));
     k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, ctx->max_games, ctx->stats_dev);
     C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -1114,7 +1133,16 @@ extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations,
     if (sims) *sims = (int64_t)(after[1] - before[1]) * ctx->cfg.simulations;
     if (games) *games = (int64_t)(after[2] - before[2]);
     if (device_ms) *device_ms = ms;
-    if (net_ms) *net_ms = 0.f;
+    // mean duration of the sampled launches (events on the launching stream)
+    float nsum = 0.f, tsum = 0.f;
+    for (int i = 0; i < n_sampled; i++) {
+        float t = 0.f;
+        if (eval_kind == C4_EVAL_NET) { C4_CUDA(cudaEventElapsedTime(&t, ctx->evs[2 * i], ctx->evs[2 * i + 1])); nsum += t; }
+        C4_CUDA(cudaEventElapsedTime(&t, ctx->eva[2 * i], ctx->eva[2 * i + 1]));
+        tsum += t;
+    }
+    if (net_ms) *net_ms = n_sampled ? nsum / n_sampled : 0.f;
+    if (tree_ms) *tree_ms = n_sampled ? tsum / n_sampled : 0.f;
     return 0;
 }
 

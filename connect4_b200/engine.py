@@ -179,10 +179,12 @@ class Engine():
     def bench(self, iterations, kind):
         k = {"centre": EVAL_CENTRE, "net": EVAL_NET}[kind]
         pos, ev, sims, games = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
-        ms, nms = C.c_float(0), C.c_float(0)
+        ms, nms, tms = C.c_float(0), C.c_float(0), C.c_float(0)
         _lib.check(self.lib.c4_selfplay_bench(self.h, k, int(iterations), C.byref(pos), C.byref(ev), C.byref(sims),
-                                              C.byref(games), C.byref(ms), C.byref(nms), _lib.stream_ptr()))
-        return dict(positions=pos.value, evals=ev.value, sims=sims.value, games=games.value, device_ms=ms.value)
+                                              C.byref(games), C.byref(ms), C.byref(nms), C.byref(tms),
+                                              _lib.stream_ptr()))
+        return dict(positions=pos.value, evals=ev.value, sims=sims.value, games=games.value, device_ms=ms.value,
+                    net_ms=nms.value, tree_ms=tms.value, iterations=int(iterations))
 
     def reset_pool(self):
         _lib.check(self.lib.c4_selfplay_reset(self.h, _lib.stream_ptr()))

@@ -64,7 +64,7 @@ def _init_state_dict(nc: NetConfig):
 
 class ModelWrapper():
     def __init__(self, config: Optional[ModelConfig] = None, file_name: Optional[str] = None, state_dict=None,
-                 device: Optional[int] = None):
+                 device: Optional[int] = None, operand_dtype: str = "fp16"):
         import torch
         _lib.require_gpu()
         self.config = config if config is not None else ModelConfig()
@@ -79,7 +79,8 @@ class ModelWrapper():
             sd = _init_state_dict(self.config.net_config)
         self.state_dict = {k: (v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))) for k, v in sd.items()}
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-        blob = fold_state_dict(self.state_dict)
+        self.operand_dtype = operand_dtype
+        blob = fold_state_dict(self.state_dict, operand_dtype)
         h = C.c_void_p()
         _lib.check(_lib.load().c4_net_create(self.device.index, blob.ctypes.data_as(C.c_void_p), blob.size, C.byref(h)))
         self.c4_net = h

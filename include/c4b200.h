@@ -64,7 +64,7 @@ int c4_board_evaluate_centre(const uint64_t *c0, const uint64_t *c1, double *val
  * 252-282, and Net.forward, model.py:120-134)
  * ------------------------------------------------------------------------------------------------------------ */
 /* `blob` (HOST, float32) is the BN-folded parameter image built by connect4_b200.neural.weights.fold_state_dict:
- *   [0] magic 0xC4B2 [1] filters F [2] n_residuals R [3] reserved, then
+ *   [0] magic 0xC4B2 [1] filters F [2] n_residuals R [3] n_fc | (operand dtype << 8) (dtype 0 = fp16, 1 = bf16), then
  *   stem W[F][3][3][3] (co,ci,ky,kx), stem b[F]; per residual conv (2R of them): W[F][F][3][3], b[F];
  *   value head: wv[F], bv; fc W[42][42] (the n_fc affine layers pre-multiplied), fc b[42]; fc1 w[42], b; w1, w2;
  *   policy head: wp[2][F], bp[2]; fc W[7][84], b[7].
@@ -72,7 +72,8 @@ int c4_board_evaluate_centre(const uint64_t *c0, const uint64_t *c1, double *val
 int c4_net_create(int device, const float *blob, int64_t n_floats, c4_net **out);
 int c4_net_destroy(c4_net *net);
 /* out[i] = {prior[0..6], value} as 8 float32 (DEVICE, 32 B per position); `count` (DEVICE int32, may be NULL)
- * overrides n with a device-side position count <= n. bf16 tensor-core tower, fp32 accumulation. */
+ * overrides n with a device-side position count <= n. 16-bit tensor-core tower (fp16 operands by default, bf16
+ * selectable in the blob header), fp32 accumulation, fp32 residual stream. */
 int c4_net_forward(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count, float *out,
                    void *stream);
 /* FLOPs (2*MAC, convs + linears) per position of this network: the roofline numerator */
@@ -165,10 +166,12 @@ int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int64_t game_id
                     int64_t *n_records_out, void *stream);
 /* Steady-state throughput mode for benchmarks: keeps every slot busy (unbounded re-seeding) for `iterations`
  * lock-step passes (one leaf batch each) and reports what was done (HOST outputs): positions = root moves played,
- * evals = network evaluations, sims = simulations.  Records are discarded.  The pool state persists across calls, so
- * warm-up calls bring it to steady state.  Device time (ms) between the first and last pass is returned too. */
+ * evals = evaluator calls, sims = simulations, games = games finished.  Records are discarded.  The pool state
+ * persists across calls, so warm-up calls bring it to steady state.  device_ms = CUDA-event time of all passes;
+ * net_ms / tree_ms = mean duration of the network launch / tree-pass launch over <= 64 evenly sampled passes
+ * (CUDA events on the launching stream; pass NULL for both to disable sampling).  Synchronises the stream. */
 int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations, int64_t *positions, int64_t *evals,
-                      int64_t *sims, int64_t *games, float *device_ms, float *net_ms, void *stream);
+                      int64_t *sims, int64_t *games, float *device_ms, float *net_ms, float *tree_ms, void *stream);
 int c4_selfplay_reset(c4_ctx *ctx, void *stream);
 
 /* Generation sink: records -> the reference's data.pth tensors with left-right flip augmentation

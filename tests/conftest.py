@@ -47,5 +47,5 @@ def random_positions(seed, n, max_plies=34):
                 break
         if ok:
             out.append((c0, c1))
-    a = np.array(out, dtype=np.uint64)
+    a = np.array(out, dtype=np.uint64).reshape(-1, 2)
     return a[:, 0].copy(), a[:, 1].copy()

@@ -256,7 +256,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(2 * n_pass + 4 * args.steps),
-            "roofline": {"kernel": "k_net_resident<OpFP16,32,8>", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+            "roofline": {"kernel": "k_net_tc<OpFP16> (tcgen05/TMEM)", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
                          "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals_per_pass,
                          "net_ms_per_launch": net_ms, "tree_ms_per_launch": tree_ms,

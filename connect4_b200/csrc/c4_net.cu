@@ -18,6 +18,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -47,6 +49,8 @@ struct c4_net {
     int device;
     int F, R, n_fc;
     bool fp16;            // operand element type of the conv GEMMs (false: bf16)
+    bool use_tc;          // tcgen05 kernel (filters == 32) instead of the mma.sync kernels
+    void *image_tc;       // device: [L][TC_WSTAGE_BYTES] weights + biases + head block
     void *image;          // device: smem image (kernel A) / per-layer weight images (kernel B)
     size_t image_bytes;
     double flops;
@@ -77,6 +81,7 @@ __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : LEAKY * x
 // same tensor-core rate ("operand precision").
 struct OpBF16 {
     static constexpr uint32_t ONE = 0x3F80u;
+    static constexpr uint32_t FMT = 1u;   // tcgen05 instruction-descriptor a/b format
     __device__ static __forceinline__ void mma(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) { mma16816(c, a, b0, b1); }
     __device__ static __forceinline__ uint32_t pack(float lo, float hi)
     {
@@ -90,6 +95,7 @@ struct OpBF16 {
 };
 struct OpFP16 {
     static constexpr uint32_t ONE = 0x3C00u;
+    static constexpr uint32_t FMT = 0u;
     __device__ static __forceinline__ void mma(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) { mma16816h(c, a, b0, b1); }
     __device__ static __forceinline__ uint32_t pack(float lo, float hi)
     {
@@ -174,6 +180,49 @@ __device__ __forceinline__ void store_act(unsigned char *buf, const float (&v)[3
         }
 }
 
+// head tails for one board (model.py:83-91,112-117): scratch[0..41] = value-conv activations, scratch[42..125] =
+// policy-conv activations (channel-major); writes {prior[7], value} to out[0..7].  One warp.
+__device__ __forceinline__ void head_tail(const float *scratch, const float *hp, float *out, int lane)
+{
+    // value: (pre-multiplied) Linear(42,42) stack -> LeakyReLU -> Linear(42,1) -> tanh -> (x + w1) * w2
+    float part = 0.f;
+    for (int i = lane; i < 42; i += 32) {
+        float a = hp[HO_FCB + i];
+#pragma unroll 6
+        for (int j = 0; j < 42; j++) a = fmaf(hp[HO_FCT + j * 42 + i], scratch[j], a);
+        part = fmaf(hp[HO_FC1W + i], leaky(a), part);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    const float value = (tanhf(part + hp[HO_FC1B]) + hp[HO_W1]) * hp[HO_W2];
+    // policy: Linear(84,7) on the channel-major flatten -> softmax
+    float lg[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) lg[k] = 0.f;
+    for (int m = lane; m < 84; m += 32) {
+        float xv = scratch[42 + m];
+#pragma unroll
+        for (int k = 0; k < 7; k++) lg[k] = fmaf(hp[HO_POLW + k * 84 + m], xv, lg[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) lg[k] += __shfl_xor_sync(0xffffffffu, lg[k], off);
+        lg[k] += hp[HO_POLB + k];
+    }
+    float mx = lg[0];
+#pragma unroll
+    for (int k = 1; k < 7; k++) mx = fmaxf(mx, lg[k]);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 7; k++) { lg[k] = expf(lg[k] - mx); sum += lg[k]; }
+    float mine = value;
+#pragma unroll
+    for (int k = 0; k < 7; k++) if (lane == k) mine = lg[k] / sum;
+    if (lane < 8) out[lane] = mine;
+    __syncwarp();
+}
+
 // value + policy heads from the fp32 trunk fragments (model.py:77-91,107-117); scratch: >= 126 floats of shared memory
 template <int F>
 __device__ __forceinline__ void heads(const float (&x)[3][F / 8][4], const float *hp, float *scratch, float *out, int lane)
@@ -217,43 +266,7 @@ __device__ __forceinline__ void heads(const float (&x)[3][F / 8][4], const float
             }
     }
     __syncwarp();
-    // value: (pre-multiplied) Linear(42,42) stack -> LeakyReLU -> Linear(42,1) -> tanh -> (x + w1) * w2
-    float part = 0.f;
-    for (int i = lane; i < 42; i += 32) {
-        float a = hp[HO_FCB + i];
-#pragma unroll 6
-        for (int j = 0; j < 42; j++) a = fmaf(hp[HO_FCT + j * 42 + i], scratch[j], a);
-        part = fmaf(hp[HO_FC1W + i], leaky(a), part);
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-    const float value = (tanhf(part + hp[HO_FC1B]) + hp[HO_W1]) * hp[HO_W2];
-    // policy: Linear(84,7) on the channel-major flatten -> softmax
-    float lg[7];
-#pragma unroll
-    for (int k = 0; k < 7; k++) lg[k] = 0.f;
-    for (int m = lane; m < 84; m += 32) {
-        float xv = scratch[42 + m];
-#pragma unroll
-        for (int k = 0; k < 7; k++) lg[k] = fmaf(hp[HO_POLW + k * 84 + m], xv, lg[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 7; k++) {
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) lg[k] += __shfl_xor_sync(0xffffffffu, lg[k], off);
-        lg[k] += hp[HO_POLB + k];
-    }
-    float mx = lg[0];
-#pragma unroll
-    for (int k = 1; k < 7; k++) mx = fmaxf(mx, lg[k]);
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < 7; k++) { lg[k] = expf(lg[k] - mx); sum += lg[k]; }
-    float mine = value;
-#pragma unroll
-    for (int k = 0; k < 7; k++) if (lane == k) mine = lg[k] / sum;
-    if (lane < 8) out[lane] = mine;
-    __syncwarp();
+    head_tail(scratch, hp, out, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel A (F = 32)
@@ -430,6 +443,376 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------ kernel C (tcgen05)
+// Blackwell-native tower for filters = 32: tcgen05.mma with TMEM accumulators, one persistent CTA per SM.
+//
+//  * STRIP: up to 16 boards stacked in one 8-wide padded pixel strip (7 row-blocks of 8 pixels per board: one shared
+//    zero row-block + 6 board rows; pixel column 0 of every row-block is a shared zero column).  112 row-blocks = 896
+//    rows = exactly 7 M-tiles of 128.
+//  * GEMM: the three dx taps are folded into N:  E_dx[r] = sum_dy A[r + 8 dy] . W[dy][dx]  is ONE accumulation chain
+//    of 3 (dy) x Cin/16 MMAs of shape M128 x N96 x K16 whose A operand is only ever shifted by +-8 rows = whole
+//    core matrices, done with the descriptor start address.  A is read 3x per conv instead of 9x, which is what
+//    makes the small-N conv tensor-bound instead of shared-memory-operand-bound (tools/umma_test.cu: 56 cycles per MMA
+//    against a 48-cycle tensor floor).  The epilogue finishes the conv:  out[q] = E_-1[q-1] + E_0[q] + E_+1[q+1],
+//    a one-lane shuffle because TMEM lane = strip row.
+//  * shared memory: activations [k-chunk][row][8 x 16-bit] (K-major, SWIZZLE_NONE core matrices; a thread's 16-byte
+//    store per k-chunk is conflict-free); weights [dy][k-chunk][n = dx*32+co][8] streamed per layer through a 3-stage
+//    ring with cp.async.bulk + mbarrier (generic in depth; 18 KB per layer).
+//  * TMEM (512 columns): fp32 residual stream of the 7 tiles (224 columns) + 3 accumulator slots of 96 columns, so
+//    the MMA warp runs up to 3 tiles ahead of the epilogue.
+//  * warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one thread), warps 2..9 = epilogue (TMEM lane
+//    quadrant = warp % 4, channel half = (warp - 2) / 4).  MMA(layer l+1, tile t) only waits for epilogue(l, tile t+1),
+//    so layers overlap tile by tile; no CTA-wide barrier inside a strip.
+#define TC_NB 16                       // boards per strip
+#define TC_T 7                         // M-tiles per full strip
+#define TC_ROWS 912                    // activation rows: 114 row-blocks (one extra zero block on each side)
+#define TC_KC 4                        // 16-byte k-chunks per pixel (32 channels)
+#define TC_NN 96                       // N = 3 dx x 32 output channels
+#define TC_ACT_BYTES (TC_KC * TC_ROWS * 16)
+#define TC_WSTAGE_BYTES (3 * TC_KC * TC_NN * 16)
+#define TC_WSTAGES 3
+#define TC_ACC_SLOTS 3
+#define TC_ACC_COL0 (TC_T * 32)
+#define TC_THREADS 576
+#define TC_EPI_WARPS 16                // 4 TMEM lane quadrants x 4 channel quarters (8 channels per thread)
+#define TC_CH 8
+
+struct TcSmem {
+    static constexpr int X = 0;
+    static constexpr int H = X + TC_ACT_BYTES;
+    static constexpr int W = H + TC_ACT_BYTES;
+    static constexpr int SMALL = W + TC_WSTAGES * TC_WSTAGE_BYTES;          // biases + head params (fp32)
+    __host__ __device__ static constexpr int scratch(int R) { return SMALL + ((1 + 2 * R) * 32 + HEAD_FLOATS) * 4; }
+    __host__ __device__ static constexpr int bars(int R) { return scratch(R) + 4 * TC_NB * 128 * 4; }   // [quarter][board][128]
+    __host__ __device__ static constexpr int total(int R) { return bars(R) + 256; }
+};
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+template <int ACC>
+__device__ __forceinline__ void umma_f16c(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *r)
+{
+    uint32_t u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                   "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                 :: "r"(taddr), "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])),
+                    "r"(__float_as_uint(r[3])), "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])),
+                    "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7])), "r"(__float_as_uint(r[8])),
+                    "r"(__float_as_uint(r[9])), "r"(__float_as_uint(r[10])), "r"(__float_as_uint(r[11])),
+                    "r"(__float_as_uint(r[12])), "r"(__float_as_uint(r[13])), "r"(__float_as_uint(r[14])),
+                    "r"(__float_as_uint(r[15])) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *r)
+{
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+                 :: "r"(taddr), "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])),
+                    "r"(__float_as_uint(r[3])), "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])),
+                    "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7])) : "memory");
+}
+#define TC_FENCE_BEFORE() asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory")
+#define TC_FENCE_AFTER() asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory")
+#define TC_PROXY_FENCE() asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory")
+#define EPI_BAR() asm volatile("bar.sync 1, 512;\n" ::: "memory")      // the 16 epilogue warps only
+
+// global image: [L layers][TC_WSTAGE_BYTES] weights, then biases [(1+2R)*32] fp32, then head block [HEAD_FLOATS] fp32
+template <typename OP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__ c0, const u64 *__restrict__ c1, int n,
+         const int *__restrict__ count, float *__restrict__ out, long long *__restrict__ dbg)
+{
+#define DBG_T(var) if (dbg) { long long _now = clock64(); var += _now - tmark; tmark = _now; }
+    long long tmark = clock64(), d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
+    extern __shared__ __align__(16) unsigned char smem[];
+    if (count) { int m = *count; n = m < n ? m : n; }
+    // static, even partition of the batch over the grid
+    const int per = n / (int)gridDim.x, extra = n % (int)gridDim.x;
+    const int my_n = per + ((int)blockIdx.x < extra ? 1 : 0);
+    const int my_first = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
+    if (my_n == 0) return;
+    const int n_strips = (my_n + TC_NB - 1) / TC_NB;
+    const int L = 1 + 2 * R;
+    // warp index through a broadcast so the compiler knows the role branches below are warp-uniform (otherwise every
+    // shuffle of the epilogue is wrapped in WARPSYNC.COLLECTIVE)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+    unsigned char *sX = smem + TcSmem::X, *sH = smem + TcSmem::H, *sW = smem + TcSmem::W;
+    float *small = reinterpret_cast<float *>(smem + TcSmem::SMALL);
+    const float *bias = small, *hp = small + L * 32;
+    float *scratch = reinterpret_cast<float *>(smem + TcSmem::scratch(R));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::bars(R));
+    const uint32_t b_wfull = smem_u32(bars), b_wempty = b_wfull + 8 * TC_WSTAGES;
+    const uint32_t b_accfull = b_wempty + 8 * TC_WSTAGES, b_accempty = b_accfull + 8 * TC_ACC_SLOTS;
+    const uint32_t b_epi = b_accempty + 8 * TC_ACC_SLOTS;                   // TC_T barriers
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_WSTAGES + 2 * TC_ACC_SLOTS + TC_T);
+
+    // ---- one-time setup: zero the strips (pad rows/columns stay zero for ever), small params, barriers, TMEM
+    for (int i = threadIdx.x; i < 2 * TC_ACT_BYTES / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(sX)[i] = make_uint4(0u, 0u, 0u, 0u);
+    {
+        const unsigned char *src = image + (size_t)L * TC_WSTAGE_BYTES;
+        const int nb16 = (L * 32 + HEAD_FLOATS) * 4 / 16;
+        for (int i = threadIdx.x; i < nb16; i += blockDim.x)
+            reinterpret_cast<uint4 *>(small)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_WSTAGES; i++) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, 1); }
+        for (int i = 0; i < TC_ACC_SLOTS; i++) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, TC_EPI_WARPS); }
+        for (int i = 0; i < TC_T; i++) mbar_init(b_epi + 8 * i, TC_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    TC_PROXY_FENCE();
+    TC_FENCE_BEFORE();
+    __syncthreads();
+    TC_FENCE_AFTER();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= weight producer: layer g of the (strip, layer) sequence -> ring stage g % 3
+        if (lane == 0) {
+            const int total = n_strips * L;
+            for (int g = 0; g < total; g++) {
+                const int st = g % TC_WSTAGES, use = g / TC_WSTAGES;
+                if (use > 0) mbar_wait(b_wempty + 8 * st, (use - 1) & 1);
+                mbar_expect_tx(b_wfull + 8 * st, TC_WSTAGE_BYTES);
+                bulk_g2s(smem_u32(sW + st * TC_WSTAGE_BYTES), image + (size_t)(g % L) * TC_WSTAGE_BYTES, TC_WSTAGE_BYTES,
+                         b_wfull + 8 * st);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)OP::FMT << 7) | ((uint32_t)OP::FMT << 10) |
+                                   ((uint32_t)(TC_NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int g = 0, c = 0;                                   // (strip, layer) counter, (strip, layer, tile) counter
+            for (int s = 0; s < n_strips; s++) {
+                const int nb = min(TC_NB, my_n - s * TC_NB);
+                const int T = (7 * nb + 15) / 16;
+                for (int l = 0; l < L; l++, g++) {
+                    const int st = g % TC_WSTAGES;
+                    mbar_wait(b_wfull + 8 * st, (g / TC_WSTAGES) & 1);
+                    DBG_T(d0)
+                    const uint32_t wbase = smem_u32(sW + st * TC_WSTAGE_BYTES);
+                    const uint32_t abase = smem_u32((l == 0 || (l & 1) == 0) ? sH : sX);   // stem and conv2 read H
+                    const uint64_t a_l = umma_desc(abase, TC_ROWS * 16, 128);      // tile 0, dy = -1: buffer row 8 - 8
+                    const uint64_t b_l = umma_desc(wbase, TC_NN * 16, 128);
+                    // epilogue arrivals seen so far on each tile barrier: (L + 1) per finished strip, l + 1 needed now
+                    const uint32_t ep_par = (uint32_t)(s * (L + 1) + l) & 1u;
+                    for (int t = 0; t < T; t++, c++) {
+                        mbar_wait(b_epi + 8 * min(t + 1, T - 1), ep_par);
+                        DBG_T(d1)
+                        const int slot = c % TC_ACC_SLOTS, use = c / TC_ACC_SLOTS;
+                        if (use > 0) mbar_wait(b_accempty + 8 * slot, (use - 1) & 1);
+                        DBG_T(d2)
+                        TC_FENCE_AFTER();
+                        const uint32_t d = tmem + TC_ACC_COL0 + slot * TC_NN;
+                        // descriptors advance by adding 16-byte units to the start-address field:
+                        //   A: +8 per dy (8 rows), +2*TC_ROWS per 16-channel k-step;  B: +kc*96 per dy, +2*96 per k-step
+                        const uint64_t a = a_l + (uint64_t)(128 * t);
+                        if (l != 0) {
+                            umma_f16c<0>(d, a, b_l, idesc);
+                            umma_f16c<1>(d, a + 2 * TC_ROWS, b_l + 2 * TC_NN, idesc);
+                            umma_f16c<1>(d, a + 8, b_l + 4 * TC_NN, idesc);
+                            umma_f16c<1>(d, a + 8 + 2 * TC_ROWS, b_l + 6 * TC_NN, idesc);
+                            umma_f16c<1>(d, a + 16, b_l + 8 * TC_NN, idesc);
+                            umma_f16c<1>(d, a + 16 + 2 * TC_ROWS, b_l + 10 * TC_NN, idesc);
+                        } else {
+                            umma_f16c<0>(d, a, b_l, idesc);
+                            umma_f16c<1>(d, a + 8, b_l + 2 * TC_NN, idesc);
+                            umma_f16c<1>(d, a + 16, b_l + 4 * TC_NN, idesc);
+                        }
+                        umma_commit(b_accfull + 8 * slot);
+                        DBG_T(d3)
+                    }
+                    umma_commit(b_wempty + 8 * st);
+                }
+            }
+            if (dbg && blockIdx.x == 0) { dbg[0] = d0; dbg[1] = d1; dbg[2] = d2; dbg[3] = d3; }
+        }
+    } else {
+        // ================= epilogue warps
+        const int e = warp - 2, quad = warp & 3, qtr = e >> 2;               // channels [8 qtr, 8 qtr + 8)
+        const int et = threadIdx.x - 64;                                     // 0..511
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
+        int c = 0;
+        for (int s = 0; s < n_strips; s++) {
+            const int nb = min(TC_NB, my_n - s * TC_NB);
+            const int T = (7 * nb + 15) / 16;
+            const int first = my_first + s * TC_NB;
+            // ---- input planes (Board.to_array) -> channels 0..15 of H
+            for (int i = et; i < nb * 42; i += 32 * TC_EPI_WARPS) {
+                const int b = i / 42, px = i - b * 42, r = px / 7, col = px - r * 7;
+                const u64 a0 = c0[first + b], a1 = c1[first + b];
+                const int bit = 7 * col + (5 - r);
+                const uint32_t tomove = ((__popcll(a0 | a1) & 1) == 0) ? OP::ONE : 0u;
+                const uint32_t o = (uint32_t)((a0 >> bit) & 1ULL) * OP::ONE, x = (uint32_t)((a1 >> bit) & 1ULL) * OP::ONE;
+                const int row = 8 + (7 * b + 1 + r) * 8 + (col + 1);
+                *reinterpret_cast<uint4 *>(sH + (size_t)row * 16) = make_uint4(tomove | (o << 16), x, 0u, 0u);
+                *reinterpret_cast<uint4 *>(sH + (size_t)(TC_ROWS + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            TC_PROXY_FENCE();
+            EPI_BAR();
+            if (lane == 0)
+                for (int t = 0; t < T; t++) mbar_arrive(b_epi + 8 * t);
+
+            for (int l = 0; l < L; l++) {
+                const bool to_res = (l == 0) || ((l & 1) == 0);               // stem / conv2: result is the residual stream
+                const bool add_res = (l != 0) && ((l & 1) == 0);
+                const bool last = (l == L - 1);
+                unsigned char *dst = (to_res ? sX : sH) + (size_t)qtr * TC_ROWS * 16;   // this quarter = one k-chunk
+                float bl[TC_CH];
+#pragma unroll
+                for (int j = 0; j < TC_CH; j++) bl[j] = bias[l * 32 + TC_CH * qtr + j];
+                for (int t = 0; t < T; t++, c++) {
+                    const int slot = c % TC_ACC_SLOTS;
+                    DBG_T(d4)
+                    mbar_wait(b_accfull + 8 * slot, (c / TC_ACC_SLOTS) & 1);
+                    DBG_T(d0)
+                    TC_FENCE_AFTER();
+                    const uint32_t ta = tmem + lane_base + TC_ACC_COL0 + slot * TC_NN + TC_CH * qtr;
+                    const uint32_t tr = tmem + lane_base + 32 * t + TC_CH * qtr;
+                    float em[TC_CH], ez[TC_CH], ep[TC_CH], rs[TC_CH];
+                    tmem_ld8(ta, em);
+                    tmem_ld8(ta + 32, ez);
+                    tmem_ld8(ta + 64, ep);
+                    if (add_res) tmem_ld8(tr, rs);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                    DBG_T(d1)
+                    TC_FENCE_BEFORE();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b_accempty + 8 * slot);        // accumulator slot free for the MMA warp
+                    DBG_T(d5)
+                    const int srow = 128 * t + 32 * quad + lane;              // strip row
+                    const int rb = srow >> 3, col8 = srow & 7;
+                    const int b = rb / 7;
+                    const bool valid = (col8 != 0) && (rb - 7 * b != 0) && (b < nb);
+                    // out[q] = E_-1[q-1] + E_0[q] + E_+1[q+1].  Rotating shuffles need no edge fix-up: lane 0 is a pad-column
+                    // row (its result is discarded) and lane 31 wraps to lane 0 whose E is exactly 0 (A is zero on pad rows).
+                    float v[TC_CH];
+#pragma unroll
+                    for (int j = 0; j < TC_CH; j++) {
+                        float m1 = __shfl_sync(0xffffffffu, em[j], lm);
+                        float p1 = __shfl_sync(0xffffffffu, ep[j], lp);
+                        float y = (m1 + ez[j]) + (p1 + bl[j]);
+                        if (add_res) y += rs[j];
+                        v[j] = fmaxf(y, LEAKY * y);
+                    }
+                    DBG_T(d6)
+                    if (to_res && !last) tmem_st8(tr, v);
+                    DBG_T(d7)
+                    if (valid && !last)
+                        *reinterpret_cast<uint4 *>(dst + (size_t)(8 + srow) * 16) =
+                            make_uint4(OP::pack(v[0], v[1]), OP::pack(v[2], v[3]), OP::pack(v[4], v[5]), OP::pack(v[6], v[7]));
+                    if (last && valid) {
+                        // head 1x1 convs (model.py:77-79,107-109): this thread's 8 channels of one pixel; the four channel
+                        // quarters are summed in a fixed order by head tail below (deterministic, no atomics)
+                        float a = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < TC_CH; j++) {
+                            a = fmaf(v[j], hp[HO_VW + TC_CH * qtr + j], a);
+                            p0 = fmaf(v[j], hp[HO_PW + TC_CH * qtr + j], p0);
+                            p1 = fmaf(v[j], hp[HO_PW + 32 + TC_CH * qtr + j], p1);
+                        }
+                        float *sc = scratch + (qtr * TC_NB + b) * 128 + (rb - 7 * b - 1) * 7 + (col8 - 1);
+                        sc[0] = a; sc[42] = p0; sc[84] = p1;
+                    }
+                    DBG_T(d2)
+                    if (to_res && !last) asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                    TC_PROXY_FENCE();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b_epi + 8 * t);
+                    DBG_T(d3)
+                }
+            }
+            // ---- head tails: one warp per board
+            if (dbg && blockIdx.x == 0 && e == 0 && lane == 0 && s == n_strips - 1) {
+                dbg[8] = d0; dbg[9] = d1; dbg[10] = d2; dbg[11] = d3; dbg[12] = d4; dbg[13] = d5; dbg[14] = d6; dbg[15] = d7;
+            }
+            EPI_BAR();
+            for (int b = e; b < nb; b += TC_EPI_WARPS) {
+                float *sc = scratch + b * 128;
+                for (int i = lane; i < 126; i += 32) {
+                    float bb = i < 42 ? hp[HO_VB] : (i < 84 ? hp[HO_PB] : hp[HO_PB + 1]);
+                    float x = ((sc[i] + sc[TC_NB * 128 + i]) + sc[2 * TC_NB * 128 + i]) + sc[3 * TC_NB * 128 + i];
+                    sc[i] = leaky(x + bb);
+                }
+                __syncwarp();
+                head_tail(sc, hp, out + (size_t)(first + b) * 8, lane);
+            }
+            EPI_BAR();
+        }
+    }
+    TC_FENCE_BEFORE();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static uint16_t f2bf(float f)
 {
@@ -479,7 +862,8 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
     C4_REQUIRE(blob && out, "c4_net_create: null pointer");
     C4_REQUIRE(n_floats >= 4 && (int)blob[0] == 0xC4B2, "c4_net_create: bad blob magic");
     const int F = (int)blob[1], R = (int)blob[2], n_fc = (int)blob[3] & 0xff;
-    const bool fp16 = ((int)blob[3] >> 8) != 1;                 // header[3] = n_fc | (operand dtype << 8): 0 fp16, 1 bf16
+    const bool fp16 = (((int)blob[3] >> 8) & 0xff) != 1;        // header[3] = n_fc | (operand dtype << 8) | (kernel << 16)
+    const int kernel_sel = ((int)blob[3] >> 16) & 0xff;         // 0 = auto (tcgen05 when filters == 32), 1 = mma.sync
     C4_REQUIRE(F == 32 || F == 64, "c4_net_create: filters must be 32 or 64");
     C4_REQUIRE(R >= 1 && R <= 16, "c4_net_create: n_residuals out of range");
     const int64_t expect = 4 + (int64_t)F * 27 + F + (int64_t)2 * R * ((int64_t)F * F * 9 + F) + F + 1 + 42 * 42 + 42 +
@@ -528,6 +912,33 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
                         84.0 * 7);
     if (cudaMalloc(&net->image, total) != cudaSuccess) { delete net; c4_set_error("cudaMalloc failed"); return -2; }
     C4_CUDA(cudaMemcpy(net->image, img.data(), total, cudaMemcpyHostToDevice));
+    net->use_tc = (F == 32) && kernel_sel != 1 && TcSmem::total(R) <= 227 * 1024;
+    net->image_tc = nullptr;
+    if (net->use_tc) {
+        // tcgen05 image: per layer [dy][k-chunk][n = dx*32 + co][8 ci] 16-bit, K-major SWIZZLE_NONE core matrices
+        const int L = 1 + 2 * R;
+        const size_t small_bytes = (size_t)(L * 32 + HEAD_FLOATS) * 4;
+        std::vector<unsigned char> tc((size_t)L * TC_WSTAGE_BYTES + small_bytes, 0);
+        const float *q = blob + 4;
+        for (int l = 0; l < L; l++) {
+            const int cin = l == 0 ? 3 : 32, kc = l == 0 ? 2 : TC_KC;
+            uint16_t *dst = reinterpret_cast<uint16_t *>(tc.data() + (size_t)l * TC_WSTAGE_BYTES);
+            for (int co = 0; co < 32; co++)
+                for (int ci = 0; ci < cin; ci++)
+                    for (int ky = 0; ky < 3; ky++)
+                        for (int kx = 0; kx < 3; kx++) {
+                            float w = q[((co * cin + ci) * 3 + ky) * 3 + kx];
+                            size_t idx = ((size_t)(ky * kc + ci / 8) * TC_NN + (kx * 32 + co)) * 8 + (ci % 8);
+                            dst[idx] = fp16 ? f2h(w) : f2bf(w);
+                        }
+            q += (size_t)32 * cin * 9 + 32;
+        }
+        memcpy(tc.data() + (size_t)L * TC_WSTAGE_BYTES, bias, small_bytes);     // biases + head block, as in image A
+        if (cudaMalloc(&net->image_tc, tc.size()) != cudaSuccess) { delete net; c4_set_error("cudaMalloc failed"); return -2; }
+        C4_CUDA(cudaMemcpy(net->image_tc, tc.data(), tc.size(), cudaMemcpyHostToDevice));
+        C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(R)));
+        C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(R)));
+    }
     if (F == 32) {
         C4_REQUIRE((smem_resident<32, WARPS_A>(R)) <= 227 * 1024, "c4_net_create: F=32 network too deep for the resident kernel");
         C4_CUDA(cudaFuncSetAttribute(k_net_resident<OpFP16, 32, WARPS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -549,6 +960,7 @@ extern "C" int c4_net_destroy(c4_net *net)
     if (!net) return 0;
     cudaSetDevice(net->device);
     cudaFree(net->image);
+    if (net->image_tc) cudaFree(net->image_tc);
     delete net;
     return 0;
 }
@@ -562,7 +974,22 @@ extern "C" int c4_net_forward(c4_net *net, const uint64_t *c0, const uint64_t *c
     C4_REQUIRE(n >= 0 && n < (1LL << 31), "c4_net_forward: n out of range");
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (net->F == 32) {
+    if (net->use_tc) {
+        int grid = (int)std::min<int64_t>(148, n);
+        auto k = net->fp16 ? k_net_tc<OpFP16> : k_net_tc<OpBF16>;
+        static long long *dbg = nullptr;
+        static bool dbg_on = getenv("C4_TC_DEBUG") != nullptr;
+        if (dbg_on && !dbg) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
+        k<<<grid, TC_THREADS, TcSmem::total(net->R), s>>>((const unsigned char *)net->image_tc, net->R, (const u64 *)c0,
+                                                         (const u64 *)c1, (int)n, count, out, dbg);
+        if (dbg_on) {
+            long long h[16];
+            cudaStreamSynchronize(s);
+            cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[tc dbg] mma: wait_w %lld wait_epi %lld wait_accempty %lld issue %lld | epi warp0: wait_accfull %lld ld %lld "
+                            "sts/heads %lld store-wait+fence %lld loop %lld | arrive_accempty %lld shfl+fp %lld sttm %lld\n", h[0], h[1], h[2], h[3], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
+        }
+    } else if (net->F == 32) {
         int grid = (int)std::min<int64_t>(148, (n + WARPS_A - 1) / WARPS_A);
         auto k = net->fp16 ? k_net_resident<OpFP16, 32, WARPS_A> : k_net_resident<OpBF16, 32, WARPS_A>;
         k<<<grid, WARPS_A * 32, smem_resident<32, WARPS_A>(net->R), s>>>(

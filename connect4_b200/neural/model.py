@@ -64,7 +64,7 @@ def _init_state_dict(nc: NetConfig):
 
 class ModelWrapper():
     def __init__(self, config: Optional[ModelConfig] = None, file_name: Optional[str] = None, state_dict=None,
-                 device: Optional[int] = None, operand_dtype: str = "fp16"):
+                 device: Optional[int] = None, operand_dtype: str = "fp16", kernel: str = "auto"):
         import torch
         _lib.require_gpu()
         self.config = config if config is not None else ModelConfig()
@@ -80,7 +80,8 @@ class ModelWrapper():
         self.state_dict = {k: (v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))) for k, v in sd.items()}
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.operand_dtype = operand_dtype
-        blob = fold_state_dict(self.state_dict, operand_dtype)
+        self.kernel = kernel
+        blob = fold_state_dict(self.state_dict, operand_dtype, kernel)
         h = C.c_void_p()
         _lib.check(_lib.load().c4_net_create(self.device.index, blob.ctypes.data_as(C.c_void_p), blob.size, C.byref(h)))
         self.c4_net = h

@@ -64,7 +64,8 @@ int c4_board_evaluate_centre(const uint64_t *c0, const uint64_t *c1, double *val
  * 252-282, and Net.forward, model.py:120-134)
  * ------------------------------------------------------------------------------------------------------------ */
 /* `blob` (HOST, float32) is the BN-folded parameter image built by connect4_b200.neural.weights.fold_state_dict:
- *   [0] magic 0xC4B2 [1] filters F [2] n_residuals R [3] n_fc | (operand dtype << 8) (dtype 0 = fp16, 1 = bf16), then
+ *   [0] magic 0xC4B2 [1] filters F [2] n_residuals R [3] n_fc | (operand dtype << 8) | (kernel << 16)
+ *       (dtype 0 = fp16, 1 = bf16; kernel 0 = auto: tcgen05 tower for F = 32, 1 = force the mma.sync kernels), then
  *   stem W[F][3][3][3] (co,ci,ky,kx), stem b[F]; per residual conv (2R of them): W[F][F][3][3], b[F];
  *   value head: wv[F], bv; fc W[42][42] (the n_fc affine layers pre-multiplied), fc b[42]; fc1 w[42], b; w1, w2;
  *   policy head: wp[2][F], bp[2]; fc W[7][84], b[7].

@@ -136,3 +136,27 @@ def test_bf16_operand_mode_is_selectable_and_less_accurate():
     eb = np.abs(vb.cpu().numpy() - g["value"])
     print("fp16 max %.2e mean %.2e | bf16 max %.2e mean %.2e" % (e16.max(), e16.mean(), eb.max(), eb.mean()))
     assert e16.max() < TOL and eb.mean() < 5e-3 and eb.max() < 0.1 and e16.mean() < eb.mean()
+
+
+def test_tcgen05_and_mma_sync_kernels_agree():
+    """the default tcgen05/TMEM tower and the mma.sync tower are two independent implementations of the same math:
+    both within tolerance of the reference, and within 2.5e-3 of each other (different fp32 summation order)"""
+    import torch
+    from oracle import net_ref as nr
+    from connect4_b200.neural.model import ModelWrapper
+    g = golden("net_outputs.npz")
+    sd = nr.load_golden_state(os.path.join(GOLDEN, "example_net_state.npz"))
+    tc = ModelWrapper(state_dict=sd, kernel="auto")
+    mma = ModelWrapper(state_dict=sd, kernel="mma")
+    for n in (1, 15, 16, 17, 147, 148, 149, 1536):
+        v1, p1 = tc.evaluate_bitboards(g["c0"][:n], g["c1"][:n])
+        v2, p2 = mma.evaluate_bitboards(g["c0"][:n], g["c1"][:n])
+        v1, p1, v2, p2 = v1.cpu().numpy(), p1.cpu().numpy(), v2.cpu().numpy(), p2.cpu().numpy()
+        assert np.abs(v1 - g["value"][:n]).max() < TOL and np.abs(p1 - g["prior"][:n]).max() < TOL
+        assert np.abs(v2 - g["value"][:n]).max() < TOL and np.abs(p2 - g["prior"][:n]).max() < TOL
+        assert np.abs(v1 - v2).max() < 2.5e-3 and np.abs(p1 - p2).max() < 2.5e-3
+    # a position's result does not depend on where in the batch (strip / tile / CTA) it is evaluated
+    perm = np.random.RandomState(0).permutation(1536)
+    v3, p3 = tc.evaluate_bitboards(g["c0"][perm], g["c1"][perm])
+    v1, p1 = tc.evaluate_bitboards(g["c0"], g["c1"])
+    assert torch.equal(v3, v1[torch.as_tensor(perm).cuda()]) and torch.equal(p3, p1[torch.as_tensor(perm).cuda()])

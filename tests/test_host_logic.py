@@ -65,7 +65,7 @@ def _blob_forward(blob, planes):
     import torch.nn.functional as F
     t = torch.as_tensor(blob)
     Fi, R = int(blob[1]), int(blob[2])
-    assert int(blob[3]) >> 8 == 0                   # default operand dtype: fp16
+    assert int(blob[3]) >> 8 == 0                   # default operand dtype fp16, kernel auto
     pos = [4]
 
     def take(*shape):

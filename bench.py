@@ -201,6 +201,7 @@ def main():
             tot[k] += r[k]
         tot["net_ms"] += r["net_ms"]
         tot["tree_ms"] += r["tree_ms"]
+        pools = r["pools"]
     barrier()
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if sampler else None
@@ -241,7 +242,7 @@ def main():
         peak_tf, peak_hbm, peak_src = peaks()
         flops = model.flops_per_position
         n_pass = args.steps * args.passes
-        evals_per_pass = tot["evals"] / n_pass
+        evals_per_pass = tot["evals"] / (n_pass * pools)          # per network launch (one launch per half pool per pass)
         net_ms = tot["net_ms"] / args.steps
         tree_ms = tot["tree_ms"] / args.steps
         achieved = (evals_per_pass * flops) / (net_ms * 1e-3) / 1e12 if net_ms > 0 else None
@@ -255,12 +256,13 @@ def main():
                              (args.games * (SIMS + 2) * 256 / 1e6)},
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": int(2 * n_pass + 4 * args.steps),
+            "gpu_launches": int(2 * pools * n_pass + 4 * args.steps),
             "roofline": {"kernel": "k_net_tc<OpFP16> (tcgen05/TMEM)", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
                          "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals_per_pass,
                          "net_ms_per_launch": net_ms, "tree_ms_per_launch": tree_ms,
-                         "net_share_of_step": (net_ms * n_pass / args.steps) / (1000.0 * secs / args.steps) if secs else None},
+                         "half_pools": pools,
+                         "net_share_of_step": (net_ms * pools * n_pass / args.steps) / (1000.0 * secs / args.steps) if secs else None},
             "sims_per_sec": value * SIMS, "evals_per_sec": evals / secs, "games_finished": games,
             "wall_s_timed_region": t_wall,
         }

@@ -50,6 +50,7 @@ SIGNATURES = {
     "c4_ctx_destroy": (C.c_int, [vp]),
     "c4_ctx_set_config": (C.c_int, [vp, C.POINTER(MCTSConfigC)]),
     "c4_ctx_set_net": (C.c_int, [vp, vp]),
+    "c4_ctx_get": (C.c_int, [vp, C.c_int]),
     "c4_ctx_set_rng": (C.c_int, [vp, C.c_int, C.c_uint64, vp, vp, C.c_int]),
     "c4_search_begin": (C.c_int, [vp, vp, vp, C.c_int32, vp]),
     "c4_search_pending": (C.c_int, [vp, vp, vp, vp, C.POINTER(C.c_int32), vp]),

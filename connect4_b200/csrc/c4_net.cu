@@ -579,8 +579,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__ c0, const u64 *__restrict__ c1, int n,
          const int *__restrict__ count, float *__restrict__ out, long long *__restrict__ dbg)
 {
+#ifdef C4_TC_PROFILE   // per-role cycle accounting (build with -DC4_TC_PROFILE, run with C4_TC_DEBUG=1)
 #define DBG_T(var) if (dbg) { long long _now = clock64(); var += _now - tmark; tmark = _now; }
     long long tmark = clock64(), d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
+#else
+#define DBG_T(var)
+    const long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
+#endif
     extern __shared__ __align__(16) unsigned char smem[];
     if (count) { int m = *count; n = m < n ? m : n; }
     // static, even partition of the batch over the grid
@@ -751,14 +756,18 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                     const bool valid = (col8 != 0) && (rb - 7 * b != 0) && (b < nb);
                     // out[q] = E_-1[q-1] + E_0[q] + E_+1[q+1].  Rotating shuffles need no edge fix-up: lane 0 is a pad-column
                     // row (its result is discarded) and lane 31 wraps to lane 0 whose E is exactly 0 (A is zero on pad rows).
+                    // packed fp32x2 adds / muls (FADD2 / FMUL2 on sm_100): the epilogue is FP32-pipe bound
                     float v[TC_CH];
 #pragma unroll
-                    for (int j = 0; j < TC_CH; j++) {
-                        float m1 = __shfl_sync(0xffffffffu, em[j], lm);
-                        float p1 = __shfl_sync(0xffffffffu, ep[j], lp);
-                        float y = (m1 + ez[j]) + (p1 + bl[j]);
-                        if (add_res) y += rs[j];
-                        v[j] = fmaxf(y, LEAKY * y);
+                    for (int j = 0; j < TC_CH; j += 2) {
+                        float2 m1 = make_float2(__shfl_sync(0xffffffffu, em[j], lm), __shfl_sync(0xffffffffu, em[j + 1], lm));
+                        float2 p1 = make_float2(__shfl_sync(0xffffffffu, ep[j], lp), __shfl_sync(0xffffffffu, ep[j + 1], lp));
+                        float2 y = __fadd2_rn(__fadd2_rn(m1, make_float2(ez[j], ez[j + 1])),
+                                              __fadd2_rn(p1, make_float2(bl[j], bl[j + 1])));
+                        if (add_res) y = __fadd2_rn(y, make_float2(rs[j], rs[j + 1]));
+                        float2 z = __fmul2_rn(y, make_float2(LEAKY, LEAKY));
+                        v[j] = fmaxf(y.x, z.x);
+                        v[j + 1] = fmaxf(y.y, z.y);
                     }
                     DBG_T(d6)
                     if (to_res && !last) tmem_st8(tr, v);
@@ -814,6 +823,8 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+int c4_net_forward_ex(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count, float *out,
+                      void *stream, int max_ctas);
 static uint16_t f2bf(float f)
 {
     uint32_t u;
@@ -970,12 +981,19 @@ extern "C" double c4_net_flops_per_position(const c4_net *net) { return net ? ne
 extern "C" int c4_net_forward(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count,
                               float *out, void *stream)
 {
+    return c4_net_forward_ex(net, c0, c1, n, count, out, stream, 148);
+}
+
+// internal: same, with a cap on the number of CTAs (the self-play engine leaves SMs to the concurrent tree pass)
+int c4_net_forward_ex(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count, float *out,
+                      void *stream, int max_ctas)
+{
     C4_REQUIRE(net && (n == 0 || (c0 && c1 && out)), "c4_net_forward: null pointer");
     C4_REQUIRE(n >= 0 && n < (1LL << 31), "c4_net_forward: n out of range");
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (net->use_tc) {
-        int grid = (int)std::min<int64_t>(148, n);
+        int grid = (int)std::min<int64_t>(std::max(1, std::min(max_ctas, 148)), n);
         auto k = net->fp16 ? k_net_tc<OpFP16> : k_net_tc<OpBF16>;
         static long long *dbg = nullptr;
         static bool dbg_on = getenv("C4_TC_DEBUG") != nullptr;

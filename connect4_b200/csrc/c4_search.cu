@@ -39,14 +39,14 @@ struct C4Counters {
     unsigned long long n_records;
     unsigned long long n_done;          // stand-alone searches finished
     unsigned long long overflow;        // records dropped (records_out too small)
-    int leaf_count[2];                  // ping-pong leaf batch counters
-    int pad[2];
+    int leaf_count[2][2];               // [pool][parity] ping-pong leaf batch counters
 };
 
 struct C4Dev {
     C4Node *pool;
     int blocks_per_game;
     const double *pbc;                  // pbc[N] = log((N + base + 1)/base) + init
+    const double *sqt;                  // sqt[N] = sqrt(N)  (correctly rounded, = math.sqrt)
     int sims;
     double frac, one_minus_frac;
     float one_minus_frac_f;
@@ -74,6 +74,7 @@ struct C4Dev {
     const double *ext_value;            // [G]
     const void *ext_prior;              // [G][7] fp64 or fp32
     int ext_prior_dtype;
+    long long cycle_limit;              // a warp starts no further descent in a pass after this many SM cycles (0 = off)
     // self-play control
     C4Counters *ctr;
     long long n_games_target;
@@ -275,7 +276,7 @@ __device__ __forceinline__ Leaf descend(const C4Dev &d, const Game &G)
         const bool exists = (lane < 7) && (a.meta & C4_META_EXISTS);
         // ucb_score: pb_c = (log((N+base+1)/base)+init) * (sqrt(N)/(n+1)); score = pb_c*prior + value
         const double pbc = d.pbc[visits];
-        const double sq = __dsqrt_rn((double)visits);
+        const double sq = d.sqt[visits];                  // sqrt is exact in IEEE: table == __dsqrt_rn == math.sqrt
         double score = -1.0;
         if (exists) {
             double pb = __dmul_rn(pbc, __ddiv_rn(sq, (double)(a.visits + 1u)));
@@ -376,11 +377,11 @@ __device__ __forceinline__ int sample_child(double v, bool exists, int lane, dou
     return 31 - __clz(m);
 }
 
-__device__ __forceinline__ void emit_request(const C4Dev &d, Game &G, int parity, u64 c0, u64 c1, uint32_t node,
-                                             int path_len, uint32_t path_lo, uint32_t path_hi)
+__device__ __forceinline__ void emit_request(const C4Dev &d, Game &G, int pool, int g0, int parity, u64 c0, u64 c1,
+                                             uint32_t node, int path_len, uint32_t path_lo, uint32_t path_hi)
 {
     int slot = 0;
-    if (G.lane == 0) slot = atomicAdd(&d.ctr->leaf_count[parity], 1);
+    if (G.lane == 0) slot = g0 + atomicAdd(&d.ctr->leaf_count[pool][parity], 1);   // a pool's batch lives at [g0, g0 + n)
     slot = __shfl_sync(FULL, slot, 0);
     if (G.lane == 0) {
         d.leaf_c0[slot] = c0; d.leaf_c1[slot] = c1; d.leaf_game[slot] = G.g;
@@ -478,12 +479,14 @@ __device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
 // ------------------------------------------------------------------------------------------------ the pass kernel
 // MODE: C4_EVAL_EXTERNAL / C4_EVAL_CENTRE / C4_EVAL_NET.  One warp per game slot.
 template <int MODE, bool SELFPLAY>
-__global__ void __launch_bounds__(128) k_advance(C4Dev d, int n_games, int parity, int budget)
+__global__ void __launch_bounds__(128, 8) k_advance(C4Dev d, int g0, int n_games, int pool, int parity, int budget)
 {
-    const int g = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int gi = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int g = g0 + gi;
     const int lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.ctr->leaf_count[parity ^ 1] = 0;
-    if (g >= n_games) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.ctr->leaf_count[pool][parity ^ 1] = 0;
+    if (gi >= n_games) return;
+    const long long t_start = clock64();
     int st = d.status[g];
     if (st == ST_IDLE || st == ST_DONE) return;
 
@@ -534,6 +537,7 @@ __global__ void __launch_bounds__(128) k_advance(C4Dev d, int n_games, int parit
         st = ST_READY;
     }
 
+    bool first_descent_done = false;
     for (;;) {
         if (st == ST_NEWROOT) {
             // Tree(board) + evaluate root (oinkoink/mcts.py:98-105): fresh pool, root = node 0 of block 0
@@ -548,7 +552,7 @@ __global__ void __launch_bounds__(128) k_advance(C4Dev d, int n_games, int parit
                 if (lane == 0) d.stat_evals[g] += 1ULL;
                 st = ST_READY;
             } else {
-                emit_request(d, G, parity, G.c0, G.c1, 0u, 0, 0u, 0u);
+                emit_request(d, G, pool, g0, parity, G.c0, G.c1, 0u, 0, 0u, 0u);
                 st = ST_WAIT;
                 break;
             }
@@ -564,6 +568,10 @@ __global__ void __launch_bounds__(128) k_advance(C4Dev d, int n_games, int parit
             continue;
         }
         if (budget-- <= 0) break;
+        // bound the tail of the pass: the first descent is always allowed, later ones (after terminal re-visits) only
+        // while the warp is inside its cycle budget
+        if (d.cycle_limit > 0 && first_descent_done && clock64() - t_start > d.cycle_limit) break;
+        first_descent_done = true;
         Leaf L = descend(d, G);
         if (L.meta & C4_META_TERMINAL) {
             // terminal branch of evaluate_node (mcts.py:125-128) + backpropagate: leaf and all ancestors get the result
@@ -579,7 +587,7 @@ __global__ void __launch_bounds__(128) k_advance(C4Dev d, int n_games, int parit
             G.sims_done++;
             continue;
         }
-        emit_request(d, G, parity, L.c0, L.c1, L.node, L.depth + 1, L.path_lo, L.path_hi);
+        emit_request(d, G, pool, g0, parity, L.c0, L.c1, L.node, L.depth + 1, L.path_lo, L.path_hi);
         st = ST_WAIT;
         break;
     }
@@ -596,7 +604,7 @@ __global__ void k_search_begin(C4Dev d, const u64 *c0, const u64 *c1, int n, int
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) {
-        d.ctr->leaf_count[0] = 0; d.ctr->leaf_count[1] = 0;
+        d.ctr->leaf_count[0][0] = 0; d.ctr->leaf_count[0][1] = 0; d.ctr->leaf_count[1][0] = 0; d.ctr->leaf_count[1][1] = 0;
         d.ctr->n_done = 0;
     }
     if (g >= max_games) return;
@@ -614,7 +622,7 @@ __global__ void k_selfplay_init(C4Dev d, int max_games)
 {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) {
-        d.ctr->leaf_count[0] = 0; d.ctr->leaf_count[1] = 0;
+        d.ctr->leaf_count[0][0] = 0; d.ctr->leaf_count[0][1] = 0; d.ctr->leaf_count[1][0] = 0; d.ctr->leaf_count[1][1] = 0;
         d.ctr->games_finished = 0; d.ctr->n_records = 0; d.ctr->overflow = 0; d.ctr->n_done = 0;
         long long first = d.n_games_target < (long long)max_games ? d.n_games_target : (long long)max_games;
         d.ctr->next_game = (unsigned long long)first;
@@ -737,12 +745,18 @@ struct c4_ctx {
     c4_net *net;
     std::vector<void *> allocs;
     double *pbc_dev;
+    double *sqt_dev;
     float *net_out;
     double *ext_value;
     void *ext_prior;
     unsigned long long *stats_dev;      // [2]
     unsigned long long *pinned;         // host pinned scratch (8 words)
-    int parity;
+    int parity;                         // single-pool paths (stand-alone searches)
+    int pool_parity[2];                 // self-play half pools
+    int n_pools;                        // 2: the tree pass of one half overlaps the network launch of the other
+    int net_ctas;                       // CTA cap of a half-pool network launch (leaves SMs for the concurrent tree pass)
+    cudaStream_t pool_stream[2];
+    cudaEvent_t ev_fork, ev_join[2];
     int n_search;                       // searches started by the last c4_search_begin
     int budget_net;                     // terminal re-visits a game may play through per pass (NET / EXTERNAL)
     int last_pending;
@@ -770,10 +784,13 @@ static int upload_config(c4_ctx *ctx, const c4_mcts_config *cfg)
     C4_REQUIRE(cfg->simulations >= 0 && cfg->simulations <= ctx->sims_cap, "simulations exceeds the context capacity");
     C4_REQUIRE(cfg->pb_c_base > 0, "pb_c_base must be positive");
     ctx->cfg = *cfg;
-    std::vector<double> t(ctx->sims_cap + 2);
-    for (int n = 0; n < (int)t.size(); n++)                    // oinkoink/mcts.py:150-152, host libm log
+    std::vector<double> t(ctx->sims_cap + 2), q(ctx->sims_cap + 2);
+    for (int n = 0; n < (int)t.size(); n++) {                  // oinkoink/mcts.py:150-154, host libm log / sqrt
         t[n] = log(((double)n + cfg->pb_c_base + 1.0) / cfg->pb_c_base) + cfg->pb_c_init;
+        q[n] = sqrt((double)n);
+    }
     C4_CUDA(cudaMemcpy(ctx->pbc_dev, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    C4_CUDA(cudaMemcpy(ctx->sqt_dev, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
     ctx->d.sims = cfg->simulations;
     ctx->d.alpha = cfg->root_dirichlet_alpha;
     ctx->d.frac = cfg->root_exploration_fraction;
@@ -800,19 +817,26 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     ctx->net = nullptr;
     ctx->parity = 0;
     ctx->n_search = 0;
-    ctx->budget_net = getenv("C4_BUDGET") ? atoi(getenv("C4_BUDGET")) : 2;
+    ctx->budget_net = getenv("C4_BUDGET") ? atoi(getenv("C4_BUDGET")) : 8;
+    ctx->n_pools = getenv("C4_POOLS") ? atoi(getenv("C4_POOLS")) : 1;
+    if (ctx->n_pools < 1 || ctx->n_pools > 2) ctx->n_pools = 1;
+    ctx->net_ctas = getenv("C4_NET_CTAS") ? atoi(getenv("C4_NET_CTAS")) : 112;
+    ctx->pool_parity[0] = ctx->pool_parity[1] = 0;
     ctx->last_pending = 0;
     ctx->supplied = true;
     ctx->pool_fresh = false;
     memset(&ctx->d, 0, sizeof(ctx->d));
     C4Dev &d = ctx->d;
+    d.cycle_limit = getenv("C4_CYCLE_LIMIT") ? atoll(getenv("C4_CYCLE_LIMIT")) : 20000;
     const size_t G = (size_t)max_games;
     d.blocks_per_game = cfg->simulations + 2;
     int rc = 0;
 #define A(ptr, n) if ((rc = dev_alloc(ctx, &(ptr), (n))) != 0) { c4_ctx_destroy(ctx); return rc; }
     A(d.pool, G * d.blocks_per_game * C4_SLOTS);
     A(ctx->pbc_dev, (size_t)cfg->simulations + 2);
+    A(ctx->sqt_dev, (size_t)cfg->simulations + 2);
     d.pbc = ctx->pbc_dev;
+    d.sqt = ctx->sqt_dev;
     A(d.root_c0, G); A(d.root_c1, G); A(d.status, G); A(d.sims_done, G); A(d.n_blocks, G);
     A(d.pending_node, G); A(d.pending_slot, G); A(d.path_len, G); A(d.ply, G);
     A(d.pend_c0, G); A(d.pend_c1, G); A(d.path, G * PATH_CAP); A(d.game_id, G);
@@ -834,6 +858,11 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
         return -2;
     }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 2; i++) {
+        cudaStreamCreateWithFlags(&ctx->pool_stream[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    }
     for (int i = 0; i < 2 * N_SAMPLES; i++) { cudaEventCreate(&ctx->evs[i]); cudaEventCreate(&ctx->eva[i]); }
     rc = upload_config(ctx, cfg);
     if (rc) { c4_ctx_destroy(ctx); return rc; }
@@ -848,7 +877,8 @@ extern "C" int c4_ctx_destroy(c4_ctx *ctx)
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) {
-        cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+        cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_fork);
+        for (int i = 0; i < 2; i++) { cudaStreamDestroy(ctx->pool_stream[i]); cudaEventDestroy(ctx->ev_join[i]); }
         for (int i = 0; i < 2 * N_SAMPLES; i++) { cudaEventDestroy(ctx->evs[i]); cudaEventDestroy(ctx->eva[i]); }
     }
     delete ctx;
@@ -860,6 +890,18 @@ extern "C" int c4_ctx_set_config(c4_ctx *ctx, const c4_mcts_config *cfg)
     C4_REQUIRE(ctx && cfg, "c4_ctx_set_config: null pointer");
     C4_CUDA(cudaSetDevice(ctx->device));
     return upload_config(ctx, cfg);
+}
+
+extern "C" int c4_ctx_get(c4_ctx *ctx, int key)
+{
+    if (!ctx) return -1;
+    switch (key) {
+    case 0: return ctx->n_pools;
+    case 1: return ctx->net_ctas;
+    case 2: return ctx->budget_net;
+    case 3: return ctx->max_games;
+    default: return -1;
+    }
 }
 
 extern "C" int c4_ctx_set_net(c4_ctx *ctx, c4_net *net)
@@ -880,26 +922,44 @@ extern "C" int c4_ctx_set_rng(c4_ctx *ctx, int mode, uint64_t seed, double *nois
     return 0;
 }
 
+int c4_net_forward_ex(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count, float *out,
+                      void *stream, int max_ctas);
+
+// one tree pass over games [g0, g0 + n_games) of pool `pool`
 template <bool SP>
-static int launch_advance(c4_ctx *ctx, int mode, int n_games, int budget, cudaStream_t s)
+static int launch_advance_pool(c4_ctx *ctx, int mode, int g0, int n_games, int pool, int parity, int budget, cudaStream_t s)
 {
-    ctx->parity ^= 1;
     const int threads = 128, wpb = threads / 32;
     const int blocks = (n_games + wpb - 1) / wpb;
     switch (mode) {
-    case C4_EVAL_EXTERNAL: k_advance<C4_EVAL_EXTERNAL, SP><<<blocks, threads, 0, s>>>(ctx->d, n_games, ctx->parity, budget); break;
-    case C4_EVAL_CENTRE: k_advance<C4_EVAL_CENTRE, SP><<<blocks, threads, 0, s>>>(ctx->d, n_games, ctx->parity, budget); break;
-    case C4_EVAL_NET: k_advance<C4_EVAL_NET, SP><<<blocks, threads, 0, s>>>(ctx->d, n_games, ctx->parity, budget); break;
+    case C4_EVAL_EXTERNAL: k_advance<C4_EVAL_EXTERNAL, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget); break;
+    case C4_EVAL_CENTRE: k_advance<C4_EVAL_CENTRE, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget); break;
+    case C4_EVAL_NET: k_advance<C4_EVAL_NET, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget); break;
     default: c4_set_error("bad eval kind"); return -1;
     }
     C4_CUDA(cudaGetLastError());
     return 0;
 }
 
+template <bool SP>
+static int launch_advance(c4_ctx *ctx, int mode, int n_games, int budget, cudaStream_t s)
+{
+    ctx->parity ^= 1;
+    return launch_advance_pool<SP>(ctx, mode, 0, n_games, 0, ctx->parity, budget, s);
+}
+
 static int run_net(c4_ctx *ctx, cudaStream_t s)
 {
     return c4_net_forward(ctx->net, (const uint64_t *)ctx->d.leaf_c0, (const uint64_t *)ctx->d.leaf_c1, ctx->max_games,
-                          &ctx->d.ctr->leaf_count[ctx->parity], ctx->net_out, s);
+                          &ctx->d.ctr->leaf_count[0][ctx->parity], ctx->net_out, s);
+}
+
+static inline void pool_range(const c4_ctx *ctx, int pool, int *g0, int *n)
+{
+    if (ctx->n_pools == 1) { *g0 = 0; *n = ctx->max_games; return; }
+    const int half = (ctx->max_games + 1) / 2;
+    *g0 = pool ? half : 0;
+    *n = pool ? ctx->max_games - half : half;
 }
 
 extern "C" int c4_search_begin(c4_ctx *ctx, const uint64_t *c0, const uint64_t *c1, int32_t n, void *stream)
@@ -929,7 +989,7 @@ extern "C" int c4_search_pending(c4_ctx *ctx, uint64_t *leaf_c0, uint64_t *leaf_
     C4_CUDA(cudaSetDevice(ctx->device));
     int rc = launch_advance<false>(ctx, C4_EVAL_EXTERNAL, ctx->max_games, 0x7fffffff, s);
     if (rc) return rc;
-    C4_CUDA(cudaMemcpyAsync(ctx->pinned, &ctx->d.ctr->leaf_count[ctx->parity], sizeof(int), cudaMemcpyDeviceToHost, s));
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned, &ctx->d.ctr->leaf_count[0][ctx->parity], sizeof(int), cudaMemcpyDeviceToHost, s));
     C4_CUDA(cudaStreamSynchronize(s));
     int m = *(int *)ctx->pinned;
     if (m > 0) {
@@ -1028,24 +1088,55 @@ extern "C" int c4_search_export_tree(c4_ctx *ctx, int32_t game, void *nodes_out,
     return 0;
 }
 
-// `sample_every` > 0: bracket every sample_every-th pass's two launches with CUDA events (at most N_SAMPLES samples)
+// `sample_every` > 0: bracket every sample_every-th pass's launches (of half pool 0) with CUDA events (<= N_SAMPLES samples).
+// With two half pools the launches go to two internal streams (forked from / joined to the caller's stream), so the
+// tree pass of one half overlaps the network launch of the other; the network launch is capped at net_ctas CTAs so
+// the tree blocks find free SMs.
 static int selfplay_passes(c4_ctx *ctx, int eval_kind, int n_passes, cudaStream_t s, int sample_every = 0,
                            int *n_sampled = nullptr)
 {
     int rc, ns = 0;
+    const bool two = ctx->n_pools == 2 && eval_kind == C4_EVAL_NET;
+    if (two) {
+        C4_CUDA(cudaEventRecord(ctx->ev_fork, s));
+        for (int p = 0; p < 2; p++) C4_CUDA(cudaStreamWaitEvent(ctx->pool_stream[p], ctx->ev_fork, 0));
+    }
     for (int k = 0; k < n_passes; k++) {
         const bool sample = sample_every > 0 && (k % sample_every) == sample_every / 2 && ns < N_SAMPLES;
-        if (sample) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns], s));
-        if (eval_kind == C4_EVAL_CENTRE) {
-            if ((rc = launch_advance<true>(ctx, C4_EVAL_CENTRE, ctx->max_games, 512, s))) return rc;
-            if (sample) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], s));
+        if (!two) {
+            if (sample) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns], s));
+            if (eval_kind == C4_EVAL_CENTRE) {
+                if ((rc = launch_advance<true>(ctx, C4_EVAL_CENTRE, ctx->max_games, 512, s))) return rc;
+                if (sample) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], s));
+            } else {
+                if ((rc = launch_advance<true>(ctx, C4_EVAL_NET, ctx->max_games, ctx->budget_net, s))) return rc;
+                if (sample) { C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], s)); C4_CUDA(cudaEventRecord(ctx->evs[2 * ns], s)); }
+                if ((rc = run_net(ctx, s))) return rc;
+                if (sample) C4_CUDA(cudaEventRecord(ctx->evs[2 * ns + 1], s));
+            }
         } else {
-            if ((rc = launch_advance<true>(ctx, C4_EVAL_NET, ctx->max_games, ctx->budget_net, s))) return rc;
-            if (sample) { C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], s)); C4_CUDA(cudaEventRecord(ctx->evs[2 * ns], s)); }
-            if ((rc = run_net(ctx, s))) return rc;
-            if (sample) C4_CUDA(cudaEventRecord(ctx->evs[2 * ns + 1], s));
+            for (int p = 0; p < 2; p++) {
+                cudaStream_t ps = ctx->pool_stream[p];
+                int g0, n;
+                pool_range(ctx, p, &g0, &n);
+                ctx->pool_parity[p] ^= 1;
+                const bool smp = sample && p == 0;
+                if (smp) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns], ps));
+                if ((rc = launch_advance_pool<true>(ctx, C4_EVAL_NET, g0, n, p, ctx->pool_parity[p], ctx->budget_net, ps))) return rc;
+                if (smp) { C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], ps)); C4_CUDA(cudaEventRecord(ctx->evs[2 * ns], ps)); }
+                if ((rc = c4_net_forward_ex(ctx->net, (const uint64_t *)(ctx->d.leaf_c0 + g0), (const uint64_t *)(ctx->d.leaf_c1 + g0),
+                                            n, &ctx->d.ctr->leaf_count[p][ctx->pool_parity[p]], ctx->net_out + (size_t)g0 * 8, ps,
+                                            ctx->net_ctas))) return rc;
+                if (smp) C4_CUDA(cudaEventRecord(ctx->evs[2 * ns + 1], ps));
+            }
         }
         if (sample) ns++;
+    }
+    if (two) {
+        for (int p = 0; p < 2; p++) {
+            C4_CUDA(cudaEventRecord(ctx->ev_join[p], ctx->pool_stream[p]));
+            C4_CUDA(cudaStreamWaitEvent(s, ctx->ev_join[p], 0));
+        }
     }
     if (n_sampled) *n_sampled = ns;
     return 0;
@@ -1070,6 +1161,7 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
     k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
     C4_CUDA(cudaGetLastError());
     ctx->parity = 0;
+    ctx->pool_parity[0] = ctx->pool_parity[1] = 0;
     int rc;
     C4Counters c;
     for (long long it = 0;; it++) {
@@ -1109,6 +1201,7 @@ extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations,
         k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
         C4_CUDA(cudaGetLastError());
         ctx->parity = 0;
+        ctx->pool_parity[0] = ctx->pool_parity[1] = 0;
         ctx->pool_fresh = true;
     }
     unsigned long long before[3], after[3];

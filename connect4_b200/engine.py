@@ -183,8 +183,10 @@ class Engine():
         _lib.check(self.lib.c4_selfplay_bench(self.h, k, int(iterations), C.byref(pos), C.byref(ev), C.byref(sims),
                                               C.byref(games), C.byref(ms), C.byref(nms), C.byref(tms),
                                               _lib.stream_ptr()))
+        pools = self.lib.c4_ctx_get(self.h, 0) if k == EVAL_NET else 1
         return dict(positions=pos.value, evals=ev.value, sims=sims.value, games=games.value, device_ms=ms.value,
-                    net_ms=nms.value, tree_ms=tms.value, iterations=int(iterations))
+                    net_ms=nms.value, tree_ms=tms.value, iterations=int(iterations), pools=pools,
+                    net_ctas=self.lib.c4_ctx_get(self.h, 1))
 
     def reset_pool(self):
         _lib.check(self.lib.c4_selfplay_reset(self.h, _lib.stream_ptr()))

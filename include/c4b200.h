@@ -103,6 +103,10 @@ int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config *cfg, c4_c
 int c4_ctx_destroy(c4_ctx *ctx);
 int c4_ctx_set_config(c4_ctx *ctx, const c4_mcts_config *cfg);   /* simulations must not exceed the created size */
 int c4_ctx_set_net(c4_ctx *ctx, c4_net *net);                    /* evaluator for C4_EVAL_NET */
+/* engine tuning read-out: key 0 = number of half pools self-play runs (2 = the tree pass of one half overlaps the
+ * network launch of the other; env C4_POOLS), 1 = CTA cap of a half-pool network launch (env C4_NET_CTAS),
+ * 2 = terminal re-visits played through per pass (env C4_BUDGET), 3 = max_games. */
+int c4_ctx_get(c4_ctx *ctx, int key);
 /* root-noise / move-sampling randomness (oinkoink/mcts.py:171-181, tree.py:75-82).
  * PHILOX: counter-based, keyed by (seed, global game id, ply).  INJECTED: noise[g][ply][7] raw gamma draws and
  * uniform[g][ply] (DEVICE fp64, g = game slot), e.g. recorded from the reference.  If `record` is non-zero in

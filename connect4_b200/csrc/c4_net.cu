@@ -474,8 +474,9 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
 #define TC_ACC_SLOTS 3
 #define TC_ACC_COL0 (TC_T * 32)
 #define TC_THREADS 576
-#define TC_EPI_WARPS 16                // 4 TMEM lane quadrants x 4 channel quarters (8 channels per thread)
-#define TC_CH 8
+#define TC_EPI_WARPS 16                // 2 tile groups x 4 TMEM lane quadrants x 2 channel halves (16 channels per thread)
+#define TC_CH 16
+#define TC_GROUP_WARPS 8
 
 struct TcSmem {
     static constexpr int X = 0;
@@ -483,7 +484,7 @@ struct TcSmem {
     static constexpr int W = H + TC_ACT_BYTES;
     static constexpr int SMALL = W + TC_WSTAGES * TC_WSTAGE_BYTES;          // biases + head params (fp32)
     __host__ __device__ static constexpr int scratch(int R) { return SMALL + ((1 + 2 * R) * 32 + HEAD_FLOATS) * 4; }
-    __host__ __device__ static constexpr int bars(int R) { return scratch(R) + 4 * TC_NB * 128 * 4; }   // [quarter][board][128]
+    __host__ __device__ static constexpr int bars(int R) { return scratch(R) + 2 * TC_NB * 128 * 4; }   // [half][board][128]
     __host__ __device__ static constexpr int total(int R) { return bars(R) + 256; }
 };
 
@@ -573,6 +574,91 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *r)
 #define TC_PROXY_FENCE() asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory")
 #define EPI_BAR() asm volatile("bar.sync 1, 512;\n" ::: "memory")      // the 16 epilogue warps only
 
+// Epilogue of one layer, specialised on the layer kind so the tile loop carries no layer-type branches:
+//   KIND 0 = stem (result -> residual stream + X), 1 = first conv of a block (-> H),
+//   2 = second conv (+= residual, -> residual stream + X), 3 = the last conv of the tower (+= residual, -> head partials).
+// The per-tile epilogue is a serial chain of long-latency steps (barrier wake-up, TMEM loads, shuffles, TMEM / shared
+// stores, fences, arrive: ~1100 cycles), so the 16 epilogue warps form TWO groups that take alternate tiles of the
+// global tile sequence: two chains are always in flight.  A tile's residual columns are touched in layers 0, 2, 4, ...
+// whose tile counters differ by a multiple of 2T, i.e. always by the same group and the same thread.
+struct EpiCtx {
+    uint32_t b_accfull, b_accempty, b_epi;
+    uint32_t tmem_acc;        // tmem + lane quadrant + TC_ACC_COL0 + 16 * half
+    uint32_t tmem_res;        // tmem + lane quadrant + 16 * half
+    unsigned char *dst_x, *dst_h;   // smem row of this thread in tile 0, k-chunk 2 * half
+    const float *bias, *hp;
+    float *scratch;           // + half * TC_NB * 128
+    uint32_t valid_mask;      // bit t: this thread's row of tile t is a real pixel of a board of this strip
+    int lane, lm, lp, half, group, rb0, col8;
+};
+
+template <typename OP, int KIND>
+__device__ __forceinline__ void tc_epilogue_layer(const EpiCtx &E, int l, int T, int c0)
+{
+    constexpr bool TO_RES = (KIND == 0 || KIND == 2), ADD_RES = (KIND == 2 || KIND == 3), LAST = (KIND == 3);
+    unsigned char *dst = (KIND == 1) ? E.dst_h : E.dst_x;
+    const float *bl = E.bias + l * 32 + TC_CH * E.half;
+#pragma unroll 1
+    for (int t = (c0 + E.group) & 1; t < T; t += 2) {                     // tiles c = c0 + t with c % 2 == group
+        const int c = c0 + t, slot = c % TC_ACC_SLOTS;
+        mbar_wait(E.b_accfull + 8 * slot, (uint32_t)(c / TC_ACC_SLOTS) & 1u);
+        TC_FENCE_AFTER();
+        const uint32_t ta = E.tmem_acc + slot * TC_NN;
+        const uint32_t tr = E.tmem_res + 32 * t;
+        float em[TC_CH], ez[TC_CH], ep[TC_CH], rs[TC_CH];
+        tmem_ld16(ta, em);
+        tmem_ld16(ta + 32, ez);
+        tmem_ld16(ta + 64, ep);
+        if (ADD_RES) tmem_ld16(tr, rs);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        TC_FENCE_BEFORE();
+        __syncwarp();
+        if (E.lane == 0) mbar_arrive(E.b_accempty + 8 * slot);            // accumulator slot free for the MMA warp
+        // out[q] = E_-1[q-1] + E_0[q] + E_+1[q+1].  Rotating shuffles need no edge fix-up: lane 0 is a pad-column row
+        // (its result is discarded) and lane 31 wraps to lane 0 whose E is exactly 0 (A is zero on pad rows).
+        // Packed fp32x2 adds / muls (FADD2 / FMUL2 on sm_100).
+        float v[TC_CH];
+#pragma unroll
+        for (int j = 0; j < TC_CH; j += 2) {
+            float2 m1 = make_float2(__shfl_sync(0xffffffffu, em[j], E.lm), __shfl_sync(0xffffffffu, em[j + 1], E.lm));
+            float2 p1 = make_float2(__shfl_sync(0xffffffffu, ep[j], E.lp), __shfl_sync(0xffffffffu, ep[j + 1], E.lp));
+            float2 y = __fadd2_rn(__fadd2_rn(m1, make_float2(ez[j], ez[j + 1])), __fadd2_rn(p1, make_float2(bl[j], bl[j + 1])));
+            if (ADD_RES) y = __fadd2_rn(y, make_float2(rs[j], rs[j + 1]));
+            float2 z = __fmul2_rn(y, make_float2(LEAKY, LEAKY));
+            v[j] = fmaxf(y.x, z.x);
+            v[j + 1] = fmaxf(y.y, z.y);
+        }
+        const bool valid = (E.valid_mask >> t) & 1u;
+        if (TO_RES) tmem_st16(tr, v);
+        if (!LAST) {
+            if (valid) {
+                unsigned char *p = dst + (size_t)t * (128 * 16);
+                *reinterpret_cast<uint4 *>(p) =
+                    make_uint4(OP::pack(v[0], v[1]), OP::pack(v[2], v[3]), OP::pack(v[4], v[5]), OP::pack(v[6], v[7]));
+                *reinterpret_cast<uint4 *>(p + TC_ROWS * 16) =
+                    make_uint4(OP::pack(v[8], v[9]), OP::pack(v[10], v[11]), OP::pack(v[12], v[13]), OP::pack(v[14], v[15]));
+            }
+        } else if (valid) {
+            // head 1x1 convs (model.py:77-79,107-109): this thread's 16 channels of one pixel; the two channel halves are
+            // summed in a fixed order by the head tail (deterministic, no atomics)
+            float a = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < TC_CH; j++) {
+                a = fmaf(v[j], E.hp[HO_VW + TC_CH * E.half + j], a);
+                p0 = fmaf(v[j], E.hp[HO_PW + TC_CH * E.half + j], p0);
+                p1 = fmaf(v[j], E.hp[HO_PW + 32 + TC_CH * E.half + j], p1);
+            }
+            const int rb = 16 * t + E.rb0, b = rb / 7;
+            float *sc = E.scratch + b * 128 + (rb - 7 * b - 1) * 7 + (E.col8 - 1);
+            sc[0] = a; sc[42] = p0; sc[84] = p1;
+        }
+        if (TO_RES) asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        if (!LAST) TC_PROXY_FENCE();
+        __syncwarp();
+        if (E.lane == 0) mbar_arrive(E.b_epi + 8 * t);
+    }
+}
+
 // global image: [L layers][TC_WSTAGE_BYTES] weights, then biases [(1+2R)*32] fp32, then head block [HEAD_FLOATS] fp32
 template <typename OP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -584,7 +670,6 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
     long long tmark = clock64(), d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
 #else
 #define DBG_T(var)
-    const long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
 #endif
     extern __shared__ __align__(16) unsigned char smem[];
     if (count) { int m = *count; n = m < n ? m : n; }
@@ -620,8 +705,8 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_WSTAGES; i++) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, 1); }
-        for (int i = 0; i < TC_ACC_SLOTS; i++) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, TC_EPI_WARPS); }
-        for (int i = 0; i < TC_T; i++) mbar_init(b_epi + 8 * i, TC_EPI_WARPS);
+        for (int i = 0; i < TC_ACC_SLOTS; i++) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, TC_GROUP_WARPS); }
+        for (int i = 0; i < TC_T; i++) mbar_init(b_epi + 8 * i, TC_GROUP_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -666,7 +751,10 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                     // epilogue arrivals seen so far on each tile barrier: (L + 1) per finished strip, l + 1 needed now
                     const uint32_t ep_par = (uint32_t)(s * (L + 1) + l) & 1u;
                     for (int t = 0; t < T; t++, c++) {
-                        mbar_wait(b_epi + 8 * min(t + 1, T - 1), ep_par);
+                        // rows of tiles t-1, t, t+1 of the previous layer are read; the two epilogue groups finish
+                        // tiles out of order, so every tile is waited for once (tile t+1 here, tile 0 at t == 0)
+                        if (t == 0) mbar_wait(b_epi, ep_par);
+                        if (t + 1 < T) mbar_wait(b_epi + 8 * (t + 1), ep_par);
                         DBG_T(d1)
                         const int slot = c % TC_ACC_SLOTS, use = c / TC_ACC_SLOTS;
                         if (use > 0) mbar_wait(b_accempty + 8 * slot, (use - 1) & 1);
@@ -694,19 +782,34 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                     umma_commit(b_wempty + 8 * st);
                 }
             }
+#ifdef C4_TC_PROFILE
             if (dbg && blockIdx.x == 0) { dbg[0] = d0; dbg[1] = d1; dbg[2] = d2; dbg[3] = d3; }
+#endif
         }
     } else {
         // ================= epilogue warps
-        const int e = warp - 2, quad = warp & 3, qtr = e >> 2;               // channels [8 qtr, 8 qtr + 8)
+        const int e = warp - 2, quad = warp & 3, half = (e >> 2) & 1, group = e >> 3;
         const int et = threadIdx.x - 64;                                     // 0..511
-        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        const int lm = (lane + 31) & 31, lp = (lane + 1) & 31;
-        int c = 0;
+        EpiCtx E;
+        E.b_accfull = b_accfull; E.b_accempty = b_accempty; E.b_epi = b_epi;
+        E.tmem_acc = tmem + ((uint32_t)(quad * 32) << 16) + TC_ACC_COL0 + TC_CH * half;
+        E.tmem_res = tmem + ((uint32_t)(quad * 32) << 16) + TC_CH * half;
+        E.dst_x = sX + (size_t)(2 * half * TC_ROWS + 8 + 32 * quad + lane) * 16;
+        E.dst_h = sH + (size_t)(2 * half * TC_ROWS + 8 + 32 * quad + lane) * 16;
+        E.bias = bias; E.hp = hp;
+        E.scratch = scratch + half * TC_NB * 128;
+        E.lane = lane; E.lm = (lane + 31) & 31; E.lp = (lane + 1) & 31; E.half = half; E.group = group;
+        E.rb0 = 4 * quad + (lane >> 3); E.col8 = lane & 7;
+        int c = 0;                                                           // global (strip, layer, tile) counter
         for (int s = 0; s < n_strips; s++) {
             const int nb = min(TC_NB, my_n - s * TC_NB);
             const int T = (7 * nb + 15) / 16;
             const int first = my_first + s * TC_NB;
+            E.valid_mask = 0;
+            for (int t = 0; t < T; t++) {
+                const int rb = 16 * t + E.rb0, b = rb / 7;
+                if (E.col8 != 0 && rb - 7 * b != 0 && b < nb) E.valid_mask |= 1u << t;
+            }
             // ---- input planes (Board.to_array) -> channels 0..15 of H
             for (int i = et; i < nb * 42; i += 32 * TC_EPI_WARPS) {
                 const int b = i / 42, px = i - b * 42, r = px / 7, col = px - r * 7;
@@ -720,93 +823,23 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
             }
             TC_PROXY_FENCE();
             EPI_BAR();
-            if (lane == 0)
+            if (lane == 0 && e < TC_GROUP_WARPS)                             // 8 arrivals per tile barrier and epoch
                 for (int t = 0; t < T; t++) mbar_arrive(b_epi + 8 * t);
 
-            for (int l = 0; l < L; l++) {
-                const bool to_res = (l == 0) || ((l & 1) == 0);               // stem / conv2: result is the residual stream
-                const bool add_res = (l != 0) && ((l & 1) == 0);
-                const bool last = (l == L - 1);
-                unsigned char *dst = (to_res ? sX : sH) + (size_t)qtr * TC_ROWS * 16;   // this quarter = one k-chunk
-                float bl[TC_CH];
-#pragma unroll
-                for (int j = 0; j < TC_CH; j++) bl[j] = bias[l * 32 + TC_CH * qtr + j];
-                for (int t = 0; t < T; t++, c++) {
-                    const int slot = c % TC_ACC_SLOTS;
-                    DBG_T(d4)
-                    mbar_wait(b_accfull + 8 * slot, (c / TC_ACC_SLOTS) & 1);
-                    DBG_T(d0)
-                    TC_FENCE_AFTER();
-                    const uint32_t ta = tmem + lane_base + TC_ACC_COL0 + slot * TC_NN + TC_CH * qtr;
-                    const uint32_t tr = tmem + lane_base + 32 * t + TC_CH * qtr;
-                    float em[TC_CH], ez[TC_CH], ep[TC_CH], rs[TC_CH];
-                    tmem_ld8(ta, em);
-                    tmem_ld8(ta + 32, ez);
-                    tmem_ld8(ta + 64, ep);
-                    if (add_res) tmem_ld8(tr, rs);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                    DBG_T(d1)
-                    TC_FENCE_BEFORE();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(b_accempty + 8 * slot);        // accumulator slot free for the MMA warp
-                    DBG_T(d5)
-                    const int srow = 128 * t + 32 * quad + lane;              // strip row
-                    const int rb = srow >> 3, col8 = srow & 7;
-                    const int b = rb / 7;
-                    const bool valid = (col8 != 0) && (rb - 7 * b != 0) && (b < nb);
-                    // out[q] = E_-1[q-1] + E_0[q] + E_+1[q+1].  Rotating shuffles need no edge fix-up: lane 0 is a pad-column
-                    // row (its result is discarded) and lane 31 wraps to lane 0 whose E is exactly 0 (A is zero on pad rows).
-                    // packed fp32x2 adds / muls (FADD2 / FMUL2 on sm_100): the epilogue is FP32-pipe bound
-                    float v[TC_CH];
-#pragma unroll
-                    for (int j = 0; j < TC_CH; j += 2) {
-                        float2 m1 = make_float2(__shfl_sync(0xffffffffu, em[j], lm), __shfl_sync(0xffffffffu, em[j + 1], lm));
-                        float2 p1 = make_float2(__shfl_sync(0xffffffffu, ep[j], lp), __shfl_sync(0xffffffffu, ep[j + 1], lp));
-                        float2 y = __fadd2_rn(__fadd2_rn(m1, make_float2(ez[j], ez[j + 1])),
-                                              __fadd2_rn(p1, make_float2(bl[j], bl[j + 1])));
-                        if (add_res) y = __fadd2_rn(y, make_float2(rs[j], rs[j + 1]));
-                        float2 z = __fmul2_rn(y, make_float2(LEAKY, LEAKY));
-                        v[j] = fmaxf(y.x, z.x);
-                        v[j + 1] = fmaxf(y.y, z.y);
-                    }
-                    DBG_T(d6)
-                    if (to_res && !last) tmem_st8(tr, v);
-                    DBG_T(d7)
-                    if (valid && !last)
-                        *reinterpret_cast<uint4 *>(dst + (size_t)(8 + srow) * 16) =
-                            make_uint4(OP::pack(v[0], v[1]), OP::pack(v[2], v[3]), OP::pack(v[4], v[5]), OP::pack(v[6], v[7]));
-                    if (last && valid) {
-                        // head 1x1 convs (model.py:77-79,107-109): this thread's 8 channels of one pixel; the four channel
-                        // quarters are summed in a fixed order by head tail below (deterministic, no atomics)
-                        float a = 0.f, p0 = 0.f, p1 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < TC_CH; j++) {
-                            a = fmaf(v[j], hp[HO_VW + TC_CH * qtr + j], a);
-                            p0 = fmaf(v[j], hp[HO_PW + TC_CH * qtr + j], p0);
-                            p1 = fmaf(v[j], hp[HO_PW + 32 + TC_CH * qtr + j], p1);
-                        }
-                        float *sc = scratch + (qtr * TC_NB + b) * 128 + (rb - 7 * b - 1) * 7 + (col8 - 1);
-                        sc[0] = a; sc[42] = p0; sc[84] = p1;
-                    }
-                    DBG_T(d2)
-                    if (to_res && !last) asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-                    TC_PROXY_FENCE();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(b_epi + 8 * t);
-                    DBG_T(d3)
-                }
+            tc_epilogue_layer<OP, 0>(E, 0, T, c); c += T;
+            for (int l = 1; l < L - 1; l += 2) {
+                tc_epilogue_layer<OP, 1>(E, l, T, c); c += T;
+                if (l + 1 < L - 1) { tc_epilogue_layer<OP, 2>(E, l + 1, T, c); c += T; }
             }
+            tc_epilogue_layer<OP, 3>(E, L - 1, T, c); c += T;
+
             // ---- head tails: one warp per board
-            if (dbg && blockIdx.x == 0 && e == 0 && lane == 0 && s == n_strips - 1) {
-                dbg[8] = d0; dbg[9] = d1; dbg[10] = d2; dbg[11] = d3; dbg[12] = d4; dbg[13] = d5; dbg[14] = d6; dbg[15] = d7;
-            }
             EPI_BAR();
             for (int b = e; b < nb; b += TC_EPI_WARPS) {
                 float *sc = scratch + b * 128;
                 for (int i = lane; i < 126; i += 32) {
                     float bb = i < 42 ? hp[HO_VB] : (i < 84 ? hp[HO_PB] : hp[HO_PB + 1]);
-                    float x = ((sc[i] + sc[TC_NB * 128 + i]) + sc[2 * TC_NB * 128 + i]) + sc[3 * TC_NB * 128 + i];
-                    sc[i] = leaky(x + bb);
+                    sc[i] = leaky((sc[i] + sc[TC_NB * 128 + i]) + bb);
                 }
                 __syncwarp();
                 head_tail(sc, hp, out + (size_t)(first + b) * 8, lane);
@@ -1004,6 +1037,7 @@ int c4_net_forward_ex(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64
             long long h[16];
             cudaStreamSynchronize(s);
             cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaMemset(dbg, 0, 16 * sizeof(long long));
             fprintf(stderr, "[tc dbg] mma: wait_w %lld wait_epi %lld wait_accempty %lld issue %lld | epi warp0: wait_accfull %lld ld %lld "
                             "sts/heads %lld store-wait+fence %lld loop %lld | arrive_accempty %lld shfl+fp %lld sttm %lld\n", h[0], h[1], h[2], h[3], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
         }

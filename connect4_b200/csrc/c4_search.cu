@@ -74,7 +74,6 @@ struct C4Dev {
     const double *ext_value;            // [G]
     const void *ext_prior;              // [G][7] fp64 or fp32
     int ext_prior_dtype;
-    long long cycle_limit;              // a warp starts no further descent in a pass after this many SM cycles (0 = off)
     // self-play control
     C4Counters *ctr;
     long long n_games_target;
@@ -479,7 +478,7 @@ __device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
 // ------------------------------------------------------------------------------------------------ the pass kernel
 // MODE: C4_EVAL_EXTERNAL / C4_EVAL_CENTRE / C4_EVAL_NET.  One warp per game slot.
 template <int MODE, bool SELFPLAY>
-__global__ void __launch_bounds__(128, 8) k_advance(C4Dev d, int g0, int n_games, int pool, int parity, int budget)
+__global__ void __launch_bounds__(128, 8) k_advance(C4Dev d, int g0, int n_games, int pool, int parity, int budget, long long cycle_limit)
 {
     const int gi = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int g = g0 + gi;
@@ -570,7 +569,7 @@ __global__ void __launch_bounds__(128, 8) k_advance(C4Dev d, int g0, int n_games
         if (budget-- <= 0) break;
         // bound the tail of the pass: the first descent is always allowed, later ones (after terminal re-visits) only
         // while the warp is inside its cycle budget
-        if (d.cycle_limit > 0 && first_descent_done && clock64() - t_start > d.cycle_limit) break;
+        if (cycle_limit > 0 && first_descent_done && clock64() - t_start > cycle_limit) break;
         first_descent_done = true;
         Leaf L = descend(d, G);
         if (L.meta & C4_META_TERMINAL) {
@@ -758,6 +757,7 @@ struct c4_ctx {
     cudaStream_t pool_stream[2];
     cudaEvent_t ev_fork, ev_join[2];
     int n_search;                       // searches started by the last c4_search_begin
+    long long cycle_limit;
     int budget_net;                     // terminal re-visits a game may play through per pass (NET / EXTERNAL)
     int last_pending;
     bool supplied;
@@ -827,7 +827,8 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     ctx->pool_fresh = false;
     memset(&ctx->d, 0, sizeof(ctx->d));
     C4Dev &d = ctx->d;
-    d.cycle_limit = getenv("C4_CYCLE_LIMIT") ? atoll(getenv("C4_CYCLE_LIMIT")) : 20000;
+    // a warp starts no further descent in a NET pass after this many SM cycles (bounds the tail of the pass; 0 = off)
+    ctx->cycle_limit = getenv("C4_CYCLE_LIMIT") ? atoll(getenv("C4_CYCLE_LIMIT")) : 20000;
     const size_t G = (size_t)max_games;
     d.blocks_per_game = cfg->simulations + 2;
     int rc = 0;
@@ -932,9 +933,9 @@ static int launch_advance_pool(c4_ctx *ctx, int mode, int g0, int n_games, int p
     const int threads = 128, wpb = threads / 32;
     const int blocks = (n_games + wpb - 1) / wpb;
     switch (mode) {
-    case C4_EVAL_EXTERNAL: k_advance<C4_EVAL_EXTERNAL, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget); break;
-    case C4_EVAL_CENTRE: k_advance<C4_EVAL_CENTRE, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget); break;
-    case C4_EVAL_NET: k_advance<C4_EVAL_NET, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget); break;
+    case C4_EVAL_EXTERNAL: k_advance<C4_EVAL_EXTERNAL, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, 0LL); break;
+    case C4_EVAL_CENTRE: k_advance<C4_EVAL_CENTRE, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, 0LL); break;
+    case C4_EVAL_NET: k_advance<C4_EVAL_NET, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, ctx->cycle_limit); break;
     default: c4_set_error("bad eval kind"); return -1;
     }
     C4_CUDA(cudaGetLastError());

@@ -6,7 +6,7 @@
 
 Workload (ours): BASELINE.json configs[2] -- 4096 concurrent self-play games per GPU, default NetConfig ResNet
 (32 filters / 3 residual / 4 fc; the reference's example_net weights), 800 simulations per move, AlphaZero root noise +
-6 sampled moves, bf16 batched leaf evaluation.  Games never interact, so with N GPUs every rank runs its own pool
+6 sampled moves, 16-bit tensor-core batched leaf evaluation (fp16 operands, fp32 accumulate).  Games never interact, so with N GPUs every rank runs its own pool
 (weak scaling, no data-path collective).
 
 A "step" = `--passes` lock-step passes of the pool in steady state (finished games re-seeded at once); every pass
@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
     ap.add_argument("--passes", type=int, default=4000, help="lock-step passes per step")
     ap.add_argument("--preroll", type=int, default=36000, help="untimed passes that bring the pool to steady state")
-    ap.add_argument("--e2e-games", type=int, default=4096)
+    ap.add_argument("--e2e-games", type=int, default=16384, help="games of the end-to-end generation (4 pool-fulls)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
@@ -234,8 +234,8 @@ def main():
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e = {"value": float(e.item()) / float(tm.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(2 * 8 * args.e2e_games), "d2h_bytes_per_step": int(len(rec) * 64),
-               "what": "SelfPlayPool.generate_records(%d games from host start positions) -> host records, "
-                       "wall clock incl. pool drain" % args.e2e_games}
+               "what": "SelfPlayPool.generate_records(%d games on %d slots, host start positions) -> host records; wall "
+                       "clock of the whole generation incl. the drain of the last games" % (args.e2e_games, args.games)}
         pool2.engine.close()
 
     if rank == 0:

@@ -145,8 +145,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
-    ap.add_argument("--passes", type=int, default=4000, help="lock-step passes per step")
-    ap.add_argument("--preroll", type=int, default=36000, help="untimed passes that bring the pool to steady state")
+    ap.add_argument("--passes", type=int, default=2000, help="lock-step passes per step")
+    ap.add_argument("--preroll", type=int, default=12000, help="untimed passes that bring the pool to steady state")
     ap.add_argument("--e2e-games", type=int, default=16384, help="games of the end-to-end generation (4 pool-fulls)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
@@ -193,12 +193,13 @@ def main():
 
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    tot = dict(positions=0, evals=0, device_ms=0.0, net_ms=0.0, tree_ms=0.0, games=0)
+    tot = dict(positions=0, evals=0, device_ms=0.0, net_ms=0.0, tree_ms=0.0, games=0, memo_hits=0)
     t_wall = time.perf_counter()
     for _ in range(args.steps):
         r = pool.throughput(args.passes)
-        for k in ("positions", "evals", "device_ms", "games"):
+        for k in ("positions", "evals", "device_ms", "games", "memo_hits"):
             tot[k] += r[k]
+        memo_log2 = r["memo_log2"]
         tot["net_ms"] += r["net_ms"]
         tot["tree_ms"] += r["tree_ms"]
         pools = r["pools"]
@@ -245,26 +246,43 @@ def main():
         evals_per_pass = tot["evals"] / (n_pass * pools)          # per network launch (one launch per half pool per pass)
         net_ms = tot["net_ms"] / args.steps
         tree_ms = tot["tree_ms"] / args.steps
-        achieved = (evals_per_pass * flops) / (net_ms * 1e-3) / 1e12 if net_ms > 0 else None
+        step_ms = 1000.0 * secs / args.steps
+        net_tf = (evals_per_pass * flops) / (net_ms * 1e-3) / 1e12 if net_ms > 0 else None
+        # tree pass (dominant kernel, HBM class): algorithmic bytes = simulations in the launch x 1.28 KB (SURVEY.md 8d:
+        # select L*(4+28+13k) + backup 24 L + expand + leaf I/O at L = 6.5, k = 7) + 64 B per evaluation-memo probe
+        sims_per_launch = tot["positions"] * SIMS / (n_pass * pools)
+        probes_per_launch = (tot["evals"] + tot["memo_hits"]) / (n_pass * pools)
+        tree_bytes = sims_per_launch * 1280.0 + probes_per_launch * 64.0
+        tree_gbs = tree_bytes / (tree_ms * 1e-3) / 1e9 if tree_ms > 0 else None
+        tree_share = (tree_ms * pools * n_pass / args.steps) / step_ms if secs else None
+        net_share = (net_ms * pools * n_pass / args.steps) / step_ms if secs else None
+        roof_tree = {"kernel": "k_advance<NET,selfplay> (warp-per-game tree pass)", "bound": "hbm", "achieved": tree_gbs,
+                     "peak": peak_hbm, "unit": "GB/s", "frac": (tree_gbs / peak_hbm) if tree_gbs else None, "traffic": None,
+                     "peak_source": peak_src.replace("sustained bf16", "copy bandwidth"),
+                     "algorithmic_bytes_per_launch": tree_bytes, "sims_per_launch": sims_per_launch,
+                     "ms_per_launch": tree_ms, "share_of_step": tree_share,
+                     "note": "dependent-load latency bound (one round trip per tree level), not bandwidth bound"}
+        roof_net = {"kernel": "k_net_tc<OpFP16> (tcgen05/TMEM)", "bound": "tensor", "achieved": net_tf, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": (net_tf / peak_tf) if net_tf else None, "traffic": None,
+                    "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals_per_pass,
+                    "ms_per_launch": net_ms, "share_of_step": net_share}
+        dominant_tree = (tree_share or 0) >= (net_share or 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "games_per_gpu": args.games, "passes_per_step": args.passes,
-                       "preroll_passes": args.preroll, "simulations": SIMS,
-                       "l2": "node pool working set (%.0f MB/GPU) exceeds L2; fresh leaves every pass" %
-                             (args.games * (SIMS + 2) * 256 / 1e6)},
+                       "preroll_passes": args.preroll, "simulations": SIMS, "evaluation_memo_log2_entries": memo_log2,
+                       "l2": "node pool (%.0f MB/GPU) + evaluation memo (%.1f GB) exceed L2; fresh leaves every pass" %
+                             (args.games * (SIMS + 2) * 256 / 1e6, (64 << memo_log2) / 1e9 if memo_log2 else 0.0)},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(2 * pools * n_pass + 4 * args.steps),
-            "roofline": {"kernel": "k_net_tc<OpFP16> (tcgen05/TMEM)", "bound": "tensor", "achieved": achieved, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
-                         "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals_per_pass,
-                         "net_ms_per_launch": net_ms, "tree_ms_per_launch": tree_ms,
-                         "half_pools": pools,
-                         "net_share_of_step": (net_ms * pools * n_pass / args.steps) / (1000.0 * secs / args.steps) if secs else None},
-            "sims_per_sec": value * SIMS, "evals_per_sec": evals / secs, "games_finished": games,
-            "wall_s_timed_region": t_wall,
+            "roofline": roof_tree if dominant_tree else roof_net,
+            "roofline_other": roof_net if dominant_tree else roof_tree,
+            "sims_per_sec": value * SIMS, "network_evals_per_sec": evals / secs,
+            "memo_hit_rate": (tot["memo_hits"] / max(1.0, tot["memo_hits"] + tot["evals"])),
+            "games_finished": games, "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu:
             r, cores = cpu_port(args.cpu_seconds)

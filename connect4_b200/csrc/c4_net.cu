@@ -48,6 +48,7 @@
 struct c4_net {
     int device;
     int F, R, n_fc;
+    unsigned long long uid;  // unique per created network (the engine's evaluation memo is keyed on it)
     bool fp16;            // operand element type of the conv GEMMs (false: bf16)
     bool use_tc;          // tcgen05 kernel (filters == 32) instead of the mma.sync kernels
     void *image_tc;       // device: [L][TC_WSTAGE_BYTES] weights + biases + head block
@@ -949,7 +950,9 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
     memcpy(hp + HO_POLW, p, 7 * 84 * 4); p += 7 * 84;
     memcpy(hp + HO_POLB, p, 7 * 4); p += 7;
 
+    static unsigned long long next_uid = 1;
     c4_net *net = new c4_net();
+    net->uid = next_uid++;
     net->device = device; net->F = F; net->R = R; net->n_fc = n_fc; net->fp16 = fp16;
     net->image_bytes = total;
     net->flops = 2.0 * (42.0 * 27 * F + 2.0 * R * 42 * 9 * F * F + 42.0 * F + (double)n_fc * 42 * 42 + 42 + 42.0 * F * 2 +
@@ -1010,6 +1013,7 @@ extern "C" int c4_net_destroy(c4_net *net)
 }
 
 extern "C" double c4_net_flops_per_position(const c4_net *net) { return net ? net->flops : 0.0; }
+unsigned long long c4_net_uid(const c4_net *net) { return net ? net->uid : 0ULL; }   // internal (not part of the C ABI)
 
 extern "C" int c4_net_forward(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count,
                               float *out, void *stream)

@@ -28,6 +28,8 @@
 
 #include "c4_common.cuh"
 
+unsigned long long c4_net_uid(const c4_net *net);     // c4_net.cu (internal)
+
 enum { ST_IDLE = 0, ST_READY = 1, ST_WAIT = 2, ST_DONE = 3, ST_NEWROOT = 4 };
 #define PATH_CAP 48
 #define MAX_PLY 42
@@ -69,6 +71,12 @@ struct C4Dev {
     // leaf batch
     u64 *leaf_c0, *leaf_c1;
     int *leaf_game;
+    // evaluation memo (the reference's Evaluator.position_table, oinkoink/evaluators.py:18-25): direct-mapped table of
+    // 64-byte entries {c0, c1, out[8], check64}; looked up before a leaf is sent to the network, filled when the
+    // network's answer is consumed.  Pure cache: a hit returns bit-identical numbers to a network evaluation.
+    uint32_t *memo;                     // [memo_mask + 1][16] words, or nullptr
+    uint32_t memo_mask;
+    unsigned long long *stat_hits;      // [G]
     // evaluator answers
     const float *net_out;               // [G][8] {prior[7], value}
     const double *ext_value;            // [G]
@@ -153,6 +161,56 @@ __device__ double c4_gamma(Philox &ph, double alpha)
     double g = d * v;
     if (alpha < 1.0) g *= pow(u4, 1.0 / alpha);
     return g;
+}
+
+__device__ __forceinline__ u64 memo_mix(u64 x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ uint32_t memo_index(u64 c0, u64 c1, uint32_t mask)
+{
+    return (uint32_t)(memo_mix(c0 * 0x9E3779B97F4A7C15ULL ^ c1 * 0xC2B2AE3D27D4EB4FULL) >> 20) & mask;
+}
+// 64-bit checksum over key and payload: a torn entry (two warps writing the same slot) reads as a miss
+__device__ __forceinline__ u64 memo_check(u64 c0, u64 c1, uint32_t payload_xor_rot)
+{
+    return memo_mix(c0 ^ memo_mix(c1 + 0x632BE59BD9B4E019ULL) ^ ((u64)payload_xor_rot * 0xD6E8FEB86659FD93ULL)) | 1ULL;
+}
+// lanes 0..7 hold the payload words (out[lane] bits); returns a warp-uniform digest of them
+__device__ __forceinline__ uint32_t memo_payload_digest(uint32_t w, int lane)
+{
+    uint32_t x = (lane < 8) ? __funnelshift_l(w, w, 3 * lane) + (uint32_t)lane * 0x9E3779B9u : 0u;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) x ^= __shfl_xor_sync(FULL, x, off);
+    return __shfl_sync(FULL, x, 0);
+}
+// store {c0, c1, out[8]} (lane l < 8 holds out[l]); one coalesced 64-byte store
+__device__ __forceinline__ void memo_insert(const C4Dev &d, u64 c0, u64 c1, float out_lane, int lane)
+{
+    const uint32_t w = __float_as_uint(out_lane);
+    const u64 chk = memo_check(c0, c1, memo_payload_digest(w, lane));
+    uint32_t *e = d.memo + (size_t)memo_index(c0, c1, d.memo_mask) * 16;
+    const uint32_t pw = __shfl_sync(FULL, w, (lane - 4) & 31);         // lane 4 + l <- out[l]
+    uint32_t v = 0u;
+    if (lane < 2) v = (uint32_t)(c0 >> (32 * lane));
+    else if (lane < 4) v = (uint32_t)(c1 >> (32 * (lane - 2)));
+    else if (lane < 12) v = pw;
+    else if (lane < 14) v = (uint32_t)(chk >> (32 * (lane - 12)));
+    if (lane < 16) e[lane] = v;
+}
+// true on a hit; out_lane (lanes 0..7) receives out[lane]
+__device__ __forceinline__ bool memo_lookup(const C4Dev &d, u64 c0, u64 c1, float &out_lane, int lane)
+{
+    const uint32_t *e = d.memo + (size_t)memo_index(c0, c1, d.memo_mask) * 16;
+    const uint32_t v = (lane < 16) ? __ldcg(e + lane) : 0u;
+    const u64 k0 = (u64)__shfl_sync(FULL, v, 0) | ((u64)__shfl_sync(FULL, v, 1) << 32);
+    const u64 k1 = (u64)__shfl_sync(FULL, v, 2) | ((u64)__shfl_sync(FULL, v, 3) << 32);
+    const u64 chk = (u64)__shfl_sync(FULL, v, 12) | ((u64)__shfl_sync(FULL, v, 13) << 32);
+    const uint32_t w = __shfl_sync(FULL, v, (lane + 4) & 31);          // lane l < 8 <- word 4 + l
+    const uint32_t dig = memo_payload_digest(w, lane);
+    out_lane = __uint_as_float(w);
+    return k0 == c0 && k1 == c1 && chk == memo_check(c0, c1, dig);
 }
 
 struct Game {
@@ -508,8 +566,10 @@ __global__ void __launch_bounds__(128, 8) k_advance(C4Dev d, int g0, int n_games
         const int ply = SELFPLAY ? d.ply[g] : 0;
         if (MODE == C4_EVAL_NET) {
             const float *o = d.net_out + (size_t)slot * 8;
-            float pf = (lane < 7) ? o[lane] : 0.f;
-            double value = (double)o[7];
+            const float ov = (lane < 8) ? o[lane] : 0.f;
+            if (d.memo) memo_insert(d, lc0, lc1, ov, lane);
+            float pf = (lane < 7) ? ov : 0.f;
+            double value = (double)__shfl_sync(FULL, ov, 7);
             apply_eval<true>(d, G, node, lc0, lc1, lage, value, 0.0, pf, is_root, ply);
             if (!is_root) {
                 uint32_t plo = (lane < plen) ? d.path[(size_t)g * PATH_CAP + lane] : 0u;
@@ -551,9 +611,19 @@ __global__ void __launch_bounds__(128, 8) k_advance(C4Dev d, int g0, int n_games
                 if (lane == 0) d.stat_evals[g] += 1ULL;
                 st = ST_READY;
             } else {
-                emit_request(d, G, pool, g0, parity, G.c0, G.c1, 0u, 0, 0u, 0u);
-                st = ST_WAIT;
-                break;
+                float ov;
+                if (MODE == C4_EVAL_NET && d.memo && memo_lookup(d, G.c0, G.c1, ov, lane)) {
+                    // the new root was evaluated before (usually as a leaf of the previous move's search)
+                    const int ply = SELFPLAY ? d.ply[g] : 0;
+                    apply_eval<true>(d, G, 0u, G.c0, G.c1, G.age, (double)__shfl_sync(FULL, ov, 7), 0.0,
+                                     (lane < 7) ? ov : 0.f, true, ply);
+                    if (lane == 0) d.stat_hits[g] += 1ULL;
+                    st = ST_READY;
+                } else {
+                    emit_request(d, G, pool, g0, parity, G.c0, G.c1, 0u, 0, 0u, 0u);
+                    st = ST_WAIT;
+                    break;
+                }
             }
         }
         if (G.sims_done >= d.sims) {
@@ -585,6 +655,17 @@ __global__ void __launch_bounds__(128, 8) k_advance(C4Dev d, int g0, int n_games
             if (lane == 0) d.stat_evals[g] += 1ULL;
             G.sims_done++;
             continue;
+        }
+        if (MODE == C4_EVAL_NET && d.memo) {
+            float ov;
+            if (memo_lookup(d, L.c0, L.c1, ov, lane)) {
+                const double value = (double)__shfl_sync(FULL, ov, 7);
+                apply_eval<true>(d, G, L.node, L.c0, L.c1, L.age, value, 0.0, (lane < 7) ? ov : 0.f, false, 0);
+                backup(G, L.path_lo, L.path_hi, L.depth, value);
+                if (lane == 0) d.stat_hits[g] += 1ULL;
+                G.sims_done++;
+                continue;
+            }
         }
         emit_request(d, G, pool, g0, parity, L.c0, L.c1, L.node, L.depth + 1, L.path_lo, L.path_hi);
         st = ST_WAIT;
@@ -628,7 +709,7 @@ __global__ void k_selfplay_init(C4Dev d, int max_games)
     }
     if (g >= max_games) return;
     d.sims_done[g] = 0; d.n_blocks[g] = 1; d.ply[g] = 0; d.path_len[g] = 0;
-    d.stat_evals[g] = 0; d.stat_positions[g] = 0;
+    d.stat_evals[g] = 0; d.stat_positions[g] = 0; d.stat_hits[g] = 0;
     if ((long long)g < d.n_games_target) {
         d.root_c0[g] = d.start_c0 ? d.start_c0[g] : 0ULL;
         d.root_c1[g] = d.start_c1 ? d.start_c1[g] : 0ULL;
@@ -695,19 +776,21 @@ __global__ void k_readout(C4Dev d, int n, int32_t *visits, double *value_sum, in
     }
 }
 
-__global__ void k_sum_stats(const unsigned long long *evals, const unsigned long long *positions, int n,
-                            unsigned long long *out)
+__global__ void k_sum_stats(const unsigned long long *evals, const unsigned long long *positions,
+                            const unsigned long long *hits, int n, unsigned long long *out)
 {
-    unsigned long long e = 0, p = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { e += evals[i]; p += positions[i]; }
-    __shared__ unsigned long long se[256], sp[256];
-    se[threadIdx.x] = e; sp[threadIdx.x] = p;
+    unsigned long long e = 0, p = 0, h = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { e += evals[i]; p += positions[i]; h += hits[i]; }
+    __shared__ unsigned long long se[256], sp[256], sh[256];
+    se[threadIdx.x] = e; sp[threadIdx.x] = p; sh[threadIdx.x] = h;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) { se[threadIdx.x] += se[threadIdx.x + s]; sp[threadIdx.x] += sp[threadIdx.x + s]; }
+        if ((int)threadIdx.x < s) {
+            se[threadIdx.x] += se[threadIdx.x + s]; sp[threadIdx.x] += sp[threadIdx.x + s]; sh[threadIdx.x] += sh[threadIdx.x + s];
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { out[0] = se[0]; out[1] = sp[0]; }
+    if (threadIdx.x == 0) { out[0] = se[0]; out[1] = sp[0]; out[2] = sh[0]; }
 }
 
 // generation sink: native_to_pytorch(add_fliplr=True) (oinkoink/neural/pytorch/data.py:78-105); one thread per
@@ -758,6 +841,9 @@ struct c4_ctx {
     cudaEvent_t ev_fork, ev_join[2];
     int n_search;                       // searches started by the last c4_search_begin
     long long cycle_limit;
+    unsigned long long memo_net_uid;    // network whose outputs the memo currently holds
+    long long last_memo_hits;           // memo hits during the last c4_selfplay_bench call
+    int memo_log2;                      // log2(entries) of the evaluation memo, 0 = disabled
     int budget_net;                     // terminal re-visits a game may play through per pass (NET / EXTERNAL)
     int last_pending;
     bool supplied;
@@ -817,7 +903,7 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     ctx->net = nullptr;
     ctx->parity = 0;
     ctx->n_search = 0;
-    ctx->budget_net = getenv("C4_BUDGET") ? atoi(getenv("C4_BUDGET")) : 8;
+    ctx->budget_net = getenv("C4_BUDGET") ? atoi(getenv("C4_BUDGET")) : 96;
     ctx->n_pools = getenv("C4_POOLS") ? atoi(getenv("C4_POOLS")) : 1;
     if (ctx->n_pools < 1 || ctx->n_pools > 2) ctx->n_pools = 1;
     ctx->net_ctas = getenv("C4_NET_CTAS") ? atoi(getenv("C4_NET_CTAS")) : 112;
@@ -828,7 +914,16 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     memset(&ctx->d, 0, sizeof(ctx->d));
     C4Dev &d = ctx->d;
     // a warp starts no further descent in a NET pass after this many SM cycles (bounds the tail of the pass; 0 = off)
-    ctx->cycle_limit = getenv("C4_CYCLE_LIMIT") ? atoll(getenv("C4_CYCLE_LIMIT")) : 20000;
+    ctx->cycle_limit = getenv("C4_CYCLE_LIMIT") ? atoll(getenv("C4_CYCLE_LIMIT")) : 160000;
+    ctx->last_memo_hits = 0;
+    ctx->memo_net_uid = 0;
+    {   // evaluation memo: 65536 entries per game slot, 2^14 .. 2^28 entries of 64 B (<= 16 GiB of the 180 GB HBM; the hit
+        // rate keeps rising with the size because 4096 games share openings); C4_MEMO_LOG2=0 disables
+        int lg = 14;
+        while (lg < 28 && (1LL << lg) < (long long)max_games * 65536) lg++;
+        if (getenv("C4_MEMO_LOG2")) lg = atoi(getenv("C4_MEMO_LOG2"));
+        ctx->memo_log2 = (lg >= 10 && lg <= 28) ? lg : 0;
+    }
     const size_t G = (size_t)max_games;
     d.blocks_per_game = cfg->simulations + 2;
     int rc = 0;
@@ -841,13 +936,13 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     A(d.root_c0, G); A(d.root_c1, G); A(d.status, G); A(d.sims_done, G); A(d.n_blocks, G);
     A(d.pending_node, G); A(d.pending_slot, G); A(d.path_len, G); A(d.ply, G);
     A(d.pend_c0, G); A(d.pend_c1, G); A(d.path, G * PATH_CAP); A(d.game_id, G);
-    A(d.stat_evals, G); A(d.stat_positions, G); A(d.staging, G * MAX_PLY);
+    A(d.stat_evals, G); A(d.stat_positions, G); A(d.stat_hits, G); A(d.staging, G * MAX_PLY);
     A(d.leaf_c0, G); A(d.leaf_c1, G); A(d.leaf_game, G);
     A(ctx->net_out, G * 8); A(ctx->ext_value, G);
     double *extp = nullptr;
     A(extp, G * 7);
     ctx->ext_prior = extp;
-    A(d.ctr, 1); A(ctx->stats_dev, 2);
+    A(d.ctr, 1); A(ctx->stats_dev, 4);
 #undef A
     d.net_out = ctx->net_out;
     d.ext_value = ctx->ext_value;
@@ -901,6 +996,8 @@ extern "C" int c4_ctx_get(c4_ctx *ctx, int key)
     case 1: return ctx->net_ctas;
     case 2: return ctx->budget_net;
     case 3: return ctx->max_games;
+    case 4: return ctx->d.memo ? ctx->memo_log2 : 0;
+    case 5: return (int)std::min<long long>(ctx->last_memo_hits, 0x7fffffff);
     default: return -1;
     }
 }
@@ -908,6 +1005,20 @@ extern "C" int c4_ctx_get(c4_ctx *ctx, int key)
 extern "C" int c4_ctx_set_net(c4_ctx *ctx, c4_net *net)
 {
     C4_REQUIRE(ctx, "c4_ctx_set_net: null context");
+    C4_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->memo_log2 > 0) {
+        // the memo caches THIS network's outputs: (re)start empty whenever the evaluator changes
+        const size_t bytes = ((size_t)1 << ctx->memo_log2) * 64;
+        if (!ctx->d.memo) {
+            uint32_t *m = nullptr;
+            if (cudaMalloc((void **)&m, bytes) != cudaSuccess) { c4_set_error("cudaMalloc of the evaluation memo failed"); return -2; }
+            ctx->allocs.push_back(m);
+            ctx->d.memo = m;
+            ctx->d.memo_mask = (uint32_t)(((size_t)1 << ctx->memo_log2) - 1);
+        }
+        if (c4_net_uid(net) != ctx->memo_net_uid) C4_CUDA(cudaMemset(ctx->d.memo, 0, bytes));
+        ctx->memo_net_uid = c4_net_uid(net);
+    }
     ctx->net = net;
     return 0;
 }
@@ -1205,21 +1316,22 @@ extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations,
         ctx->pool_parity[0] = ctx->pool_parity[1] = 0;
         ctx->pool_fresh = true;
     }
-    unsigned long long before[3], after[3];
+    unsigned long long before[4], after[4];
     C4Counters c;
-    k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, ctx->max_games, ctx->stats_dev);
-    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, d.stat_hits, ctx->max_games, ctx->stats_dev);
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if ((rc = read_counters(ctx, &c, s))) return rc;
-    before[0] = ctx->pinned[8]; before[1] = ctx->pinned[9]; before[2] = c.games_finished;
+    before[0] = ctx->pinned[8]; before[1] = ctx->pinned[9]; before[2] = c.games_finished; before[3] = ctx->pinned[10];
     int n_sampled = 0;
     const int sample_every = (net_ms || tree_ms) ? (int)std::max<int64_t>(1, iterations / N_SAMPLES) : 0;
     C4_CUDA(cudaEventRecord(ctx->ev0, s));
     if ((rc = selfplay_passes(ctx, eval_kind, (int)iterations, s, sample_every, &n_sampled))) return rc;
     C4_CUDA(cudaEventRecord(ctx->ev1, s));
-    k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, ctx->max_games, ctx->stats_dev);
-    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, d.stat_hits, ctx->max_games, ctx->stats_dev);
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if ((rc = read_counters(ctx, &c, s))) return rc;
-    after[0] = ctx->pinned[8]; after[1] = ctx->pinned[9]; after[2] = c.games_finished;
+    after[0] = ctx->pinned[8]; after[1] = ctx->pinned[9]; after[2] = c.games_finished; after[3] = ctx->pinned[10];
+    ctx->last_memo_hits = (long long)(after[3] - before[3]);
     float ms = 0.f;
     C4_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (evals) *evals = (int64_t)(after[0] - before[0]);

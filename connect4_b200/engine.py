@@ -186,7 +186,8 @@ class Engine():
         pools = self.lib.c4_ctx_get(self.h, 0) if k == EVAL_NET else 1
         return dict(positions=pos.value, evals=ev.value, sims=sims.value, games=games.value, device_ms=ms.value,
                     net_ms=nms.value, tree_ms=tms.value, iterations=int(iterations), pools=pools,
-                    net_ctas=self.lib.c4_ctx_get(self.h, 1))
+                    net_ctas=self.lib.c4_ctx_get(self.h, 1), memo_log2=self.lib.c4_ctx_get(self.h, 4),
+                    memo_hits=self.lib.c4_ctx_get(self.h, 5))
 
     def reset_pool(self):
         _lib.check(self.lib.c4_selfplay_reset(self.h, _lib.stream_ptr()))

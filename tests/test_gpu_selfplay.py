@@ -273,3 +273,25 @@ def test_generation_sink_matches_reference_tensors(tmp_path):
     ds = Connect4Dataset.load(str(tmp_path / "data.pth"))
     assert np.array_equal(ds.boards.numpy().astype(np.uint8), s["boards_t"]) and len(ds) == 2 * len(boards)
     assert os.path.exists(tmp_path / "games.pkl")
+
+
+def test_evaluation_memo_changes_work_not_results(monkeypatch):
+    """the device-side evaluation memo (Evaluator.position_table of the reference, evaluators.py:18-25) is a pure cache:
+    NN-guided self-play with it on and off produces identical records, and it does get hits"""
+    from connect4_b200.neural.game_pool import SelfPlayPool
+    model = _golden_model()
+    cfg = _cfg(64, 0.3, 0.25, 6)
+    recs = {}
+    for log2 in ("0", "18"):
+        monkeypatch.setenv("C4_MEMO_LOG2", log2)
+        pool = SelfPlayPool(model, cfg, concurrent_games=32, seed=11)
+        assert pool.engine.lib.c4_ctx_get(pool.engine.h, 4) == int(log2)
+        rec = pool.generate_records(64)
+        recs[log2] = rec[np.lexsort((rec["ply"], rec["game_id"]))]
+        stats = pool.throughput(50)
+        assert (stats["memo_hits"] > 0) == (log2 != "0")
+        pool.engine.close()
+    a, b = recs["0"], recs["18"]
+    assert len(a) == len(b)
+    for f in a.dtype.names:                       # field by field: bit-identical (NaN search values compare by bits)
+        assert a[f].tobytes() == b[f].tobytes(), f

@@ -126,8 +126,9 @@ def run_reference(args, rank):
     finally:
         pp.close()
     v = pos / secs
-    sample = "%d single-threaded workers x 32 games in flight, %d steps x %.0f s of self-play at 800 sims/move" % (
-        procs, args.steps, budget)
+    sample = ("%d single-threaded workers x 32 games in flight, %d steps x %.0f s of self-play at 800 sims/move (C oracle "
+              "tree + torch fp32 net + per-process evaluation memo like Evaluator.position_table)" % (
+                  procs, args.steps, budget))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(args.steps, 1), "higher_is_better": True,
@@ -289,8 +290,9 @@ def main():
             line["cpu_baseline"] = {
                 "value": r["positions_per_sec"], "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "%d single-threaded workers x 32 games in flight, %.0f s of self-play at 800 sims/move "
-                          "(C oracle tree + torch fp32 net); the unmodified Python reference measured 13 positions/s on "
-                          "8 cores (BASELINE.md)" % (cores, args.cpu_seconds),
+                          "(C oracle tree + torch fp32 net + per-process evaluation memo like the reference's "
+                          "Evaluator.position_table); the unmodified Python reference measured 13 positions/s on 8 cores "
+                          "(BASELINE.md)" % (cores, args.cpu_seconds),
                 "evals_per_sec": r["evals_per_sec"]}
         print(json.dumps(line), flush=True)
     if world > 1:

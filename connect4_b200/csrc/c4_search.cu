@@ -331,6 +331,14 @@ __device__ __forceinline__ Leaf descend(const C4Dev &d, const Game &G)
         C4NodeA a = ld_a(cn);
         C4NodeB b = ld_b(cn);
         const bool exists = (lane < 7) && (a.meta & C4_META_EXISTS);
+        // speculative prefetch: the descent is one dependent round trip per level and the scoring below is ~300 cycles of
+        // fp64 work, so every lane pulls ITS child's block (two 128-byte lines) towards L2 while the warp decides;
+        // HBM bandwidth is nowhere near a limit for this kernel (profiles/README.md)
+        if (exists && b.child_block != 0u) {
+            const char *pf = reinterpret_cast<const char *>(G.gp + (size_t)b.child_block * C4_SLOTS);
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(pf + 128));
+        }
         // ucb_score: pb_c = (log((N+base+1)/base)+init) * (sqrt(N)/(n+1)); score = pb_c*prior + value
         const double pbc = d.pbc[visits];
         const double sq = d.sqt[visits];                  // sqrt is exact in IEEE: table == __dsqrt_rn == math.sqrt

@@ -5,9 +5,10 @@ What it is: the reference's algorithm (oinkoink/neural/training_game.py:8-19 ove
 neural/training.py:209-216) with the tree work done by the C oracle (oracle/c4_oracle.c) and the network by the fp32
 torch restatement (oracle/net_ref.py) on the host cores.  Like the reference's game_pool + InferenceServer
 (neural/game_pool.py:15-49, inference_server.py:37-63) each worker keeps a set of games in flight and evaluates their
-pending leaves as one batch; one single-threaded worker process per core.  It is a faster arrangement than the
-reference's own Python (C tree code, no pipes, no GIL): the survey measured the unmodified reference at 1.08
-positions/s per core and 13 positions/s on 8 cores, this port does several times that.
+pending leaves as one batch, and memoises evaluations in a per-process table exactly like the reference's
+Evaluator.position_table (evaluators.py:18-25, game_pool.py:21-27); one single-threaded worker process per core.  It is a
+faster arrangement than the reference's own Python (C tree code, no pipes, no GIL): the survey measured the unmodified
+reference at 1.08 positions/s per core and 13 positions/s on 8 cores, this port does many times that.
 """
 import os
 import sys
@@ -46,39 +47,65 @@ def _new_search(g):
     g.update(tree=t, leaf=(a, b))
 
 
+def _finish_search(g):
+    """search finished: play the move (mcts.py:81-86); start the next search / the next game"""
+    S = _STATE
+    o = S["o"]
+    t = g["tree"]
+    age = o.age(g["c0"], g["c1"])
+    mv = t.sample_move(S["rng"].random()) if age < 6 else t.best_move()
+    g["c0"], g["c1"], res = o.drop(g["c0"], g["c1"], mv)
+    if res != o.RES_NONE:
+        g["c0"], g["c1"] = 0, 0
+    _new_search(g)
+
+
+def _advance(g):
+    """run game g until its pending leaf is NOT in the evaluation memo (Evaluator.position_table,
+    oinkoink/evaluators.py:18-25: one table per process shared by all its games); returns moves played"""
+    S = _STATE
+    o, table = S["o"], S["table"]
+    moves = hits = 0
+    while True:
+        hit = table.get(g["leaf"])
+        if hit is None:
+            return moves, hits
+        hits += 1
+        st, a, b = g["tree"].supply(hit[0], hit[1])
+        if st == o.DONE:
+            _finish_search(g)
+            moves += 1
+        else:
+            g["leaf"] = (a, b)
+
+
 def _step(budget_s):
-    """advance this worker's games for ~budget_s seconds; returns (positions, evals, elapsed)"""
+    """advance this worker's games for ~budget_s seconds; returns (positions, evals, elapsed, memo hits)"""
     S = _STATE
     o, nr, torch = S["o"], S["nr"], S["torch"]
     if S["games"] is None:
         S["cfg"] = o.make_config(S["sims"], 19652, 1.25, 0.3, 0.25, 6)
+        S["table"] = {}
         S["games"] = [dict(c0=0, c1=0) for _ in range(S["G"])]
         for g in S["games"]:
             _new_search(g)
-    games = S["games"]
-    positions = evals = 0
+    games, table = S["games"], S["table"]
+    positions = evals = hits = 0
     t0 = time.perf_counter()
     with torch.no_grad():
         while time.perf_counter() - t0 < budget_s:
+            for g in games:                                   # play through memo hits
+                m, h = _advance(g)
+                positions += m
+                hits += h
             c0 = np.array([g["leaf"][0] for g in games], np.uint64)
             c1 = np.array([g["leaf"][1] for g in games], np.uint64)
             v, p = nr.forward_state(S["sd"], nr.planes_from_bitboards(c0, c1))
             v, p = v.numpy(), p.numpy()
             evals += len(games)
             for i, g in enumerate(games):
-                st, a, b = g["tree"].supply(float(v[i]), p[i])
-                while st == o.DONE:                         # search finished: play the move (mcts.py:81-86)
-                    t = g["tree"]
-                    age = o.age(g["c0"], g["c1"])
-                    mv = t.sample_move(S["rng"].random()) if age < 6 else t.best_move()
-                    g["c0"], g["c1"], res = o.drop(g["c0"], g["c1"], mv)
-                    positions += 1
-                    if res != o.RES_NONE:
-                        g["c0"], g["c1"] = 0, 0
-                    _new_search(g)
-                    st, (a, b) = o.NEED_EVAL, g["leaf"]
-                g["leaf"] = (a, b)
-    return positions, evals, time.perf_counter() - t0
+                table[g["leaf"]] = (float(v[i]), p[i].copy())
+    return positions, evals, time.perf_counter() - t0, hits
 
 
 class PortPool:
@@ -100,9 +127,10 @@ class PortPool:
         wall = time.perf_counter() - t0
         pos = sum(r[0] for r in res)
         ev = sum(r[1] for r in res)
+        hits = sum(r[3] for r in res)
         busy = max(r[2] for r in res)
         return dict(positions=pos, evals=ev, seconds=busy, wall=wall, positions_per_sec=pos / busy,
-                    evals_per_sec=ev / busy)
+                    evals_per_sec=ev / busy, memo_hit_rate=hits / max(1, hits + ev))
 
     def close(self):
         self.pool.terminate()

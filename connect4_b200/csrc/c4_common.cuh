@@ -128,17 +128,23 @@ __device__ __forceinline__ double c4_evaluate_centre(u64 c0, u64 c1)
 }
 
 // ---------------------------------------------------------------- node pool layout
-// 32-byte node; the (<=7) children of a node form one 256-byte block of 8 slots (slot = column, slot 7 unused),
-// so one descent level is two fully used 128-byte lines read with 128-bit loads by lanes 0..6.
-struct __align__(16) C4NodeA {     // hot half: read by select, read-modify-written by backup
+// 32-byte node; the (<=7) children of a node form one 256-byte block of 8 slots (slot = column, slot 7 = block header),
+// so one descent level is two fully used 128-byte lines read with 128-bit loads by lanes 0..6.  Everything the PUCT
+// score of a child needs is in its own record, already in the form select consumes it:
+//   A = {value_sum, visit_count, meta}: meta bit0 exists, bit1 terminal, bits2-3 result code, bits 4.. = block index of
+//       this node's children (0 = not evaluated yet) -- the next level's address comes out of the same 16 bytes;
+//   B = {prior, vsel}: vsel = NodeData.value(side of the parent's mover) (oinkoink/tree.py:27-44): the terminal result,
+//       else value_sum / visit_count, else 0.0, flipped for x -- maintained by backup (ONE division per simulation and
+//       path node, in parallel lanes) instead of being recomputed by select at every level of every descent.
+// Header (slot 7): A = {position value, 0, 0}; B = {0.0, (parent node id << 32) | number of children}.
+struct __align__(16) C4NodeA {     // read by select, read-modify-written by backup
     double vsum;                   // SearchEvaluation.value_sum   (oinkoink/mcts.py:46-54)
     uint32_t visits;               // SearchEvaluation.visit_count (0 = search_value is None)
-    uint32_t meta;                 // bit0 exists, bit1 terminal, bits2-3 result code (value = code*0.5)
+    uint32_t meta;                 // flags + child block index (see above)
 };
-struct __align__(16) C4NodeB {     // cold half: written once at creation, child_block once at evaluation
+struct __align__(16) C4NodeB {
     double prior;                  // parent's PositionEvaluation.prior[this column], already normalised
-    uint32_t child_block;          // block index of this node's children (0 = not evaluated yet)
-    uint32_t parent;               // node id of the parent (debug / export)
+    double vsel;                   // side-relative value of this node as select sees it (header: packed parent / count)
 };
 struct __align__(32) C4Node {
     C4NodeA a;
@@ -148,6 +154,8 @@ static_assert(sizeof(C4Node) == 32, "node must be 32 bytes");
 
 #define C4_META_EXISTS 1u
 #define C4_META_TERMINAL 2u
+#define C4_META_FLAGS 15u
+#define C4_META_CB_SHIFT 4
 #define C4_SLOTS 8
 
 __device__ __forceinline__ uint32_t c4_make_meta(bool exists, int result)
@@ -160,6 +168,12 @@ __device__ __forceinline__ double c4_meta_value(uint32_t meta) { return (double)
 __device__ __forceinline__ int c4_meta_result(uint32_t meta)
 {
     return (meta & C4_META_TERMINAL) ? (int)((meta >> 2) & 3u) : C4_RES_NONE;
+}
+__device__ __forceinline__ uint32_t c4_meta_child_block(uint32_t meta) { return meta >> C4_META_CB_SHIFT; }
+// utils.value_to_side (oinkoink/utils.py:33-34): v for o (even age to move), 1 - v for x
+__device__ __forceinline__ double c4_side_value(double v_abs, int age_of_mover)
+{
+    return (age_of_mover & 1) ? __dsub_rn(1.0, v_abs) : v_abs;
 }
 
 // ---------------------------------------------------------------- warp helpers

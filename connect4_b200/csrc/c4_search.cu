@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "c4_common.cuh"
@@ -49,6 +50,8 @@ struct C4Dev {
     int blocks_per_game;
     const double *pbc;                  // pbc[N] = log((N + base + 1)/base) + init
     const double *sqt;                  // sqt[N] = sqrt(N)  (correctly rounded, = math.sqrt)
+    const double *rcp;                  // rcp[m] = 1.0 / m  (correctly rounded); rcp[0] unused
+    int fastdiv;                        // sqrt(N)/(n+1) by reciprocal table + two FMAs, verified exhaustively on the host
     int sims;
     double frac, one_minus_frac;
     float one_minus_frac_f;
@@ -105,7 +108,7 @@ __device__ __forceinline__ C4NodeB ld_b(const C4Node *n)
     C4NodeB b;
     uint4 v = *reinterpret_cast<const uint4 *>(&n->b);
     b.prior = __hiloint2double((int)v.y, (int)v.x);
-    b.child_block = v.z; b.parent = v.w;
+    b.vsel = __hiloint2double((int)v.w, (int)v.z);
     return b;
 }
 __device__ __forceinline__ void st_a(C4Node *n, double vsum, uint32_t visits, uint32_t meta)
@@ -114,12 +117,20 @@ __device__ __forceinline__ void st_a(C4Node *n, double vsum, uint32_t visits, ui
     v.x = (uint32_t)__double2loint(vsum); v.y = (uint32_t)__double2hiint(vsum); v.z = visits; v.w = meta;
     *reinterpret_cast<uint4 *>(&n->a) = v;
 }
-__device__ __forceinline__ void st_b(C4Node *n, double prior, uint32_t child_block, uint32_t parent)
+__device__ __forceinline__ void st_b(C4Node *n, double prior, double vsel)
 {
     uint4 v;
-    v.x = (uint32_t)__double2loint(prior); v.y = (uint32_t)__double2hiint(prior); v.z = child_block; v.w = parent;
+    v.x = (uint32_t)__double2loint(prior); v.y = (uint32_t)__double2hiint(prior);
+    v.z = (uint32_t)__double2loint(vsel); v.w = (uint32_t)__double2hiint(vsel);
     *reinterpret_cast<uint4 *>(&n->b) = v;
 }
+// block header (slot 7), second half of B: number of children and the parent's node id
+__device__ __forceinline__ double pack_header(uint32_t n_children, uint32_t parent)
+{
+    return __hiloint2double((int)parent, (int)n_children);
+}
+__device__ __forceinline__ uint32_t header_children(const C4NodeB &b) { return (uint32_t)__double2loint(b.vsel); }
+__device__ __forceinline__ uint32_t header_parent(const C4NodeB &b) { return (uint32_t)__double2hiint(b.vsel); }
 
 // sequential sum of the 7 per-lane values, left to right from 0.0 (numpy's add.reduce for n < 8)
 __device__ __forceinline__ double seq_sum7(double v)
@@ -275,33 +286,41 @@ __device__ __forceinline__ void apply_eval(const C4Dev &d, Game &G, uint32_t nod
     if (lane < 7) {
         int res = C4_RES_NONE;
         if (mine) { u64 a = c0, b = c1; res = c4_drop(a, b, age, lane); }
-        st_a(slot, 0.0, 0u, c4_make_meta(mine, res));
-        st_b(slot, mine ? p : 0.0, 0u, node);
+        const uint32_t m = c4_make_meta(mine, res);
+        st_a(slot, 0.0, 0u, m);
+        // a terminal child is worth its result to the mover here; an unvisited one 0.0 ("assume lost", tree.py:42-44)
+        st_b(slot, mine ? p : 0.0, (m & C4_META_TERMINAL) ? c4_side_value(c4_meta_value(m), age) : 0.0);
     } else if (lane == 7) {
-        st_a(slot, value, 0u, 0u);                                    // block header: position value, parent id, #children
-        st_b(slot, 0.0, (uint32_t)__popc(legal), node);
+        st_a(slot, value, 0u, 0u);                                    // block header: position value, #children, parent id
+        st_b(slot, 0.0, pack_header((uint32_t)__popc(legal), node));
     }
     if (lane == 0) {
         C4Node *n = G.gp + node;
-        st_a(n, __dadd_rn(0.0, value), 1u, C4_META_EXISTS);          // SearchEvaluation(): 0.0 + value, count 1
-        n->b.child_block = blk;
+        const double vs = __dadd_rn(0.0, value);                      // SearchEvaluation(): 0.0 + value, count 1
+        st_a(n, vs, 1u, C4_META_EXISTS | (blk << C4_META_CB_SHIFT));
+        if (node != 0u) n->b.vsel = c4_side_value(vs, age - 1);       // mean of one visit, seen by the parent's mover
     }
     __syncwarp();
 }
 
+// add `value` to one path node and refresh the side-relative mean select reads (depth = its distance from the root)
+__device__ __forceinline__ void backup_node(const Game &G, uint32_t id, int depth, double value)
+{
+    C4Node *n = G.gp + id;
+    C4NodeA a = ld_a(n);
+    const double vs = __dadd_rn(a.vsum, value);
+    const uint32_t vis = a.visits + 1u;
+    st_a(n, vs, vis, a.meta);
+    // float(search_value) = value_sum / visit_count (mcts.py:56-57), flipped for the mover at the PARENT (age + depth - 1);
+    // a terminal node keeps its result (NodeData.absolute_value, tree.py:27-38); the root is never selected
+    if (depth > 0 && !(a.meta & C4_META_TERMINAL))
+        n->b.vsel = c4_side_value(__ddiv_rn(vs, (double)vis), G.age + depth - 1);
+}
 // add `value` to the first `count` path nodes (lane i owns path entry i / i+32): oinkoink/mcts.py:164-168
 __device__ __forceinline__ void backup(Game &G, uint32_t path_lo, uint32_t path_hi, int count, double value)
 {
-    if (G.lane < count) {
-        C4Node *n = G.gp + path_lo;
-        C4NodeA a = ld_a(n);
-        st_a(n, __dadd_rn(a.vsum, value), a.visits + 1u, a.meta);
-    }
-    if (G.lane + 32 < count) {
-        C4Node *n = G.gp + path_hi;
-        C4NodeA a = ld_a(n);
-        st_a(n, __dadd_rn(a.vsum, value), a.visits + 1u, a.meta);
-    }
+    if (G.lane < count) backup_node(G, path_lo, G.lane, value);
+    if (G.lane + 32 < count) backup_node(G, path_hi, G.lane + 32, value);
     __syncwarp();
 }
 
@@ -314,8 +333,18 @@ struct Leaf {
     uint32_t path_lo, path_hi;
 };
 
+// order-preserving map of a finite double to an unsigned 64-bit key (+0.0 and -0.0 share a key)
+__device__ __forceinline__ u64 score_key(double x)
+{
+    u64 b = (u64)__double_as_longlong(x);
+    if ((b << 1) == 0ULL) b = 0ULL;
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
 // One descent from the root to a leaf: oinkoink/mcts.py:108-116 (the `while node.children` loop plus the
 // expand-then-select step, merged by eager expansion) with select_child / ucb_score (mcts.py:138-161).
+// The per-level dependent chain is what bounds the tree pass (profiles/README.md), so it is kept short:
+//   load {A,B} of the own child -> sqrt(N)/(n+1) -> two multiplies, one add -> 64-bit key -> two REDUX.MAX + one vote.
 __device__ __forceinline__ Leaf descend(const C4Dev &d, const Game &G)
 {
     const int lane = G.lane;
@@ -324,52 +353,45 @@ __device__ __forceinline__ Leaf descend(const C4Dev &d, const Game &G)
     L.path_lo = 0u; L.path_hi = 0u; L.node = 0u;
     C4NodeA ra = ld_a(G.gp);
     uint32_t visits = ra.visits, meta = ra.meta;
-    uint32_t child_block = G.gp->b.child_block;
     while (!(meta & C4_META_TERMINAL) && visits > 0u) {
-        const uint32_t blk = child_block;
+        const uint32_t blk = c4_meta_child_block(meta);
         const C4Node *cn = G.gp + (size_t)blk * C4_SLOTS + (lane & 7);
         C4NodeA a = ld_a(cn);
         C4NodeB b = ld_b(cn);
+        // exploration factor of the parent: log((N+base+1)/base)+init and sqrt(N) from host-built tables (glibc log / sqrt)
+        const double pbc = d.pbc[visits];
+        const double sq = d.sqt[visits];
         const bool exists = (lane < 7) && (a.meta & C4_META_EXISTS);
-        // speculative prefetch: the descent is one dependent round trip per level and the scoring below is ~300 cycles of
-        // fp64 work, so every lane pulls ITS child's block (two 128-byte lines) towards L2 while the warp decides;
+        // speculative prefetch: every lane pulls ITS child's block (two 128-byte lines) towards L2 while the warp decides;
         // HBM bandwidth is nowhere near a limit for this kernel (profiles/README.md)
-        if (exists && b.child_block != 0u) {
-            const char *pf = reinterpret_cast<const char *>(G.gp + (size_t)b.child_block * C4_SLOTS);
+        if (exists && c4_meta_child_block(a.meta) != 0u) {
+            const char *pf = reinterpret_cast<const char *>(G.gp + (size_t)c4_meta_child_block(a.meta) * C4_SLOTS);
             asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
             asm volatile("prefetch.global.L2 [%0];" :: "l"(pf + 128));
         }
-        // ucb_score: pb_c = (log((N+base+1)/base)+init) * (sqrt(N)/(n+1)); score = pb_c*prior + value
-        const double pbc = d.pbc[visits];
-        const double sq = d.sqt[visits];                  // sqrt is exact in IEEE: table == __dsqrt_rn == math.sqrt
-        double score = -1.0;
-        if (exists) {
-            double pb = __dmul_rn(pbc, __ddiv_rn(sq, (double)(a.visits + 1u)));
-            double ps = __dmul_rn(pb, b.prior);
-            double v;
-            if (a.meta & C4_META_TERMINAL) {
-                double av = c4_meta_value(a.meta);
-                v = (L.age & 1) ? __dsub_rn(1.0, av) : av;
-            } else if (a.visits > 0u) {
-                double av = __ddiv_rn(a.vsum, (double)a.visits);
-                v = (L.age & 1) ? __dsub_rn(1.0, av) : av;
-            } else {
-                v = 0.0;                                   // "position is unknown - assume lost" (tree.py:42-44)
-            }
-            score = __dadd_rn(ps, v);
+        // ucb_score: pb_c = (log(..)+init) * (sqrt(N)/(n+1)); score = pb_c*prior + value   (two roundings, no FMA)
+        const double den = (double)(a.visits + 1u);
+        double q;
+        if (d.fastdiv) {
+            // correctly rounded sqrt(N)/(n+1) from the correctly rounded reciprocal and two FMAs (Markstein's
+            // sequence); upload_config checked it against IEEE division for EVERY (N, n) pair this context can meet
+            const double y = d.rcp[a.visits + 1u];
+            const double q0 = __dmul_rn(sq, y);
+            q = __fma_rn(__fma_rn(-den, q0, sq), y, q0);
+        } else {
+            q = __ddiv_rn(sq, den);
         }
+        const double score = __dadd_rn(__dmul_rn(__dmul_rn(pbc, q), b.prior), b.vsel);
         // argmax over (score, column); equal scores -> highest column (Node.__gt__ on names, tree.py:11-15)
-        int col = lane & 7;
-#pragma unroll
-        for (int off = 4; off >= 1; off >>= 1) {
-            double os = __shfl_xor_sync(FULL, score, off);
-            int oc = __shfl_xor_sync(FULL, col, off);
-            if (os > score || (os == score && oc > col)) { score = os; col = oc; }
-        }
-        col = __shfl_sync(FULL, col, 0);
+        const u64 key = exists ? score_key(score) : 0ULL;
+        const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+        const uint32_t mhi = __reduce_max_sync(FULL, hi);
+        const bool cand = exists && hi == mhi;
+        const uint32_t mlo = __reduce_max_sync(FULL, cand ? lo : 0u);
+        const unsigned win = __ballot_sync(FULL, cand && lo == mlo);
+        const int col = 31 - __clz((int)win);
         visits = __shfl_sync(FULL, a.visits, col);
         meta = __shfl_sync(FULL, a.meta, col);
-        child_block = __shfl_sync(FULL, b.child_block, col);
         // replay the move on the register-resident board
         u64 bit = 1ULL << c4_drop_bit(L.c0 | L.c1, col);
         if (L.age & 1) L.c1 |= bit; else L.c0 |= bit;
@@ -464,7 +486,7 @@ __device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
 {
     const int lane = G.lane;
     const int side = G.age & 1;
-    const uint32_t blk = G.gp->b.child_block;
+    const uint32_t blk = c4_meta_child_block(ld_a(G.gp).meta);
     C4NodeA a = ld_a(G.gp + (size_t)blk * C4_SLOTS + (lane & 7));
     const bool exists = lane < 7 && (a.meta & C4_META_EXISTS);
     double v_side, v_abs;
@@ -610,7 +632,7 @@ __global__ void __launch_bounds__(128, 8) k_advance(C4Dev d, int g0, int n_games
             // Tree(board) + evaluate root (oinkoink/mcts.py:98-105): fresh pool, root = node 0 of block 0
             G.n_blocks = 1;
             G.sims_done = 0;
-            if (lane == 0) { st_a(G.gp, 0.0, 0u, C4_META_EXISTS); st_b(G.gp, 0.0, 0u, 0u); }
+            if (lane == 0) { st_a(G.gp, 0.0, 0u, C4_META_EXISTS); st_b(G.gp, 0.0, 0.0); }
             __syncwarp();
             if (MODE == C4_EVAL_CENTRE) {
                 const int ply = SELFPLAY ? d.ply[g] : 0;
@@ -740,9 +762,9 @@ __global__ void k_readout(C4Dev d, int n, int32_t *visits, double *value_sum, in
     const u64 c0 = d.root_c0[g], c1 = d.root_c1[g];
     const int side = c4_age(c0, c1) & 1;
     C4NodeA ra = ld_a(gp);
-    const uint32_t blk = gp->b.child_block;
+    const uint32_t blk = c4_meta_child_block(ra.meta);
     C4NodeA a; a.vsum = 0.0; a.visits = 0; a.meta = 0;
-    C4NodeB b; b.prior = 0.0; b.child_block = 0; b.parent = 0;
+    C4NodeB b; b.prior = 0.0; b.vsel = 0.0;
     if (blk != 0u) { a = ld_a(gp + (size_t)blk * C4_SLOTS + (lane & 7)); b = ld_b(gp + (size_t)blk * C4_SLOTS + (lane & 7)); }
     const bool exists = lane < 7 && (a.meta & C4_META_EXISTS);
     // the reference creates the root's children during the first simulation only
@@ -775,8 +797,8 @@ __global__ void k_readout(C4Dev d, int n, int32_t *visits, double *value_sum, in
         int nb = d.n_blocks[g], total = 0;
         for (int bI = 1 + lane; bI < nb; bI += 32) {
             C4NodeB h = ld_b(gp + (size_t)bI * C4_SLOTS + 7);
-            C4NodeA pa = ld_a(gp + h.parent);
-            if (pa.visits >= 2u) total += (int)h.child_block;
+            C4NodeA pa = ld_a(gp + header_parent(h));
+            if (pa.visits >= 2u) total += (int)header_children(h);
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) total += __shfl_xor_sync(FULL, total, off);
@@ -836,6 +858,7 @@ struct c4_ctx {
     std::vector<void *> allocs;
     double *pbc_dev;
     double *sqt_dev;
+    double *rcp_dev;
     float *net_out;
     double *ext_value;
     void *ext_prior;
@@ -873,18 +896,47 @@ static int dev_alloc(c4_ctx *ctx, T **p, size_t n)
     return 0;
 }
 
+// The select loop divides sqrt(N) by (n+1) with a table reciprocal and two FMAs.  That sequence is checked here against
+// IEEE division for every (N, n+1) pair a search of this capacity can produce (N, n+1 <= simulations + 1); if a single
+// pair differed (none does up to the 4096-simulation limit of the check) the kernel uses __ddiv_rn instead.
+static bool fastdiv_verified(int sims_cap)
+{
+    static std::mutex mu;
+    static int ok_cap = -1;             // every pair up to this capacity verified equal
+    static int bad_cap = 1 << 30;       // a pair below this capacity differed
+    if (sims_cap > 4096 || getenv("C4_NO_FASTDIV")) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (sims_cap <= ok_cap) return true;
+    if (sims_cap >= bad_cap) return false;
+    const int n = sims_cap + 2;
+    std::vector<double> q(n), r(n);
+    for (int i = 0; i < n; i++) { q[i] = sqrt((double)i); r[i] = i ? 1.0 / (double)i : 0.0; }
+    for (int N = 0; N < n; N++)
+        for (int m = 1; m < n; m++) {
+            if (N <= ok_cap + 1 && m <= ok_cap + 1) continue;
+            const double den = (double)m, q0 = q[N] * r[m];
+            const double qq = fma(fma(-den, q0, q[N]), r[m], q0);
+            if (qq != q[N] / den) { bad_cap = sims_cap; return false; }
+        }
+    ok_cap = sims_cap;
+    return true;
+}
+
 static int upload_config(c4_ctx *ctx, const c4_mcts_config *cfg)
 {
     C4_REQUIRE(cfg->simulations >= 0 && cfg->simulations <= ctx->sims_cap, "simulations exceeds the context capacity");
     C4_REQUIRE(cfg->pb_c_base > 0, "pb_c_base must be positive");
     ctx->cfg = *cfg;
-    std::vector<double> t(ctx->sims_cap + 2), q(ctx->sims_cap + 2);
+    std::vector<double> t(ctx->sims_cap + 2), q(ctx->sims_cap + 2), r(ctx->sims_cap + 2);
     for (int n = 0; n < (int)t.size(); n++) {                  // oinkoink/mcts.py:150-154, host libm log / sqrt
         t[n] = log(((double)n + cfg->pb_c_base + 1.0) / cfg->pb_c_base) + cfg->pb_c_init;
         q[n] = sqrt((double)n);
+        r[n] = n ? 1.0 / (double)n : 0.0;
     }
     C4_CUDA(cudaMemcpy(ctx->pbc_dev, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
     C4_CUDA(cudaMemcpy(ctx->sqt_dev, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice));
+    C4_CUDA(cudaMemcpy(ctx->rcp_dev, r.data(), r.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->d.fastdiv = fastdiv_verified(ctx->sims_cap) ? 1 : 0;
     ctx->d.sims = cfg->simulations;
     ctx->d.alpha = cfg->root_dirichlet_alpha;
     ctx->d.frac = cfg->root_exploration_fraction;
@@ -939,8 +991,10 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     A(d.pool, G * d.blocks_per_game * C4_SLOTS);
     A(ctx->pbc_dev, (size_t)cfg->simulations + 2);
     A(ctx->sqt_dev, (size_t)cfg->simulations + 2);
+    A(ctx->rcp_dev, (size_t)cfg->simulations + 2);
     d.pbc = ctx->pbc_dev;
     d.sqt = ctx->sqt_dev;
+    d.rcp = ctx->rcp_dev;
     A(d.root_c0, G); A(d.root_c1, G); A(d.status, G); A(d.sims_done, G); A(d.n_blocks, G);
     A(d.pending_node, G); A(d.pending_slot, G); A(d.path_len, G); A(d.ply, G);
     A(d.pend_c0, G); A(d.pend_c1, G); A(d.path, G * PATH_CAP); A(d.game_id, G);

@@ -15,9 +15,10 @@ RECORD_DTYPE = np.dtype({"names": ["c0", "c1", "policy", "result_value", "search
                          "offsets": [0, 8, 16, 44, 48, 52, 56, 57, 58, 59], "itemsize": 64})
 assert RECORD_DTYPE.itemsize == 64
 
+RAW_NODE_DTYPE = np.dtype([("vsum", "<f8"), ("visits", "<u4"), ("meta", "<u4"), ("prior", "<f8"), ("vsel", "<f8")])
+assert RAW_NODE_DTYPE.itemsize == 32
 NODE_DTYPE = np.dtype([("vsum", "<f8"), ("visits", "<u4"), ("meta", "<u4"), ("prior", "<f8"), ("child_block", "<u4"),
-                       ("parent", "<u4")])
-assert NODE_DTYPE.itemsize == 32
+                       ("parent", "<u4"), ("vsel", "<f8")])
 
 
 def _cfg_struct(cfg):
@@ -153,12 +154,24 @@ class Engine():
         return {k: v.cpu().numpy() for k, v in out.items()}
 
     def export_tree(self, game):
+        """node pool of one game as NODE_DTYPE records (the device packs the child block index into `meta` and keeps the
+        side-relative value select reads next to the prior; see c4_search_export_tree in include/c4b200.h)"""
         cap = (int(self.config.simulations) + 2) * 8
-        buf = np.zeros(cap, dtype=NODE_DTYPE)
+        raw = np.zeros(cap, dtype=RAW_NODE_DTYPE)
         n = C.c_int64(0)
-        _lib.check(self.lib.c4_search_export_tree(self.h, int(game), buf.ctypes.data_as(C.c_void_p), cap, C.byref(n),
+        _lib.check(self.lib.c4_search_export_tree(self.h, int(game), raw.ctypes.data_as(C.c_void_p), cap, C.byref(n),
                                                   _lib.stream_ptr()))
-        return buf[:n.value]
+        raw = raw[:n.value]
+        out = np.zeros(n.value, dtype=NODE_DTYPE)
+        out["vsum"], out["visits"], out["prior"] = raw["vsum"], raw["visits"], raw["prior"]
+        out["meta"] = raw["meta"] & 15
+        out["child_block"] = raw["meta"] >> 4
+        out["vsel"] = raw["vsel"]
+        hdr = np.arange(n.value) % 8 == 7                       # block headers: children count / parent slot
+        packed = raw["vsel"].view(np.uint64)
+        out["child_block"][hdr] = (packed[hdr] & 0xFFFFFFFF).astype(np.uint32)
+        out["parent"][hdr] = (packed[hdr] >> 32).astype(np.uint32)
+        return out
 
     # ------------------------------------------------------------------ self-play
     def selfplay(self, n_games, kind, game_id_base=0, game_id_stride=1, start=None):

@@ -146,7 +146,10 @@ int c4_search_readout(c4_ctx *ctx, int32_t n, int32_t *visits, double *value_sum
                       int32_t *root_visits, double *root_value_sum, double *root_prior, double *values_policy,
                       double *visit_policy, int8_t *best_move, double *best_value, int32_t *n_nodes, void *stream);
 /* Copy the node pool of one game to HOST memory (for Tree/NodeData views). nodes_out: capacity*32 bytes;
- * returns the number of 32-byte node slots written through n_slots (8 per block; block 0 slot 0 is the root). */
+ * returns the number of 32-byte node slots written through n_slots (8 per block; block 0 slot 0 is the root).
+ * Slot layout (little endian): f64 value_sum, u32 visit_count, u32 meta (bit0 exists, bit1 terminal, bits2-3 result code,
+ * bits 4.. block index of the children, 0 = not evaluated), f64 prior, f64 side-relative value used by select;
+ * slot 7 of a block is its header: f64 position value, 8 zero bytes, f64 0, u32 number of children, u32 parent slot. */
 int c4_search_export_tree(c4_ctx *ctx, int32_t game, void *nodes_out, int64_t capacity_slots, int64_t *n_slots,
                           void *stream);
 

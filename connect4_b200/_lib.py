@@ -71,7 +71,8 @@ RNG_NONE, RNG_PHILOX, RNG_INJECTED = 0, 1, 2
 
 
 def lib_path():
-    return _build.LIB
+    # C4_LIB: an alternative build of the SAME library (tools/build_variant.sh; kernel-variant experiments)
+    return os.environ.get("C4_LIB") or _build.LIB
 
 
 def load():

@@ -566,7 +566,10 @@ __device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
 // ------------------------------------------------------------------------------------------------ the pass kernel
 // MODE: C4_EVAL_EXTERNAL / C4_EVAL_CENTRE / C4_EVAL_NET.  One warp per game slot.
 template <int MODE, bool SELFPLAY>
-__global__ void __launch_bounds__(128, 8) k_advance(C4Dev d, int g0, int n_games, int pool, int parity, int budget, long long cycle_limit)
+#ifndef C4_ADV_MIN_BLOCKS
+#define C4_ADV_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int g0, int n_games, int pool, int parity, int budget, long long cycle_limit)
 {
     const int gi = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int g = g0 + gi;

@@ -12,6 +12,9 @@ class Game():
         self._board = board
         self.move_history = np.empty((0,), dtype='uint8')
 
+    def player_to_move(self):
+        return self._player_o if self._board.player_to_move == Side.o else self._player_x
+
     def play(self):
         if self.display:
             print("Game between", self._player_o, " and ", self._player_x)

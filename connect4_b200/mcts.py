@@ -32,13 +32,14 @@ class MCTSConfig():
 _ENGINES = {}
 
 
-def _engine(config, n):
-    """engines are cached per (capacity, simulations): creating one allocates the node pool"""
+def _engine(config, n, tag=None):
+    """engines are cached per (capacity, simulations, network): creating one allocates the node pool, and a context
+    keeps the evaluation memo of the network it last ran"""
     from .engine import Engine
     cap = 1
     while cap < n:
         cap *= 2
-    key = (cap, int(config.simulations))
+    key = (cap, int(config.simulations), tag)
     eng = _ENGINES.get(key)
     if eng is None:
         eng = Engine(cap, config)
@@ -59,9 +60,20 @@ def _host_evaluator(evaluator):
     return batch
 
 
+def device_kind(evaluator):
+    """('centre' | 'net' | 'external', ModelWrapper or None).  A bare ModelWrapper is accepted as an evaluator like in
+    the reference's `_match` (neural/training.py:189-195)."""
+    if isinstance(evaluator, Evaluator):
+        return evaluator.device_kind()
+    if hasattr(evaluator, "c4_net"):
+        return "net", evaluator
+    return "external", None
+
+
 def search_batch(config: MCTSConfig, boards: List[Board], evaluator, noise=None):
     """search() for many root positions at once (one GPU warp per tree). Returns (engine, trees-as-readout dict)."""
-    eng = _engine(config, len(boards))
+    kind, model = device_kind(evaluator)
+    eng = _engine(config, len(boards), id(model) if model is not None else None)
     c0 = np.array([int(b.color[0]) for b in boards], np.uint64)
     c1 = np.array([int(b.color[1]) for b in boards], np.uint64)
     if noise is not None:
@@ -69,7 +81,6 @@ def search_batch(config: MCTSConfig, boards: List[Board], evaluator, noise=None)
                     uniform=np.zeros((len(boards), 1)))
     else:
         eng.set_rng("none")
-    kind, model = evaluator.device_kind() if isinstance(evaluator, Evaluator) else ("external", None)
     eng.begin(c0, c1)
     if kind == "centre":
         eng.run("centre")

@@ -130,6 +130,43 @@ class ModelWrapper():
                                               _lib.stream_ptr()))
         return out[:, 7].contiguous(), out[:, :7].contiguous()
 
+    # ---- evaluation pass over a labelled set (model.py:180-198,307-342; TrainingLoop._evaluate, training.py:156-171)
+    def _eval_batches(self, data, batch_size, shuffle):
+        """yields (value_out, prior_out, value_label, prior_label-or-None) CUDA tensors per mini-batch; the positions
+        go plane tensor -> bitboards (c4_board_from_planes) -> CUDA tower, nothing is evaluated on the host."""
+        import torch
+        from ..board import BoardBatch
+        n = len(data)
+        order = torch.randperm(n) if shuffle else torch.arange(n)
+        for i in range(0, n, batch_size):
+            idx = order[i:i + batch_size]
+            planes = data.boards[idx].cuda()
+            bb = BoardBatch.from_planes(planes[:, -2], planes[:, -1])        # channels: [to-move,] o, x
+            v, p = self.evaluate_bitboards(bb.c0, bb.c1)
+            assert not torch.isnan(v).any() and not torch.isnan(p).any()
+            yield v, p, data.values[idx].cuda(), (None if data.priors is None else data.priors[idx].cuda())
+
+    def evaluate(self, data, batch_size: int = 4096, shuffle: bool = True):
+        """value MSE + policy BCE and the accuracy tallies of CombinedStats (model.py:307-328)"""
+        import torch.nn.functional as F
+        from .stats import CombinedStats
+        stats = CombinedStats()
+        for v, p, yv, yp in self._eval_batches(data, batch_size, shuffle):
+            assert v.shape == yv.shape and p.shape == yp.shape
+            stats.update(v.cpu().numpy(), yv.cpu().numpy(), F.mse_loss(v, yv).item(),
+                         p.cpu().numpy(), yp.cpu().numpy(), F.binary_cross_entropy(p, yp).item())
+        return stats
+
+    def evaluate_value_only(self, data):
+        """ValueStats over a value-labelled set such as the 8-ply positions (model.py:330-342)"""
+        import torch.nn.functional as F
+        from .stats import ValueStats
+        stats = ValueStats()
+        for v, _, yv, _ in self._eval_batches(data, 4096, True):
+            assert v.shape == yv.shape
+            stats.update(v.cpu().numpy(), yv.cpu().numpy(), F.mse_loss(v, yv).item())
+        return stats
+
     # ---- checkpoints (reference format)
     def save(self, folder_path: str):
         import torch

@@ -404,7 +404,95 @@ def gen_sink():
     print("sink:", tuple(bt.shape))
 
 
-PARTS = dict(board=gen_board, mcts_small=gen_mcts_small, mcts_kat=gen_mcts_kat, mcts_noise=gen_mcts_noise,
+def gen_storage():
+    """The reference's own generation sink on two deterministic games: games.pkl (neural/storage.py:12-17) and the
+    flip-augmented data.pth (neural/pytorch/data.py:52-64), byte-for-byte as the reference writes them."""
+    import shutil
+    import tempfile
+    from oinkoink.neural.training_game import training_game
+    from oinkoink.neural.pytorch.data import TrainingDataStorage
+    games = []
+    for sims in (30, 100):
+        player = MCTS("g", MCTSConfig(simulations=sims), evl.Evaluator(evl.evaluate_centre_with_prior))
+        games.append(training_game(player))
+    d = tempfile.mkdtemp()
+    TrainingDataStorage().save(games, d)
+    shutil.copy(os.path.join(d, "games.pkl"), os.path.join(HERE, "games_ref.pkl"))
+    shutil.copy(os.path.join(d, "data.pth"), os.path.join(HERE, "data_ref.pth"))
+    shutil.rmtree(d)
+    print("storage:", [len(g.moves) for g in games])
+
+
+def gen_eval():
+    """ModelWrapper.evaluate / evaluate_value_only (neural/pytorch/model.py:180-198,307-342) with ValueStats / PriorStats
+    (neural/stats.py) on a synthetic 8-ply-shaped labelled set, example_net.pth, CPU fp32."""
+    import torch
+    from oinkoink.neural.config import ModelConfig
+    from oinkoink.neural.pytorch.data import Connect4Dataset
+    from oinkoink.neural.pytorch.model import ModelWrapper
+    torch.set_num_threads(4)
+    torch.manual_seed(0)
+    mw = ModelWrapper(ModelConfig(use_gpu=False), "/root/reference/oinkoink/data/example_net.pth")
+    rng = random.Random(8)
+    boards = []
+    while len(boards) < 6000:
+        b = random_position(rng, 8)
+        if b is not None:
+            boards.append(b)
+    nrng = np.random.default_rng(8)
+    values = nrng.choice(np.array([0.0, 0.5, 1.0], np.float32), size=len(boards))
+    priors = np.zeros((len(boards), 7), np.float32)
+    for i in range(len(boards)):                     # one or two equally good moves (PriorStats accepts either)
+        k = nrng.choice(7, size=1 + int(nrng.integers(0, 2)), replace=False)
+        priors[i, k] = 1.0 / len(k)
+    bt = torch.FloatTensor(np.stack([b.to_array() for b in boards]))
+    vt, pt_ = torch.FloatTensor(values), torch.FloatTensor(priors)
+    with torch.no_grad():
+        vo, po = mw.net(bt)
+    combined = mw.evaluate(Connect4Dataset(bt, vt, pt_), batch_size=4096, shuffle=False)
+    value_only = mw.evaluate_value_only(Connect4Dataset(bt, vt, None))
+
+    def plain(d):
+        return {str(k): ({str(a): list(map(int, b)) for a, b in v.items()} if isinstance(v, dict) else float(v))
+                for k, v in d.items()}
+    np.savez_compressed(os.path.join(HERE, "eval_stats.npz"),
+                        c0=np.array([u64(b.color[0]) for b in boards]), c1=np.array([u64(b.color[1]) for b in boards]),
+                        values=values, priors=priors, value_out=vo.numpy(), prior_out=po.numpy(),
+                        combined=json.dumps(plain(combined.to_dict())), combined_repr=repr(combined),
+                        value_only=json.dumps(plain(value_only.to_dict())), value_only_repr=repr(value_only))
+    print("eval:", repr(combined))
+
+
+def gen_match():
+    """Match (match.py:14-76) between two different deterministic MCTS players over every 1-ply / 2-ply opening with
+    sides switched -- the shape of TrainingLoop._match (neural/training.py:176-207).  Per game: opening, move history,
+    result; plus the W/D/L dictionary the reference returns."""
+    from oinkoink.match import Match
+    out = {}
+    for mi, (plies, cfg1, cfg2) in enumerate([
+            (1, MCTSConfig(simulations=200), MCTSConfig(simulations=100, pb_c_init=2.5)),
+            (2, MCTSConfig(simulations=60), MCTSConfig(simulations=25, pb_c_init=0.8))]):
+        p1 = MCTS("one", cfg1, evl.Evaluator(evl.evaluate_centre_with_prior))
+        p2 = MCTS("two", cfg2, evl.Evaluator(evl.evaluate_centre_with_prior))
+        match = Match(False, p1, p2, plies=plies, switch=True)
+        starts = [(u64(g._board.color[0]), u64(g._board.color[1])) for g in match.games]
+        res = match.play()
+        out["m%d_plies" % mi] = np.int32(plies)
+        out["m%d_cfg" % mi] = np.array([[c.simulations, c.pb_c_base, c.pb_c_init] for c in (cfg1, cfg2)], np.float64)
+        out["m%d_c0" % mi] = np.array([s[0] for s in starts])
+        out["m%d_c1" % mi] = np.array([s[1] for s in starts])
+        out["m%d_n" % mi] = np.int32(match.n)
+        hist = np.full((len(match.games), 42), -1, np.int8)
+        for i, g in enumerate(match.games):
+            hist[i, :len(g.move_history)] = g.move_history
+        out["m%d_moves" % mi] = hist
+        out["m%d_result" % mi] = np.array([g._board.result.value for g in match.games], np.float64)
+        out["m%d_summary" % mi] = np.array([res["wins"], res["draws"], res["losses"], res["return"]], np.float64)
+        print("match", mi, res)
+    np.savez_compressed(os.path.join(HERE, "match.npz"), **out)
+
+
+PARTS = dict(match=gen_match, eval=gen_eval, storage=gen_storage, board=gen_board, mcts_small=gen_mcts_small, mcts_kat=gen_mcts_kat, mcts_noise=gen_mcts_noise,
              net=gen_net, games=gen_games, sink=gen_sink, mcts_sweep=gen_mcts_sweep)
 
 if __name__ == "__main__":

@@ -147,7 +147,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
     ap.add_argument("--passes", type=int, default=2000, help="lock-step passes per step")
-    ap.add_argument("--preroll", type=int, default=12000, help="untimed passes that bring the pool to steady state")
+    ap.add_argument("--preroll", type=int, default=0, help="untimed passes that bring the pool to steady state (0: use --preroll-seconds)")
+    ap.add_argument("--preroll-seconds", type=float, default=4.0,
+                    help="untimed device seconds of self-play before the warm-up steps (games at all plies, memo warm)")
     ap.add_argument("--e2e-games", type=int, default=16384, help="games of the end-to-end generation (4 pool-fulls)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
@@ -185,9 +187,10 @@ def main():
 
     # untimed: bring the pool to steady state (games at all plies), then W warm-up steps
     done = 0
-    while done < args.preroll:
-        n = min(4000, args.preroll - done)
-        pool.throughput(n)
+    pre_ms = 0.0
+    while (done < args.preroll) if args.preroll > 0 else (pre_ms < args.preroll_seconds * 1e3):
+        n = min(4000, args.preroll - done) if args.preroll > 0 else 2000
+        pre_ms += pool.throughput(n)["device_ms"]
         done += n
     for _ in range(args.warmup):
         pool.throughput(args.passes)
@@ -273,7 +276,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "games_per_gpu": args.games, "passes_per_step": args.passes,
-                       "preroll_passes": args.preroll, "simulations": SIMS, "evaluation_memo_log2_entries": memo_log2,
+                       "preroll_passes": done, "preroll_device_seconds": pre_ms / 1e3, "simulations": SIMS, "evaluation_memo_log2_entries": memo_log2,
                        "l2": "node pool (%.0f MB/GPU) + evaluation memo (%.1f GB) exceed L2; fresh leaves every pass" %
                              (args.games * (SIMS + 2) * 256 / 1e6, (64 << memo_log2) / 1e9 if memo_log2 else 0.0)},
             "clocks": clocks,

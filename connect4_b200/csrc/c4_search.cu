@@ -43,7 +43,12 @@ struct C4Counters {
     unsigned long long n_done;          // stand-alone searches finished
     unsigned long long overflow;        // records dropped (records_out too small)
     int leaf_count[2][2];               // [pool][parity] ping-pong leaf batch counters
+    int pad[32 - 14];
+    int stop_flag[2][2];                // [pool][parity], on its own 128-byte line: set by the warp whose request makes
+                                        // the batch reach the pass's stop count, polled (read-only) by the running warps
+    int pad2[28];
 };
+static_assert(sizeof(C4Counters) == 256, "counters: two 128-byte lines");
 
 struct C4Dev {
     C4Node *pool;
@@ -465,10 +470,15 @@ __device__ __forceinline__ int sample_child(double v, bool exists, int lane, dou
 }
 
 __device__ __forceinline__ void emit_request(const C4Dev &d, Game &G, int pool, int g0, int parity, u64 c0, u64 c1,
-                                             uint32_t node, int path_len, uint32_t path_lo, uint32_t path_hi)
+                                             uint32_t node, int path_len, uint32_t path_lo, uint32_t path_hi,
+                                             int stop_count = 0)
 {
     int slot = 0;
-    if (G.lane == 0) slot = g0 + atomicAdd(&d.ctr->leaf_count[pool][parity], 1);   // a pool's batch lives at [g0, g0 + n)
+    if (G.lane == 0) {
+        const int k = atomicAdd(&d.ctr->leaf_count[pool][parity], 1);               // a pool's batch lives at [g0, g0 + n)
+        if (stop_count > 0 && k + 1 == stop_count) d.ctr->stop_flag[pool][parity] = 1;
+        slot = g0 + k;
+    }
     slot = __shfl_sync(FULL, slot, 0);
     if (G.lane == 0) {
         d.leaf_c0[slot] = c0; d.leaf_c1[slot] = c1; d.leaf_game[slot] = G.g;
@@ -569,12 +579,12 @@ template <int MODE, bool SELFPLAY>
 #ifndef C4_ADV_MIN_BLOCKS
 #define C4_ADV_MIN_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int g0, int n_games, int pool, int parity, int budget, long long cycle_limit)
+__global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int g0, int n_games, int pool, int parity, int budget, long long cycle_limit, int stop_count)
 {
     const int gi = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int g = g0 + gi;
     const int lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) d.ctr->leaf_count[pool][parity ^ 1] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { d.ctr->leaf_count[pool][parity ^ 1] = 0; d.ctr->stop_flag[pool][parity ^ 1] = 0; }
     if (gi >= n_games) return;
     const long long t_start = clock64();
     int st = d.status[g];
@@ -630,6 +640,7 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
     }
 
     bool first_descent_done = false;
+    int waiting_seen = 0;
     for (;;) {
         if (st == ST_NEWROOT) {
             // Tree(board) + evaluate root (oinkoink/mcts.py:98-105): fresh pool, root = node 0 of block 0
@@ -653,7 +664,7 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
                     if (lane == 0) d.stat_hits[g] += 1ULL;
                     st = ST_READY;
                 } else {
-                    emit_request(d, G, pool, g0, parity, G.c0, G.c1, 0u, 0, 0u, 0u);
+                    emit_request(d, G, pool, g0, parity, G.c0, G.c1, 0u, 0, 0u, 0u, stop_count);
                     st = ST_WAIT;
                     break;
                 }
@@ -673,6 +684,14 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
         // bound the tail of the pass: the first descent is always allowed, later ones (after terminal re-visits) only
         // while the warp is inside its cycle budget
         if (cycle_limit > 0 && first_descent_done && clock64() - t_start > cycle_limit) break;
+        // ... and the pass ends for everybody once `stop_count` games of the pool wait for the network: the games still
+        // running would only keep the waiting ones from their answers (cold memo: most games miss at once and the
+        // pass lasts a simulation or two; warm memo: it runs until the usual share of games has missed)
+        // (the counter is read one simulation ahead of its use, so its L2 round trip is off the critical path)
+        if (stop_count > 0) {
+            if (first_descent_done && waiting_seen != 0) break;
+            waiting_seen = __ldcg(&d.ctr->stop_flag[pool][parity]);           // one broadcast L2 read per warp
+        }
         first_descent_done = true;
         Leaf L = descend(d, G);
         if (L.meta & C4_META_TERMINAL) {
@@ -700,7 +719,7 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
                 continue;
             }
         }
-        emit_request(d, G, pool, g0, parity, L.c0, L.c1, L.node, L.depth + 1, L.path_lo, L.path_hi);
+        emit_request(d, G, pool, g0, parity, L.c0, L.c1, L.node, L.depth + 1, L.path_lo, L.path_hi, stop_count);
         st = ST_WAIT;
         break;
     }
@@ -718,6 +737,7 @@ __global__ void k_search_begin(C4Dev d, const u64 *c0, const u64 *c1, int n, int
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) {
         d.ctr->leaf_count[0][0] = 0; d.ctr->leaf_count[0][1] = 0; d.ctr->leaf_count[1][0] = 0; d.ctr->leaf_count[1][1] = 0;
+        d.ctr->stop_flag[0][0] = 0; d.ctr->stop_flag[0][1] = 0; d.ctr->stop_flag[1][0] = 0; d.ctr->stop_flag[1][1] = 0;
         d.ctr->n_done = 0;
     }
     if (g >= max_games) return;
@@ -736,6 +756,7 @@ __global__ void k_selfplay_init(C4Dev d, int max_games)
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) {
         d.ctr->leaf_count[0][0] = 0; d.ctr->leaf_count[0][1] = 0; d.ctr->leaf_count[1][0] = 0; d.ctr->leaf_count[1][1] = 0;
+        d.ctr->stop_flag[0][0] = 0; d.ctr->stop_flag[0][1] = 0; d.ctr->stop_flag[1][0] = 0; d.ctr->stop_flag[1][1] = 0;
         d.ctr->games_finished = 0; d.ctr->n_records = 0; d.ctr->overflow = 0; d.ctr->n_done = 0;
         long long first = d.n_games_target < (long long)max_games ? d.n_games_target : (long long)max_games;
         d.ctr->next_game = (unsigned long long)first;
@@ -866,7 +887,7 @@ struct c4_ctx {
     double *ext_value;
     void *ext_prior;
     unsigned long long *stats_dev;      // [2]
-    unsigned long long *pinned;         // host pinned scratch (8 words)
+    unsigned long long *pinned;         // host pinned scratch (64 words: counters copy + stats at [40..])
     int parity;                         // single-pool paths (stand-alone searches)
     int pool_parity[2];                 // self-play half pools
     int n_pools;                        // 2: the tree pass of one half overlaps the network launch of the other
@@ -875,6 +896,8 @@ struct c4_ctx {
     cudaEvent_t ev_fork, ev_join[2];
     int n_search;                       // searches started by the last c4_search_begin
     long long cycle_limit;
+    double stop_frac;                   // a NET pass ends once this share of the live games waits for the network (0 = off)
+    long long live_games;               // upper bound of the games still being played (self-play tail)
     unsigned long long memo_net_uid;    // network whose outputs the memo currently holds
     long long last_memo_hits;           // memo hits during the last c4_selfplay_bench call
     int memo_log2;                      // log2(entries) of the evaluation memo, 0 = disabled
@@ -978,6 +1001,8 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     C4Dev &d = ctx->d;
     // a warp starts no further descent in a NET pass after this many SM cycles (bounds the tail of the pass; 0 = off)
     ctx->cycle_limit = getenv("C4_CYCLE_LIMIT") ? atoll(getenv("C4_CYCLE_LIMIT")) : 160000;
+    ctx->stop_frac = getenv("C4_STOP_FRAC") ? atof(getenv("C4_STOP_FRAC")) : 0.5;
+    ctx->live_games = max_games;
     ctx->last_memo_hits = 0;
     ctx->memo_net_uid = 0;
     {   // evaluation memo: 65536 entries per game slot, 2^14 .. 2^28 entries of 64 B (<= 16 GiB of the 180 GB HBM; the hit
@@ -1013,7 +1038,7 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     d.ext_value = ctx->ext_value;
     d.ext_prior = ctx->ext_prior;
     d.rng_mode = C4_RNG_NONE;
-    if (cudaMallocHost((void **)&ctx->pinned, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMallocHost((void **)&ctx->pinned, 64 * sizeof(unsigned long long)) != cudaSuccess) {
         c4_set_error("cudaMallocHost failed");
         c4_ctx_destroy(ctx);
         return -2;
@@ -1109,9 +1134,14 @@ static int launch_advance_pool(c4_ctx *ctx, int mode, int g0, int n_games, int p
     const int threads = 128, wpb = threads / 32;
     const int blocks = (n_games + wpb - 1) / wpb;
     switch (mode) {
-    case C4_EVAL_EXTERNAL: k_advance<C4_EVAL_EXTERNAL, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, 0LL); break;
-    case C4_EVAL_CENTRE: k_advance<C4_EVAL_CENTRE, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, 0LL); break;
-    case C4_EVAL_NET: k_advance<C4_EVAL_NET, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, ctx->cycle_limit); break;
+    case C4_EVAL_EXTERNAL: k_advance<C4_EVAL_EXTERNAL, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, 0LL, 0); break;
+    case C4_EVAL_CENTRE: k_advance<C4_EVAL_CENTRE, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, 0LL, 0); break;
+    case C4_EVAL_NET: {
+        long long live = std::min<long long>(ctx->live_games, (long long)n_games);
+        int stop = (SP && ctx->stop_frac > 0.0) ? std::max(1, (int)(ctx->stop_frac * (double)live)) : 0;
+        k_advance<C4_EVAL_NET, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, ctx->cycle_limit, stop);
+        break;
+    }
     default: c4_set_error("bad eval kind"); return -1;
     }
     C4_CUDA(cudaGetLastError());
@@ -1341,9 +1371,11 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
     ctx->pool_parity[0] = ctx->pool_parity[1] = 0;
     int rc;
     C4Counters c;
+    ctx->live_games = std::min<long long>(n_games, ctx->max_games);
     for (long long it = 0;; it++) {
         if ((rc = selfplay_passes(ctx, eval_kind, 64, s))) return rc;
         if ((rc = read_counters(ctx, &c, s))) return rc;
+        ctx->live_games = std::max<long long>(1, std::min<long long>(n_games - (long long)c.games_finished, ctx->max_games));
         if ((long long)c.games_finished >= n_games) break;
         C4_REQUIRE(it < (1LL << 24), "c4_selfplay_run: did not terminate");
     }
@@ -1372,6 +1404,7 @@ extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations,
     int rc;
     if (!ctx->pool_fresh) {
         d.n_games_target = (long long)1 << 60;
+        ctx->live_games = ctx->max_games;
         d.game_id_base = 0; d.game_id_stride = 1;
         d.start_c0 = nullptr; d.start_c1 = nullptr;
         d.records_out = nullptr; d.max_records = 0;
@@ -1384,18 +1417,18 @@ extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations,
     unsigned long long before[4], after[4];
     C4Counters c;
     k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, d.stat_hits, ctx->max_games, ctx->stats_dev);
-    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 40, ctx->stats_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if ((rc = read_counters(ctx, &c, s))) return rc;
-    before[0] = ctx->pinned[8]; before[1] = ctx->pinned[9]; before[2] = c.games_finished; before[3] = ctx->pinned[10];
+    before[0] = ctx->pinned[40]; before[1] = ctx->pinned[41]; before[2] = c.games_finished; before[3] = ctx->pinned[42];
     int n_sampled = 0;
     const int sample_every = (net_ms || tree_ms) ? (int)std::max<int64_t>(1, iterations / N_SAMPLES) : 0;
     C4_CUDA(cudaEventRecord(ctx->ev0, s));
     if ((rc = selfplay_passes(ctx, eval_kind, (int)iterations, s, sample_every, &n_sampled))) return rc;
     C4_CUDA(cudaEventRecord(ctx->ev1, s));
     k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, d.stat_hits, ctx->max_games, ctx->stats_dev);
-    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 8, ctx->stats_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 40, ctx->stats_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if ((rc = read_counters(ctx, &c, s))) return rc;
-    after[0] = ctx->pinned[8]; after[1] = ctx->pinned[9]; after[2] = c.games_finished; after[3] = ctx->pinned[10];
+    after[0] = ctx->pinned[40]; after[1] = ctx->pinned[41]; after[2] = c.games_finished; after[3] = ctx->pinned[42];
     ctx->last_memo_hits = (long long)(after[3] - before[3]);
     float ms = 0.f;
     C4_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));

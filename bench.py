@@ -14,8 +14,10 @@ advances each game to its next leaf, evaluates all leaves in one network launch 
   value = positions (root moves played) of all ranks / device time (CUDA events, max over ranks), inputs resident.
   e2e   = the same metric through the public API with HOST buffers: SelfPlayPool.generate_records() plays a whole
           generation from host-resident start positions and returns the position records to host memory.
-  roofline = the network kernel (dominant): algorithmic FLOPs per launch / its mean CUDA-event duration sampled inside
-          the timed region, against the measured sustained bf16 peak (MEASURED_PEAKS.json).
+  roofline = the dominant kernel of the step -- with the evaluation memo that is the tree pass k_advance (HBM class):
+          algorithmic bytes per launch (1.28 KB per simulation, SURVEY.md 8d, + 64 B per memo probe) / its mean
+          CUDA-event duration sampled inside the timed region, against the measured copy bandwidth; the network kernel's
+          TFLOP/s figure against the measured sustained bf16 peak (MEASURED_PEAKS.json) is reported as roofline_other.
   cpu_baseline = the oracle port (oracle/selfplay_port.py) on the box's host cores, bounded sample (rank 0, N=1 only).
 --impl reference: the CPU port alone, all host cores, same metric / config.
 """
@@ -261,7 +263,11 @@ def main():
         tree_share = (tree_ms * pools * n_pass / args.steps) / step_ms if secs else None
         net_share = (net_ms * pools * n_pass / args.steps) / step_ms if secs else None
         roof_tree = {"kernel": "k_advance<NET,selfplay> (warp-per-game tree pass)", "bound": "hbm", "achieved": tree_gbs,
-                     "peak": peak_hbm, "unit": "GB/s", "frac": (tree_gbs / peak_hbm) if tree_gbs else None, "traffic": None,
+                     "peak": peak_hbm, "unit": "GB/s", "frac": (tree_gbs / peak_hbm) if tree_gbs else None,
+                     "traffic": 53.9e6,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, ncu --set "
+                                       "full capture of the profiling command (profiles/r01_advance_v3_full_raw.csv; "
+                                       "shorter passes than the default run, see profiles/README.md)",
                      "peak_source": peak_src.replace("sustained bf16", "copy bandwidth"),
                      "algorithmic_bytes_per_launch": tree_bytes, "sims_per_launch": sims_per_launch,
                      "ms_per_launch": tree_ms, "share_of_step": tree_share,

@@ -24,7 +24,7 @@ class MCTSConfigC(C.Structure):
 class RecordC(C.Structure):
     _fields_ = [("c0", C.c_uint64), ("c1", C.c_uint64), ("policy", C.c_float * 7), ("result_value", C.c_float),
                 ("search_value", C.c_float), ("game_id", C.c_int32), ("move", C.c_int8), ("ply", C.c_int8),
-                ("n_moves", C.c_int8), ("result", C.c_int8)]
+                ("n_moves", C.c_int8), ("result", C.c_int8), ("reserved", C.c_int32)]
 
 
 assert C.sizeof(RecordC) == 64

@@ -49,6 +49,7 @@ struct C4Counters {
     int pad2[28];
 };
 static_assert(sizeof(C4Counters) == 256, "counters: two 128-byte lines");
+static_assert(sizeof(c4_record) == 64, "position record must be 64 bytes");
 
 struct C4Dev {
     C4Node *pool;
@@ -527,7 +528,7 @@ __device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
         rec->result_value = 0.f;
         rec->search_value = (float)mv_abs;
         rec->game_id = (int32_t)d.game_id[G.g];
-        rec->move = (int8_t)mv; rec->ply = (int8_t)ply; rec->n_moves = 0; rec->result = C4_RES_NONE;
+        rec->move = (int8_t)mv; rec->ply = (int8_t)ply; rec->n_moves = 0; rec->result = C4_RES_NONE; rec->reserved = 0;
         d.stat_positions[G.g] += 1ULL;
     }
     int res = c4_drop(G.c0, G.c1, G.age, mv);
@@ -549,6 +550,7 @@ __device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
                 t.result_value = (float)(res * 0.5);
                 t.n_moves = (int8_t)ply;
                 t.result = (int8_t)res;
+                t.reserved = 0;
                 d.records_out[base + r] = t;
             }
         } else if (lane == 0) {

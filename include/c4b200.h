@@ -165,6 +165,7 @@ typedef struct {
     int8_t ply;
     int8_t n_moves;       /* length of the finished game                                     */
     int8_t result;        /* result code                                                     */
+    int32_t reserved;     /* always 0 (keeps the record 64 bytes and a generation byte-reproducible) */
 } c4_record;
 
 /* Play `n_games` complete games (global ids game_id_base + i*game_id_stride) on the context's `max_games` slots,

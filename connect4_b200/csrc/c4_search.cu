@@ -1173,7 +1173,7 @@ static inline void pool_range(const c4_ctx *ctx, int pool, int *g0, int *n)
 
 extern "C" int c4_search_begin(c4_ctx *ctx, const uint64_t *c0, const uint64_t *c1, int32_t n, void *stream)
 {
-    C4_REQUIRE(ctx && c0 && c1, "c4_search_begin: null pointer");
+    C4_REQUIRE(ctx && (n == 0 || (c0 && c1)), "c4_search_begin: null pointer");
     C4_REQUIRE(n >= 0 && n <= ctx->max_games, "c4_search_begin: n exceeds max_games");
     C4_CUDA(cudaSetDevice(ctx->device));
     ctx->d.n_games_target = 0;

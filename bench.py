@@ -226,7 +226,8 @@ def main():
     # end to end through the public API with host buffers: one whole generation, records back on the host
     e2e = None
     if not args.no_e2e:
-        start = (np.zeros(args.e2e_games, np.uint64), np.zeros(args.e2e_games, np.uint64))   # host-resident inputs
+        start = (torch.zeros(args.e2e_games, dtype=torch.int64).pin_memory(),              # host-resident (pinned) inputs:
+                 torch.zeros(args.e2e_games, dtype=torch.int64).pin_memory())              # every game starts from the empty board
         pool2 = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=5000 + rank)
         pool2.generate_records(min(64, args.e2e_games), start=(start[0][:64], start[1][:64]))   # warm the path
         barrier()

@@ -849,27 +849,55 @@ __global__ void k_sum_stats(const unsigned long long *evals, const unsigned long
     if (threadIdx.x == 0) { out[0] = se[0]; out[1] = sp[0]; out[2] = sh[0]; }
 }
 
-// generation sink: native_to_pytorch(add_fliplr=True) (oinkoink/neural/pytorch/data.py:78-105); one thread per
-// output float of the board planes, originals first then mirrors.
-__global__ void k_augment_pack(const c4_record *__restrict__ rec, long long n, float *__restrict__ boards,
-                               float *__restrict__ values, float *__restrict__ priors)
+// generation sink: native_to_pytorch(add_fliplr=True) (oinkoink/neural/pytorch/data.py:78-105); originals first, then
+// mirrors.  HBM-write bound (536 B out per 64 B record).  Two consecutive rows of 126 plane floats are 63 aligned
+// float4, so one thread produces one float4 and a warp writes 512 contiguous bytes per store; where a plane float comes
+// from (to-move flag, or which bit of which colour) is a 126-entry table in shared memory; the 64-byte record is read
+// through L1 by the threads of its row.
+__global__ void __launch_bounds__(256) k_augment_pack(const c4_record *__restrict__ rec, long long n, float *__restrict__ boards,
+                                                     float *__restrict__ values, float *__restrict__ priors)
 {
-    const long long total = 2 * n * 126;
+    __shared__ unsigned char tab[126];                                    // (channel << 6) | bit index (board.py:147-154)
+    for (int k = threadIdx.x; k < 126; k += blockDim.x) {
+        const int ch = k / 42, px = k - ch * 42, rr = px / 7, c = px - rr * 7;
+        tab[k] = (unsigned char)((ch << 6) | (7 * c + (5 - rr)));
+    }
+    __syncthreads();
+    const long long total = n * 63;                                       // float4 units: 2n rows / 2 rows per 63 float4
+    float4 *out4 = reinterpret_cast<float4 *>(boards);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        long long row = e / 126;
-        int k = (int)(e - row * 126);
-        bool flip = row >= n;
+        const long long pair = e / 63;
+        const int f0 = 4 * (int)(e - pair * 63);                          // first of 4 floats inside the 252-float row pair
+        float v[4];
+        long long row_prev = -1;
+        u64 a = 0, b = 0;
+        float tomove = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int f = f0 + i;
+            const long long row = 2 * pair + (f >= 126);
+            const int k = f >= 126 ? f - 126 : f;
+            if (row != row_prev) {                                        // at most two records per thread
+                const bool flip = row >= n;
+                const c4_record &r = rec[flip ? row - n : row];
+                a = r.c0; b = r.c1;
+                if (flip) { a = c4_fliplr(a); b = c4_fliplr(b); }
+                tomove = ((__popcll(a | b) & 1) == 0) ? 1.f : 0.f;
+                row_prev = row;
+            }
+            const unsigned t = tab[k];
+            const u64 src = (t & 64u) ? a : b;
+            v[i] = (t < 64u) ? tomove : (float)((src >> (t & 63u)) & 1ULL);
+        }
+        out4[e] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    // values and priors: 8 floats per row, one thread per row
+    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < 2 * n; row += (long long)gridDim.x * blockDim.x) {
+        const bool flip = row >= n;
         const c4_record &r = rec[flip ? row - n : row];
-        u64 a = r.c0, b = r.c1;
-        if (flip) { a = c4_fliplr(a); b = c4_fliplr(b); }
-        int ch = k / 42, px = k - ch * 42, rr = px / 7, c = px - rr * 7;
-        int bit = 7 * c + (5 - rr);
-        float v;
-        if (ch == 0) v = ((__popcll(a | b) & 1) == 0) ? 1.f : 0.f;
-        else v = (float)(((ch == 1 ? a : b) >> bit) & 1ULL);
-        boards[e] = v;
-        if (k < 7) priors[row * 7 + k] = flip ? r.policy[6 - k] : r.policy[k];
-        if (k == 7) values[row] = r.result_value;
+        values[row] = r.result_value;
+#pragma unroll
+        for (int j = 0; j < 7; j++) priors[row * 7 + j] = flip ? r.policy[6 - j] : r.policy[j];
     }
 }
 
@@ -1457,9 +1485,9 @@ extern "C" int c4_records_augment_pack(const c4_record *records, int64_t n, floa
 {
     C4_REQUIRE(n >= 0 && (n == 0 || (records && boards && values && priors)), "c4_records_augment_pack: null pointer");
     if (n == 0) return 0;
-    long long total = 2 * n * 126;
+    long long total = n * 63;
     long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > 148 * 32) blocks = 148 * 32;
     k_augment_pack<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(records, n, boards, values, priors);
     C4_CUDA(cudaGetLastError());
     return 0;

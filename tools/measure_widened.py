@@ -68,6 +68,8 @@ ms = ev0.elapsed_time(ev1) / 10
 print(json.dumps({"row": "network kernel alone, 67,557 resident positions", "ms": ms, "positions_per_sec": n / ms * 1e3,
                   "tflops": n * model.flops_per_position / ms / 1e9}))
 rec = torch.zeros((500000, 64), dtype=torch.uint8, device="cuda")
+augment_pack(rec)                                    # warm: output tensors come from the caching allocator afterwards
+torch.cuda.synchronize()
 ev0.record()
 for _ in range(10):
     augment_pack(rec)

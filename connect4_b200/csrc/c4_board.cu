@@ -64,20 +64,40 @@ __global__ void k_fliplr(const u64 *__restrict__ c0, const u64 *__restrict__ c1,
     GRID_STRIDE(i, n) { f0[i] = c4_fliplr(c0[i]); f1[i] = c4_fliplr(c1[i]); }
 }
 
-// Board.to_array (oinkoink/board.py:147-154): one thread per output element so stores are coalesced.
+// Board.to_array (oinkoink/board.py:147-154).  HBM-write bound (126 plane values out per 16 bytes in).  A block stages
+// TP positions in shared memory -- one thread per (position, channel, row) task writes that row's 7 values -- and then
+// streams the tile to global memory with 128-bit stores (a tile of TP positions is a multiple of 16 bytes).
+#define TP 64
 template <typename T>
-__global__ void k_to_planes(const u64 *__restrict__ c0, const u64 *__restrict__ c1, T *__restrict__ planes, int64_t n)
+__global__ void __launch_bounds__(256) k_to_planes(const u64 *__restrict__ c0, const u64 *__restrict__ c1, T *__restrict__ planes,
+                                                  int64_t n)
 {
-    GRID_STRIDE(e, n * 126) {
-        int64_t i = e / 126;
-        int k = (int)(e - i * 126);
-        int ch = k / 42, px = k - ch * 42, r = px / 7, c = px - r * 7;
-        u64 a = c0[i], b = c1[i];
-        int bit = 7 * c + (5 - r);
-        int v;
-        if (ch == 0) v = ((c4_age(a, b) & 1) == 0);
-        else v = (int)(((ch == 1 ? a : b) >> bit) & 1ULL);
-        planes[e] = (T)v;
+    __shared__ __align__(16) T tile[TP * 126];
+    for (int64_t p0 = (int64_t)blockIdx.x * TP; p0 < n; p0 += (int64_t)gridDim.x * TP) {
+        const int np = (int)((n - p0 < TP) ? (n - p0) : TP);
+        for (int task = threadIdx.x; task < np * 18; task += blockDim.x) {
+            const int p = task / 18, cr = task - p * 18, ch = cr / 6, r = cr - ch * 6;
+            const u64 a = c0[p0 + p], b = c1[p0 + p];
+            T *dst = tile + p * 126 + cr * 7;
+            if (ch == 0) {
+                const T tm = (T)((c4_age(a, b) & 1) == 0);
+#pragma unroll
+                for (int c = 0; c < 7; c++) dst[c] = tm;
+            } else {
+                const u64 row = ((ch == 1 ? a : b) >> (5 - r));               // column c of this row at bit 7c
+#pragma unroll
+                for (int c = 0; c < 7; c++) dst[c] = (T)((row >> (7 * c)) & 1ULL);
+            }
+        }
+        __syncthreads();
+        const int nbytes = np * 126 * (int)sizeof(T);
+        char *g = reinterpret_cast<char *>(planes + p0 * 126);
+        const char *sm = reinterpret_cast<const char *>(tile);
+        const int nv = nbytes / 16;
+        for (int v = threadIdx.x; v < nv; v += blockDim.x)
+            reinterpret_cast<uint4 *>(g)[v] = reinterpret_cast<const uint4 *>(sm)[v];
+        for (int t = nv * 16 + threadIdx.x; t < nbytes; t += blockDim.x) g[t] = sm[t];     // tail of the last tile
+        __syncthreads();
     }
 }
 
@@ -154,12 +174,13 @@ extern "C" int c4_board_to_planes(const uint64_t *c0, const uint64_t *c1, void *
     C4_REQUIRE(n >= 0 && (n == 0 || (c0 && c1 && planes)), "c4_board_to_planes: null pointer");
     C4_REQUIRE(dtype == 0 || dtype == 1, "c4_board_to_planes: dtype must be 0 (uint8) or 1 (float32)");
     if (n == 0) return 0;
+    C4_REQUIRE(((uintptr_t)planes & 15) == 0, "c4_board_to_planes: planes must be 16-byte aligned");
+    const int64_t tiles = (n + TP - 1) / TP;
+    const int blocks = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
     if (dtype == 0)
-        k_to_planes<uint8_t><<<grid_for(n * 126, 256), 256, 0, (cudaStream_t)stream>>>((const u64 *)c0, (const u64 *)c1,
-                                                                                       (uint8_t *)planes, n);
+        k_to_planes<uint8_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const u64 *)c0, (const u64 *)c1, (uint8_t *)planes, n);
     else
-        k_to_planes<float><<<grid_for(n * 126, 256), 256, 0, (cudaStream_t)stream>>>((const u64 *)c0, (const u64 *)c1,
-                                                                                     (float *)planes, n);
+        k_to_planes<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const u64 *)c0, (const u64 *)c1, (float *)planes, n);
     LAUNCH_CHECK();
     return 0;
 }

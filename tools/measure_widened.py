@@ -78,3 +78,21 @@ ms = ev0.elapsed_time(ev1) / 10
 out_bytes = 2 * 500000 * (126 + 1 + 7) * 4
 print(json.dumps({"row": "c4_records_augment_pack, 500k records -> 1M rows of data.pth tensors", "ms": ms,
                   "GB_per_s_written": out_bytes / ms / 1e6}))
+
+# ---- batched bitboard kernels (c4_board.cu): HBM-bound elementwise passes over resident positions
+N = 1 << 24
+big = BoardBatch(torch.randint(0, 1 << 40, (N,), dtype=torch.int64, device="cuda"),
+                 torch.zeros(N, dtype=torch.int64, device="cuda"))
+def dev_time(fn, reps=10):
+    fn(); torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(reps):
+        fn()
+    ev1.record(); torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / reps
+for name, fn, nbytes in (("c4_board_legal_mask", lambda: big.legal_mask(), 17), ("c4_board_result", lambda: big.result(), 17),
+                         ("c4_board_fliplr", lambda: big.fliplr(), 32), ("c4_board_evaluate_centre", lambda: big.evaluate_centre(), 24),
+                         ("c4_board_to_planes(uint8)", lambda: big.to_planes("uint8"), 16 + 126)):
+    ms = dev_time(fn)
+    print(json.dumps({"row": "%s over %d resident positions" % (name, N), "ms": ms, "GB_per_s": N * nbytes / ms / 1e6,
+                      "bytes_per_position": nbytes}))

@@ -50,8 +50,8 @@ struct c4_net {
     int F, R, n_fc;
     unsigned long long uid;  // unique per created network (the engine's evaluation memo is keyed on it)
     bool fp16;            // operand element type of the conv GEMMs (false: bf16)
-    bool use_tc;          // tcgen05 kernel (filters == 32) instead of the mma.sync kernels
-    void *image_tc;       // device: [L][TC_WSTAGE_BYTES] weights + biases + head block
+    bool use_tc;          // tcgen05 kernel instead of the mma.sync kernels
+    void *image_tc;       // device: [L][WSTAGE_BYTES] weights + biases + head block (tcgen05 kernel)
     void *image;          // device: smem image (kernel A) / per-layer weight images (kernel B)
     size_t image_bytes;
     double flops;
@@ -464,28 +464,37 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
 //  * warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one thread), warps 2..9 = epilogue (TMEM lane
 //    quadrant = warp % 4, channel half = (warp - 2) / 4).  MMA(layer l+1, tile t) only waits for epilogue(l, tile t+1),
 //    so layers overlap tile by tile; no CTA-wide barrier inside a strip.
-#define TC_NB 16                       // boards per strip
-#define TC_T 7                         // M-tiles per full strip
-#define TC_ROWS 912                    // activation rows: 114 row-blocks (one extra zero block on each side)
-#define TC_KC 4                        // 16-byte k-chunks per pixel (32 channels)
-#define TC_NN 96                       // N = 3 dx x 32 output channels
-#define TC_ACT_BYTES (TC_KC * TC_ROWS * 16)
-#define TC_WSTAGE_BYTES (3 * TC_KC * TC_NN * 16)
-#define TC_WSTAGES 3
-#define TC_ACC_SLOTS 3
-#define TC_ACC_COL0 (TC_T * 32)
-#define TC_THREADS 576
-#define TC_EPI_WARPS 16                // 2 tile groups x 4 TMEM lane quadrants x 2 channel halves (16 channels per thread)
-#define TC_CH 16
-#define TC_GROUP_WARPS 8
-
-struct TcSmem {
+// Geometry of the kernel for one filter count.  F = 32: 16-board strips of 7 tiles, whole-layer weight stages (18 KB) in a
+// 3-deep ring, 3 accumulator slots, two epilogue groups of 8 warps (4 TMEM lane quadrants x 2 channel slices of 16) on
+// alternate tiles.  F = 64 (the reference's example_config network): N = 192 and K = 64 per tap row give 12 MMAs of 96
+// tensor cycles per tile -- four times the tensor work per hand-shake -- so one group of 16 warps (4 quadrants x 4 channel
+// slices) and a single accumulator slot keep up; strips are 6 boards (3 tiles) so that two activation buffers, one
+// 72 KB weight stage and the fp32 residual of the strip (3 x 64 TMEM columns) fit.
+template <int F_> struct TcC;
+template <> struct TcC<32> { static constexpr int F = 32, NB = 16, T = 7, ROWS = 912, WSTAGES = 3, ACC_SLOTS = 3, GROUPS = 2; };
+template <> struct TcC<64> { static constexpr int F = 64, NB = 6, T = 3, ROWS = 400, WSTAGES = 1, ACC_SLOTS = 1, GROUPS = 1; };
+#define TC_CH 16                       // channels per epilogue thread (one slice)
+#define TC_THREADS 576                 // warp 0 weight producer, warp 1 MMA issuer, warps 2..17 epilogue
+#define TC_EPI_WARPS 16
+template <int F_> struct TcK : TcC<F_> {
+    using C = TcC<F_>;
+    static constexpr int KC = C::F / 8;                                    // 16-byte k-chunks per pixel
+    static constexpr int NN = 3 * C::F;                                    // N = 3 dx x F output channels
+    static constexpr int SLICES = C::F / TC_CH;                            // channel slices of 16
+    static constexpr int GROUP_WARPS = 4 * SLICES;
+    static constexpr int ACT_BYTES = KC * C::ROWS * 16;
+    static constexpr int WSTAGE_BYTES = 3 * KC * NN * 16;
+    static constexpr int ACC_COL0 = C::T * C::F;                           // TMEM: residual stream first, then the slots
+    static_assert(GROUP_WARPS * C::GROUPS == TC_EPI_WARPS, "16 epilogue warps");
+    static_assert(ACC_COL0 + C::ACC_SLOTS * NN <= 512, "TMEM columns");
+    static_assert(16 * C::T >= 7 * C::NB && C::ROWS == 128 * C::T + 16, "strip geometry");
+    // shared memory map
     static constexpr int X = 0;
-    static constexpr int H = X + TC_ACT_BYTES;
-    static constexpr int W = H + TC_ACT_BYTES;
-    static constexpr int SMALL = W + TC_WSTAGES * TC_WSTAGE_BYTES;          // biases + head params (fp32)
-    __host__ __device__ static constexpr int scratch(int R) { return SMALL + ((1 + 2 * R) * 32 + HEAD_FLOATS) * 4; }
-    __host__ __device__ static constexpr int bars(int R) { return scratch(R) + 2 * TC_NB * 128 * 4; }   // [half][board][128]
+    static constexpr int H = X + ACT_BYTES;
+    static constexpr int W = H + ACT_BYTES;
+    static constexpr int SMALL = W + C::WSTAGES * WSTAGE_BYTES;            // biases + head params (fp32)
+    __host__ __device__ static constexpr int scratch(int R) { return SMALL + ((1 + 2 * R) * C::F + HEAD_FLOATS) * 4; }
+    __host__ __device__ static constexpr int bars(int R) { return scratch(R) + SLICES * C::NB * 128 * 4; }   // [slice][board][128]
     __host__ __device__ static constexpr int total(int R) { return bars(R) + 256; }
 };
 
@@ -584,32 +593,33 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *r)
 // whose tile counters differ by a multiple of 2T, i.e. always by the same group and the same thread.
 struct EpiCtx {
     uint32_t b_accfull, b_accempty, b_epi;
-    uint32_t tmem_acc;        // tmem + lane quadrant + TC_ACC_COL0 + 16 * half
-    uint32_t tmem_res;        // tmem + lane quadrant + 16 * half
-    unsigned char *dst_x, *dst_h;   // smem row of this thread in tile 0, k-chunk 2 * half
+    uint32_t tmem_acc;        // tmem + lane quadrant + ACC_COL0 + 16 * slice
+    uint32_t tmem_res;        // tmem + lane quadrant + 16 * slice
+    unsigned char *dst_x, *dst_h;   // smem row of this thread in tile 0, k-chunk 2 * slice
     const float *bias, *hp;
-    float *scratch;           // + half * TC_NB * 128
+    float *scratch;           // + slice * NB * 128
     uint32_t valid_mask;      // bit t: this thread's row of tile t is a real pixel of a board of this strip
     int lane, lm, lp, half, group, rb0, col8;
 };
 
-template <typename OP, int KIND>
+template <typename OP, int F, int KIND>
 __device__ __forceinline__ void tc_epilogue_layer(const EpiCtx &E, int l, int T, int c0)
 {
+    using K = TcK<F>;
     constexpr bool TO_RES = (KIND == 0 || KIND == 2), ADD_RES = (KIND == 2 || KIND == 3), LAST = (KIND == 3);
     unsigned char *dst = (KIND == 1) ? E.dst_h : E.dst_x;
-    const float *bl = E.bias + l * 32 + TC_CH * E.half;
+    const float *bl = E.bias + l * F + TC_CH * E.half;
 #pragma unroll 1
-    for (int t = (c0 + E.group) & 1; t < T; t += 2) {                     // tiles c = c0 + t with c % 2 == group
-        const int c = c0 + t, slot = c % TC_ACC_SLOTS;
-        mbar_wait(E.b_accfull + 8 * slot, (uint32_t)(c / TC_ACC_SLOTS) & 1u);
+    for (int t = (E.group + K::GROUPS - c0 % K::GROUPS) % K::GROUPS; t < T; t += K::GROUPS) {   // tiles c = c0 + t with c % GROUPS == group
+        const int c = c0 + t, slot = c % K::ACC_SLOTS;
+        mbar_wait(E.b_accfull + 8 * slot, (uint32_t)(c / K::ACC_SLOTS) & 1u);
         TC_FENCE_AFTER();
-        const uint32_t ta = E.tmem_acc + slot * TC_NN;
-        const uint32_t tr = E.tmem_res + 32 * t;
+        const uint32_t ta = E.tmem_acc + slot * K::NN;
+        const uint32_t tr = E.tmem_res + F * t;
         float em[TC_CH], ez[TC_CH], ep[TC_CH], rs[TC_CH];
         tmem_ld16(ta, em);
-        tmem_ld16(ta + 32, ez);
-        tmem_ld16(ta + 64, ep);
+        tmem_ld16(ta + F, ez);
+        tmem_ld16(ta + 2 * F, ep);
         if (ADD_RES) tmem_ld16(tr, rs);
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         TC_FENCE_BEFORE();
@@ -636,7 +646,7 @@ __device__ __forceinline__ void tc_epilogue_layer(const EpiCtx &E, int l, int T,
                 unsigned char *p = dst + (size_t)t * (128 * 16);
                 *reinterpret_cast<uint4 *>(p) =
                     make_uint4(OP::pack(v[0], v[1]), OP::pack(v[2], v[3]), OP::pack(v[4], v[5]), OP::pack(v[6], v[7]));
-                *reinterpret_cast<uint4 *>(p + TC_ROWS * 16) =
+                *reinterpret_cast<uint4 *>(p + K::ROWS * 16) =
                     make_uint4(OP::pack(v[8], v[9]), OP::pack(v[10], v[11]), OP::pack(v[12], v[13]), OP::pack(v[14], v[15]));
             }
         } else if (valid) {
@@ -647,7 +657,7 @@ __device__ __forceinline__ void tc_epilogue_layer(const EpiCtx &E, int l, int T,
             for (int j = 0; j < TC_CH; j++) {
                 a = fmaf(v[j], E.hp[HO_VW + TC_CH * E.half + j], a);
                 p0 = fmaf(v[j], E.hp[HO_PW + TC_CH * E.half + j], p0);
-                p1 = fmaf(v[j], E.hp[HO_PW + 32 + TC_CH * E.half + j], p1);
+                p1 = fmaf(v[j], E.hp[HO_PW + F + TC_CH * E.half + j], p1);
             }
             const int rb = 16 * t + E.rb0, b = rb / 7;
             float *sc = E.scratch + b * 128 + (rb - 7 * b - 1) * 7 + (E.col8 - 1);
@@ -660,8 +670,8 @@ __device__ __forceinline__ void tc_epilogue_layer(const EpiCtx &E, int l, int T,
     }
 }
 
-// global image: [L layers][TC_WSTAGE_BYTES] weights, then biases [(1+2R)*32] fp32, then head block [HEAD_FLOATS] fp32
-template <typename OP>
+// global image: [L layers][WSTAGE_BYTES] weights, then biases [(1+2R)*F] fp32, then head block [HEAD_FLOATS] fp32
+template <typename OP, int F>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__ c0, const u64 *__restrict__ c1, int n,
          const int *__restrict__ count, float *__restrict__ out, long long *__restrict__ dbg)
@@ -672,6 +682,7 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
 #else
 #define DBG_T(var)
 #endif
+    using K = TcK<F>;
     extern __shared__ __align__(16) unsigned char smem[];
     if (count) { int m = *count; n = m < n ? m : n; }
     // static, even partition of the batch over the grid
@@ -679,35 +690,35 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
     const int my_n = per + ((int)blockIdx.x < extra ? 1 : 0);
     const int my_first = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
     if (my_n == 0) return;
-    const int n_strips = (my_n + TC_NB - 1) / TC_NB;
+    const int n_strips = (my_n + K::NB - 1) / K::NB;
     const int L = 1 + 2 * R;
     // warp index through a broadcast so the compiler knows the role branches below are warp-uniform (otherwise every
     // shuffle of the epilogue is wrapped in WARPSYNC.COLLECTIVE)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
-    unsigned char *sX = smem + TcSmem::X, *sH = smem + TcSmem::H, *sW = smem + TcSmem::W;
-    float *small = reinterpret_cast<float *>(smem + TcSmem::SMALL);
-    const float *bias = small, *hp = small + L * 32;
-    float *scratch = reinterpret_cast<float *>(smem + TcSmem::scratch(R));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::bars(R));
-    const uint32_t b_wfull = smem_u32(bars), b_wempty = b_wfull + 8 * TC_WSTAGES;
-    const uint32_t b_accfull = b_wempty + 8 * TC_WSTAGES, b_accempty = b_accfull + 8 * TC_ACC_SLOTS;
-    const uint32_t b_epi = b_accempty + 8 * TC_ACC_SLOTS;                   // TC_T barriers
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_WSTAGES + 2 * TC_ACC_SLOTS + TC_T);
+    unsigned char *sX = smem + K::X, *sH = smem + K::H, *sW = smem + K::W;
+    float *small = reinterpret_cast<float *>(smem + K::SMALL);
+    const float *bias = small, *hp = small + L * F;
+    float *scratch = reinterpret_cast<float *>(smem + K::scratch(R));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + K::bars(R));
+    const uint32_t b_wfull = smem_u32(bars), b_wempty = b_wfull + 8 * K::WSTAGES;
+    const uint32_t b_accfull = b_wempty + 8 * K::WSTAGES, b_accempty = b_accfull + 8 * K::ACC_SLOTS;
+    const uint32_t b_epi = b_accempty + 8 * K::ACC_SLOTS;                   // T barriers
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * K::WSTAGES + 2 * K::ACC_SLOTS + K::T);
 
     // ---- one-time setup: zero the strips (pad rows/columns stay zero for ever), small params, barriers, TMEM
-    for (int i = threadIdx.x; i < 2 * TC_ACT_BYTES / 16; i += blockDim.x)
+    for (int i = threadIdx.x; i < 2 * K::ACT_BYTES / 16; i += blockDim.x)
         reinterpret_cast<uint4 *>(sX)[i] = make_uint4(0u, 0u, 0u, 0u);
     {
-        const unsigned char *src = image + (size_t)L * TC_WSTAGE_BYTES;
-        const int nb16 = (L * 32 + HEAD_FLOATS) * 4 / 16;
+        const unsigned char *src = image + (size_t)L * K::WSTAGE_BYTES;
+        const int nb16 = (L * F + HEAD_FLOATS) * 4 / 16;
         for (int i = threadIdx.x; i < nb16; i += blockDim.x)
             reinterpret_cast<uint4 *>(small)[i] = reinterpret_cast<const uint4 *>(src)[i];
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_WSTAGES; i++) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, 1); }
-        for (int i = 0; i < TC_ACC_SLOTS; i++) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, TC_GROUP_WARPS); }
-        for (int i = 0; i < TC_T; i++) mbar_init(b_epi + 8 * i, TC_GROUP_WARPS);
+        for (int i = 0; i < K::WSTAGES; i++) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, 1); }
+        for (int i = 0; i < K::ACC_SLOTS; i++) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, K::GROUP_WARPS); }
+        for (int i = 0; i < K::T; i++) mbar_init(b_epi + 8 * i, K::GROUP_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -721,14 +732,14 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ================= weight producer: layer g of the (strip, layer) sequence -> ring stage g % 3
+        // ================= weight producer: layer g of the (strip, layer) sequence -> ring stage g % WSTAGES
         if (lane == 0) {
             const int total = n_strips * L;
             for (int g = 0; g < total; g++) {
-                const int st = g % TC_WSTAGES, use = g / TC_WSTAGES;
+                const int st = g % K::WSTAGES, use = g / K::WSTAGES;
                 if (use > 0) mbar_wait(b_wempty + 8 * st, (use - 1) & 1);
-                mbar_expect_tx(b_wfull + 8 * st, TC_WSTAGE_BYTES);
-                bulk_g2s(smem_u32(sW + st * TC_WSTAGE_BYTES), image + (size_t)(g % L) * TC_WSTAGE_BYTES, TC_WSTAGE_BYTES,
+                mbar_expect_tx(b_wfull + 8 * st, K::WSTAGE_BYTES);
+                bulk_g2s(smem_u32(sW + st * K::WSTAGE_BYTES), image + (size_t)(g % L) * K::WSTAGE_BYTES, K::WSTAGE_BYTES,
                          b_wfull + 8 * st);
             }
         }
@@ -736,19 +747,19 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
         // ================= MMA issuer
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)OP::FMT << 7) | ((uint32_t)OP::FMT << 10) |
-                                   ((uint32_t)(TC_NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                                   ((uint32_t)(K::NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int g = 0, c = 0;                                   // (strip, layer) counter, (strip, layer, tile) counter
             for (int s = 0; s < n_strips; s++) {
-                const int nb = min(TC_NB, my_n - s * TC_NB);
+                const int nb = min(K::NB, my_n - s * K::NB);
                 const int T = (7 * nb + 15) / 16;
                 for (int l = 0; l < L; l++, g++) {
-                    const int st = g % TC_WSTAGES;
-                    mbar_wait(b_wfull + 8 * st, (g / TC_WSTAGES) & 1);
+                    const int st = g % K::WSTAGES;
+                    mbar_wait(b_wfull + 8 * st, (g / K::WSTAGES) & 1);
                     DBG_T(d0)
-                    const uint32_t wbase = smem_u32(sW + st * TC_WSTAGE_BYTES);
+                    const uint32_t wbase = smem_u32(sW + st * K::WSTAGE_BYTES);
                     const uint32_t abase = smem_u32((l == 0 || (l & 1) == 0) ? sH : sX);   // stem and conv2 read H
-                    const uint64_t a_l = umma_desc(abase, TC_ROWS * 16, 128);      // tile 0, dy = -1: buffer row 8 - 8
-                    const uint64_t b_l = umma_desc(wbase, TC_NN * 16, 128);
+                    const uint64_t a_l = umma_desc(abase, K::ROWS * 16, 128);      // tile 0, dy = -1: buffer row 8 - 8
+                    const uint64_t b_l = umma_desc(wbase, K::NN * 16, 128);
                     // epilogue arrivals seen so far on each tile barrier: (L + 1) per finished strip, l + 1 needed now
                     const uint32_t ep_par = (uint32_t)(s * (L + 1) + l) & 1u;
                     for (int t = 0; t < T; t++, c++) {
@@ -757,25 +768,26 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                         if (t == 0) mbar_wait(b_epi, ep_par);
                         if (t + 1 < T) mbar_wait(b_epi + 8 * (t + 1), ep_par);
                         DBG_T(d1)
-                        const int slot = c % TC_ACC_SLOTS, use = c / TC_ACC_SLOTS;
+                        const int slot = c % K::ACC_SLOTS, use = c / K::ACC_SLOTS;
                         if (use > 0) mbar_wait(b_accempty + 8 * slot, (use - 1) & 1);
                         DBG_T(d2)
                         TC_FENCE_AFTER();
-                        const uint32_t d = tmem + TC_ACC_COL0 + slot * TC_NN;
+                        const uint32_t d = tmem + K::ACC_COL0 + slot * K::NN;
                         // descriptors advance by adding 16-byte units to the start-address field:
-                        //   A: +8 per dy (8 rows), +2*TC_ROWS per 16-channel k-step;  B: +kc*96 per dy, +2*96 per k-step
+                        //   A: +8 per dy (8 rows), +2*ROWS per 16-channel k-step;  B: +kc*NN per dy, +2*NN per k-step
                         const uint64_t a = a_l + (uint64_t)(128 * t);
                         if (l != 0) {
-                            umma_f16c<0>(d, a, b_l, idesc);
-                            umma_f16c<1>(d, a + 2 * TC_ROWS, b_l + 2 * TC_NN, idesc);
-                            umma_f16c<1>(d, a + 8, b_l + 4 * TC_NN, idesc);
-                            umma_f16c<1>(d, a + 8 + 2 * TC_ROWS, b_l + 6 * TC_NN, idesc);
-                            umma_f16c<1>(d, a + 16, b_l + 8 * TC_NN, idesc);
-                            umma_f16c<1>(d, a + 16 + 2 * TC_ROWS, b_l + 10 * TC_NN, idesc);
+#pragma unroll
+                            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                                for (int ks = 0; ks < K::KC / 2; ks++) {
+                                    const uint64_t aa = a + 8 * dy + 2 * K::ROWS * ks, bb = b_l + (dy * K::KC + 2 * ks) * K::NN;
+                                    if (dy == 0 && ks == 0) umma_f16c<0>(d, aa, bb, idesc); else umma_f16c<1>(d, aa, bb, idesc);
+                                }
                         } else {
                             umma_f16c<0>(d, a, b_l, idesc);
-                            umma_f16c<1>(d, a + 8, b_l + 2 * TC_NN, idesc);
-                            umma_f16c<1>(d, a + 16, b_l + 4 * TC_NN, idesc);
+                            umma_f16c<1>(d, a + 8, b_l + 2 * K::NN, idesc);
+                            umma_f16c<1>(d, a + 16, b_l + 4 * K::NN, idesc);
                         }
                         umma_commit(b_accfull + 8 * slot);
                         DBG_T(d3)
@@ -789,23 +801,23 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
         }
     } else {
         // ================= epilogue warps
-        const int e = warp - 2, quad = warp & 3, half = (e >> 2) & 1, group = e >> 3;
+        const int e = warp - 2, quad = warp & 3, half = (e >> 2) % K::SLICES, group = e / K::GROUP_WARPS;   // half = channel slice
         const int et = threadIdx.x - 64;                                     // 0..511
         EpiCtx E;
         E.b_accfull = b_accfull; E.b_accempty = b_accempty; E.b_epi = b_epi;
-        E.tmem_acc = tmem + ((uint32_t)(quad * 32) << 16) + TC_ACC_COL0 + TC_CH * half;
+        E.tmem_acc = tmem + ((uint32_t)(quad * 32) << 16) + K::ACC_COL0 + TC_CH * half;
         E.tmem_res = tmem + ((uint32_t)(quad * 32) << 16) + TC_CH * half;
-        E.dst_x = sX + (size_t)(2 * half * TC_ROWS + 8 + 32 * quad + lane) * 16;
-        E.dst_h = sH + (size_t)(2 * half * TC_ROWS + 8 + 32 * quad + lane) * 16;
+        E.dst_x = sX + (size_t)(2 * half * K::ROWS + 8 + 32 * quad + lane) * 16;
+        E.dst_h = sH + (size_t)(2 * half * K::ROWS + 8 + 32 * quad + lane) * 16;
         E.bias = bias; E.hp = hp;
-        E.scratch = scratch + half * TC_NB * 128;
+        E.scratch = scratch + half * K::NB * 128;
         E.lane = lane; E.lm = (lane + 31) & 31; E.lp = (lane + 1) & 31; E.half = half; E.group = group;
         E.rb0 = 4 * quad + (lane >> 3); E.col8 = lane & 7;
         int c = 0;                                                           // global (strip, layer, tile) counter
         for (int s = 0; s < n_strips; s++) {
-            const int nb = min(TC_NB, my_n - s * TC_NB);
+            const int nb = min(K::NB, my_n - s * K::NB);
             const int T = (7 * nb + 15) / 16;
-            const int first = my_first + s * TC_NB;
+            const int first = my_first + s * K::NB;
             E.valid_mask = 0;
             for (int t = 0; t < T; t++) {
                 const int rb = 16 * t + E.rb0, b = rb / 7;
@@ -820,19 +832,19 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                 const uint32_t o = (uint32_t)((a0 >> bit) & 1ULL) * OP::ONE, x = (uint32_t)((a1 >> bit) & 1ULL) * OP::ONE;
                 const int row = 8 + (7 * b + 1 + r) * 8 + (col + 1);
                 *reinterpret_cast<uint4 *>(sH + (size_t)row * 16) = make_uint4(tomove | (o << 16), x, 0u, 0u);
-                *reinterpret_cast<uint4 *>(sH + (size_t)(TC_ROWS + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4 *>(sH + (size_t)(K::ROWS + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
             }
             TC_PROXY_FENCE();
             EPI_BAR();
-            if (lane == 0 && e < TC_GROUP_WARPS)                             // 8 arrivals per tile barrier and epoch
+            if (lane == 0 && e < K::GROUP_WARPS)                             // GROUP_WARPS arrivals per tile barrier and epoch
                 for (int t = 0; t < T; t++) mbar_arrive(b_epi + 8 * t);
 
-            tc_epilogue_layer<OP, 0>(E, 0, T, c); c += T;
+            tc_epilogue_layer<OP, F, 0>(E, 0, T, c); c += T;
             for (int l = 1; l < L - 1; l += 2) {
-                tc_epilogue_layer<OP, 1>(E, l, T, c); c += T;
-                if (l + 1 < L - 1) { tc_epilogue_layer<OP, 2>(E, l + 1, T, c); c += T; }
+                tc_epilogue_layer<OP, F, 1>(E, l, T, c); c += T;
+                if (l + 1 < L - 1) { tc_epilogue_layer<OP, F, 2>(E, l + 1, T, c); c += T; }
             }
-            tc_epilogue_layer<OP, 3>(E, L - 1, T, c); c += T;
+            tc_epilogue_layer<OP, F, 3>(E, L - 1, T, c); c += T;
 
             // ---- head tails: one warp per board
             EPI_BAR();
@@ -840,7 +852,10 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                 float *sc = scratch + b * 128;
                 for (int i = lane; i < 126; i += 32) {
                     float bb = i < 42 ? hp[HO_VB] : (i < 84 ? hp[HO_PB] : hp[HO_PB + 1]);
-                    sc[i] = leaky((sc[i] + sc[TC_NB * 128 + i]) + bb);
+                    float acc = sc[i];                                       // channel slices summed in a fixed order
+#pragma unroll
+                    for (int q = 1; q < K::SLICES; q++) acc += sc[q * K::NB * 128 + i];
+                    sc[i] = leaky(acc + bb);
                 }
                 __syncwarp();
                 head_tail(sc, hp, out + (size_t)(first + b) * 8, lane);
@@ -959,32 +974,40 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
                         84.0 * 7);
     if (cudaMalloc(&net->image, total) != cudaSuccess) { delete net; c4_set_error("cudaMalloc failed"); return -2; }
     C4_CUDA(cudaMemcpy(net->image, img.data(), total, cudaMemcpyHostToDevice));
-    net->use_tc = (F == 32) && kernel_sel != 1 && TcSmem::total(R) <= 227 * 1024;
+    const int tc_smem = (F == 32) ? TcK<32>::total(R) : TcK<64>::total(R);
+    net->use_tc = kernel_sel != 1 && tc_smem <= 227 * 1024;
     net->image_tc = nullptr;
     if (net->use_tc) {
-        // tcgen05 image: per layer [dy][k-chunk][n = dx*32 + co][8 ci] 16-bit, K-major SWIZZLE_NONE core matrices
+        // tcgen05 image: per layer [dy][k-chunk][n = dx*F + co][8 ci] 16-bit, K-major SWIZZLE_NONE core matrices
         const int L = 1 + 2 * R;
-        const size_t small_bytes = (size_t)(L * 32 + HEAD_FLOATS) * 4;
-        std::vector<unsigned char> tc((size_t)L * TC_WSTAGE_BYTES + small_bytes, 0);
+        const int KC = F / 8, NN = 3 * F;
+        const size_t stage = (size_t)3 * KC * NN * 16;
+        const size_t small_bytes = (size_t)(L * F + HEAD_FLOATS) * 4;
+        std::vector<unsigned char> tc((size_t)L * stage + small_bytes, 0);
         const float *q = blob + 4;
         for (int l = 0; l < L; l++) {
-            const int cin = l == 0 ? 3 : 32, kc = l == 0 ? 2 : TC_KC;
-            uint16_t *dst = reinterpret_cast<uint16_t *>(tc.data() + (size_t)l * TC_WSTAGE_BYTES);
-            for (int co = 0; co < 32; co++)
+            const int cin = l == 0 ? 3 : F, kc = l == 0 ? 2 : KC;
+            uint16_t *dst = reinterpret_cast<uint16_t *>(tc.data() + (size_t)l * stage);
+            for (int co = 0; co < F; co++)
                 for (int ci = 0; ci < cin; ci++)
                     for (int ky = 0; ky < 3; ky++)
                         for (int kx = 0; kx < 3; kx++) {
                             float w = q[((co * cin + ci) * 3 + ky) * 3 + kx];
-                            size_t idx = ((size_t)(ky * kc + ci / 8) * TC_NN + (kx * 32 + co)) * 8 + (ci % 8);
+                            size_t idx = ((size_t)(ky * kc + ci / 8) * NN + (kx * F + co)) * 8 + (ci % 8);
                             dst[idx] = fp16 ? f2h(w) : f2bf(w);
                         }
-            q += (size_t)32 * cin * 9 + 32;
+            q += (size_t)F * cin * 9 + F;
         }
-        memcpy(tc.data() + (size_t)L * TC_WSTAGE_BYTES, bias, small_bytes);     // biases + head block, as in image A
+        memcpy(tc.data() + (size_t)L * stage, bias, small_bytes);               // biases + head block, as in image A
         if (cudaMalloc(&net->image_tc, tc.size()) != cudaSuccess) { delete net; c4_set_error("cudaMalloc failed"); return -2; }
         C4_CUDA(cudaMemcpy(net->image_tc, tc.data(), tc.size(), cudaMemcpyHostToDevice));
-        C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(R)));
-        C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::total(R)));
+        if (F == 32) {
+            C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpFP16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem));
+            C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpBF16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem));
+        } else {
+            C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpFP16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem));
+            C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpBF16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem));
+        }
     }
     if (F == 32) {
         C4_REQUIRE((smem_resident<32, WARPS_A>(R)) <= 227 * 1024, "c4_net_create: F=32 network too deep for the resident kernel");
@@ -1031,11 +1054,13 @@ int c4_net_forward_ex(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64
     cudaStream_t s = (cudaStream_t)stream;
     if (net->use_tc) {
         int grid = (int)std::min<int64_t>(std::max(1, std::min(max_ctas, 148)), n);
-        auto k = net->fp16 ? k_net_tc<OpFP16> : k_net_tc<OpBF16>;
+        auto k = net->F == 32 ? (net->fp16 ? k_net_tc<OpFP16, 32> : k_net_tc<OpBF16, 32>)
+                              : (net->fp16 ? k_net_tc<OpFP16, 64> : k_net_tc<OpBF16, 64>);
+        const int tc_smem = net->F == 32 ? TcK<32>::total(net->R) : TcK<64>::total(net->R);
         static long long *dbg = nullptr;
         static bool dbg_on = getenv("C4_TC_DEBUG") != nullptr;
         if (dbg_on && !dbg) { cudaMalloc(&dbg, 16 * sizeof(long long)); cudaMemset(dbg, 0, 16 * sizeof(long long)); }
-        k<<<grid, TC_THREADS, TcSmem::total(net->R), s>>>((const unsigned char *)net->image_tc, net->R, (const u64 *)c0,
+        k<<<grid, TC_THREADS, tc_smem, s>>>((const unsigned char *)net->image_tc, net->R, (const u64 *)c0,
                                                          (const u64 *)c1, (int)n, count, out, dbg);
         if (dbg_on) {
             long long h[16];

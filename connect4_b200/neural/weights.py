@@ -44,7 +44,7 @@ def fold_state_dict(sd, operand_dtype="fp16", kernel="auto"):
     """operand_dtype: element type of the tensor-core conv GEMMs (accumulation is always fp32). fp16 is the default
     because bf16 operands miss the 1e-2 parity bound on the reference's trained checkpoint."""
     F, R, n_fc = net_shape(sd)
-    # kernel: "auto" = tcgen05/TMEM tower when filters == 32 (else the mma.sync kernels); "mma" forces mma.sync
+    # kernel: "auto" = tcgen05/TMEM tower (32 and 64 filters); "mma" forces the mma.sync kernels
     parts = [np.array([MAGIC, F, R, n_fc | (OPERAND_DTYPES[operand_dtype] << 8) | (KERNELS[kernel] << 16)], np.float64)]
     w, b = _fold(sd, "body.0.0.weight", None, "body.0.1")
     parts += [w.reshape(-1), b]

@@ -160,3 +160,30 @@ def test_tcgen05_and_mma_sync_kernels_agree():
     v3, p3 = tc.evaluate_bitboards(g["c0"][perm], g["c1"][perm])
     v1, p1 = tc.evaluate_bitboards(g["c0"], g["c1"])
     assert torch.equal(v3, v1[torch.as_tensor(perm).cuda()]) and torch.equal(p3, p1[torch.as_tensor(perm).cuda()])
+
+
+def test_tcgen05_kernel_for_64_filter_networks():
+    """the example_config network (64 filters / 6 residual / 6 fc) runs on the tcgen05 kernel too (N = 192, K = 64 per tap
+    row, 6-board strips): within tolerance of the reference's torch outputs, close to the mma.sync tower, and
+    independent of the batch position -- for batch sizes around the strip (6) and grid (148) boundaries"""
+    import torch
+    from connect4_b200.neural.config import ModelConfig, NetConfig
+    from connect4_b200.neural.model import ModelWrapper
+    g = golden("net_outputs.npz")
+    cfg = ModelConfig(net_config=NetConfig(filters=64, n_fc_layers=6, n_residuals=6))
+    torch.manual_seed(0)
+    tc = ModelWrapper(cfg, kernel="auto")
+    torch.manual_seed(0)
+    mma = ModelWrapper(cfg, kernel="mma")
+    nb = len(g["big_value"])
+    for n in (1, 5, 6, 7, 147, 148, 149, 887, 888, 889, 1536):
+        v1, p1 = tc.evaluate_bitboards(g["c0"][:n], g["c1"][:n])
+        v2, p2 = mma.evaluate_bitboards(g["c0"][:n], g["c1"][:n])
+        v1, p1, v2, p2 = v1.cpu().numpy(), p1.cpu().numpy(), v2.cpu().numpy(), p2.cpu().numpy()
+        m = min(n, nb)
+        assert np.abs(v1[:m] - g["big_value"][:m]).max() < TOL and np.abs(p1[:m] - g["big_prior"][:m]).max() < TOL
+        assert np.abs(v1 - v2).max() < 5e-3 and np.abs(p1 - p2).max() < 5e-3, (n, np.abs(v1 - v2).max())
+    perm = np.random.RandomState(1).permutation(1536)
+    v3, p3 = tc.evaluate_bitboards(g["c0"][perm], g["c1"][perm])
+    v1, p1 = tc.evaluate_bitboards(g["c0"], g["c1"])
+    assert torch.equal(v3, v1[torch.as_tensor(perm).cuda()]) and torch.equal(p3, p1[torch.as_tensor(perm).cuda()])

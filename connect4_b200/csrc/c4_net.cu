@@ -471,8 +471,10 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
 // slices) and a single accumulator slot keep up; strips are 6 boards (3 tiles) so that two activation buffers, one
 // 72 KB weight stage and the fp32 residual of the strip (3 x 64 TMEM columns) fit.
 template <int F_> struct TcC;
-template <> struct TcC<32> { static constexpr int F = 32, NB = 16, T = 7, ROWS = 912, WSTAGES = 3, ACC_SLOTS = 3, GROUPS = 2; };
-template <> struct TcC<64> { static constexpr int F = 64, NB = 6, T = 3, ROWS = 400, WSTAGES = 1, ACC_SLOTS = 1, GROUPS = 1; };
+// SLICED: the single weight stage is refilled one dy slice at a time -- the next layer's slice dy is requested as soon as
+// the last tile of this layer has issued its dy MMAs, so the reload runs under the rest of that tile and its epilogue.
+template <> struct TcC<32> { static constexpr int F = 32, NB = 16, T = 7, ROWS = 912, WSTAGES = 3, ACC_SLOTS = 3, GROUPS = 2; static constexpr bool SLICED = false; };
+template <> struct TcC<64> { static constexpr int F = 64, NB = 6, T = 3, ROWS = 400, WSTAGES = 1, ACC_SLOTS = 1, GROUPS = 1; static constexpr bool SLICED = true; };
 #define TC_CH 16                       // channels per epilogue thread (one slice)
 #define TC_THREADS 576                 // warp 0 weight producer, warp 1 MMA issuer, warps 2..17 epilogue
 #define TC_EPI_WARPS 16
@@ -484,6 +486,9 @@ template <int F_> struct TcK : TcC<F_> {
     static constexpr int GROUP_WARPS = 4 * SLICES;
     static constexpr int ACT_BYTES = KC * C::ROWS * 16;
     static constexpr int WSTAGE_BYTES = 3 * KC * NN * 16;
+    static constexpr int WSLICE_BYTES = KC * NN * 16;                      // one dy slice of a layer
+    static constexpr int WBARS = C::SLICED ? 3 : C::WSTAGES;               // weight barriers: per dy slice / per stage
+    static constexpr int STEM_KC = C::SLICED ? KC : 2;                     // k-chunk pitch of the stem's packed weights
     static constexpr int ACC_COL0 = C::T * C::F;                           // TMEM: residual stream first, then the slots
     static_assert(GROUP_WARPS * C::GROUPS == TC_EPI_WARPS, "16 epilogue warps");
     static_assert(ACC_COL0 + C::ACC_SLOTS * NN <= 512, "TMEM columns");
@@ -701,10 +706,10 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
     const float *bias = small, *hp = small + L * F;
     float *scratch = reinterpret_cast<float *>(smem + K::scratch(R));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + K::bars(R));
-    const uint32_t b_wfull = smem_u32(bars), b_wempty = b_wfull + 8 * K::WSTAGES;
-    const uint32_t b_accfull = b_wempty + 8 * K::WSTAGES, b_accempty = b_accfull + 8 * K::ACC_SLOTS;
+    const uint32_t b_wfull = smem_u32(bars), b_wempty = b_wfull + 8 * K::WBARS;
+    const uint32_t b_accfull = b_wempty + 8 * K::WBARS, b_accempty = b_accfull + 8 * K::ACC_SLOTS;
     const uint32_t b_epi = b_accempty + 8 * K::ACC_SLOTS;                   // T barriers
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * K::WSTAGES + 2 * K::ACC_SLOTS + K::T);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * K::WBARS + 2 * K::ACC_SLOTS + K::T);
 
     // ---- one-time setup: zero the strips (pad rows/columns stay zero for ever), small params, barriers, TMEM
     for (int i = threadIdx.x; i < 2 * K::ACT_BYTES / 16; i += blockDim.x)
@@ -716,7 +721,7 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
             reinterpret_cast<uint4 *>(small)[i] = reinterpret_cast<const uint4 *>(src)[i];
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < K::WSTAGES; i++) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, 1); }
+        for (int i = 0; i < K::WBARS; i++) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, 1); }
         for (int i = 0; i < K::ACC_SLOTS; i++) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, K::GROUP_WARPS); }
         for (int i = 0; i < K::T; i++) mbar_init(b_epi + 8 * i, K::GROUP_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -733,7 +738,16 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
 
     if (warp == 0) {
         // ================= weight producer: layer g of the (strip, layer) sequence -> ring stage g % WSTAGES
-        if (lane == 0) {
+        if (lane == 0 && K::SLICED) {
+            const int total = n_strips * L;
+            for (int g = 0; g < total; g++)
+                for (int dy = 0; dy < 3; dy++) {                              // slice dy of layer g -> its third of the stage
+                    if (g > 0) mbar_wait(b_wempty + 8 * dy, (g - 1) & 1);
+                    mbar_expect_tx(b_wfull + 8 * dy, K::WSLICE_BYTES);
+                    bulk_g2s(smem_u32(sW + dy * K::WSLICE_BYTES), image + (size_t)(g % L) * K::WSTAGE_BYTES + dy * K::WSLICE_BYTES,
+                             K::WSLICE_BYTES, b_wfull + 8 * dy);
+                }
+        } else if (lane == 0) {
             const int total = n_strips * L;
             for (int g = 0; g < total; g++) {
                 const int st = g % K::WSTAGES, use = g / K::WSTAGES;
@@ -754,7 +768,7 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                 const int T = (7 * nb + 15) / 16;
                 for (int l = 0; l < L; l++, g++) {
                     const int st = g % K::WSTAGES;
-                    mbar_wait(b_wfull + 8 * st, (g / K::WSTAGES) & 1);
+                    if (!K::SLICED) mbar_wait(b_wfull + 8 * st, (g / K::WSTAGES) & 1);
                     DBG_T(d0)
                     const uint32_t wbase = smem_u32(sW + st * K::WSTAGE_BYTES);
                     const uint32_t abase = smem_u32((l == 0 || (l & 1) == 0) ? sH : sX);   // stem and conv2 read H
@@ -776,23 +790,25 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                         // descriptors advance by adding 16-byte units to the start-address field:
                         //   A: +8 per dy (8 rows), +2*ROWS per 16-channel k-step;  B: +kc*NN per dy, +2*NN per k-step
                         const uint64_t a = a_l + (uint64_t)(128 * t);
-                        if (l != 0) {
 #pragma unroll
-                            for (int dy = 0; dy < 3; dy++)
+                        for (int dy = 0; dy < 3; dy++) {
+                            if (K::SLICED && t == 0) mbar_wait(b_wfull + 8 * dy, (uint32_t)g & 1u);
+                            if (l != 0) {
 #pragma unroll
                                 for (int ks = 0; ks < K::KC / 2; ks++) {
                                     const uint64_t aa = a + 8 * dy + 2 * K::ROWS * ks, bb = b_l + (dy * K::KC + 2 * ks) * K::NN;
                                     if (dy == 0 && ks == 0) umma_f16c<0>(d, aa, bb, idesc); else umma_f16c<1>(d, aa, bb, idesc);
                                 }
-                        } else {
-                            umma_f16c<0>(d, a, b_l, idesc);
-                            umma_f16c<1>(d, a + 8, b_l + 2 * K::NN, idesc);
-                            umma_f16c<1>(d, a + 16, b_l + 4 * K::NN, idesc);
+                            } else {                                          // stem: 16 (padded) input channels = one k-step
+                                const uint64_t aa = a + 8 * dy, bb = b_l + dy * K::STEM_KC * K::NN;
+                                if (dy == 0) umma_f16c<0>(d, aa, bb, idesc); else umma_f16c<1>(d, aa, bb, idesc);
+                            }
+                            if (K::SLICED && t == T - 1) umma_commit(b_wempty + 8 * dy);      // slice free for the next layer
                         }
                         umma_commit(b_accfull + 8 * slot);
                         DBG_T(d3)
                     }
-                    umma_commit(b_wempty + 8 * st);
+                    if (!K::SLICED) umma_commit(b_wempty + 8 * st);
                 }
             }
 #ifdef C4_TC_PROFILE
@@ -986,7 +1002,7 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
         std::vector<unsigned char> tc((size_t)L * stage + small_bytes, 0);
         const float *q = blob + 4;
         for (int l = 0; l < L; l++) {
-            const int cin = l == 0 ? 3 : F, kc = l == 0 ? 2 : KC;
+            const int cin = l == 0 ? 3 : F, kc = (l == 0 && F == 32) ? 2 : KC;    // = TcK<F>::STEM_KC for the stem
             uint16_t *dst = reinterpret_cast<uint16_t *>(tc.data() + (size_t)l * stage);
             for (int co = 0; co < F; co++)
                 for (int ci = 0; ci < cin; ci++)

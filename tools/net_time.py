@@ -6,8 +6,15 @@ sys.path.insert(0, ROOT)
 from connect4_b200.neural.model import ModelWrapper
 g = np.load(os.path.join(ROOT, "tests/golden/net_outputs.npz"))
 z = np.load(os.path.join(ROOT, "tests/golden/example_net_state.npz"))
-m = ModelWrapper(state_dict={k: z[k] for k in z.files})
-ref_v, ref_p = g["value"], g["prior"]
+if "--net64" in sys.argv:                       # the reference's example_config network, random init (torch.manual_seed(0))
+    from connect4_b200.neural.config import ModelConfig, NetConfig
+    torch.manual_seed(0)
+    m = ModelWrapper(ModelConfig(net_config=NetConfig(filters=64, n_fc_layers=6, n_residuals=6)))
+    ref_v, ref_p = g["big_value"], g["big_prior"]
+    g = {"c0": g["c0"][:len(ref_v)], "c1": g["c1"][:len(ref_v)]}
+else:
+    m = ModelWrapper(state_dict={k: z[k] for k in z.files})
+    ref_v, ref_p = g["value"], g["prior"]
 v, p = m.evaluate_bitboards(g["c0"], g["c1"])
 print("max |dv| %.2e  max |dp| %.2e over %d golden positions" % (np.abs(v.cpu().numpy() - ref_v).max(), np.abs(p.cpu().numpy() - ref_p).max(), len(ref_v)))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -776,7 +776,9 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                     const uint64_t b_l = umma_desc(wbase, K::NN * 16, 128);
                     // epilogue arrivals seen so far on each tile barrier: (L + 1) per finished strip, l + 1 needed now
                     const uint32_t ep_par = (uint32_t)(s * (L + 1) + l) & 1u;
-                    for (int t = 0; t < T; t++, c++) {
+#pragma unroll
+                    for (int t = 0; t < K::T; t++, c++) {                      // fully unrolled: per-tile constants fold away
+                        if (t >= T) break;
                         // rows of tiles t-1, t, t+1 of the previous layer are read; the two epilogue groups finish
                         // tiles out of order, so every tile is waited for once (tile t+1 here, tile 0 at t == 0)
                         if (t == 0) mbar_wait(b_epi, ep_par);
@@ -790,20 +792,27 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
                         // descriptors advance by adding 16-byte units to the start-address field:
                         //   A: +8 per dy (8 rows), +2*ROWS per 16-channel k-step;  B: +kc*NN per dy, +2*NN per k-step
                         const uint64_t a = a_l + (uint64_t)(128 * t);
+                        // (the layer-kind branch stays OUTSIDE the unrolled tap loops: this thread is the serial resource of
+                        //  the kernel and every extra instruction per tile shows up in the step time)
+                        if (l != 0) {
 #pragma unroll
-                        for (int dy = 0; dy < 3; dy++) {
-                            if (K::SLICED && t == 0) mbar_wait(b_wfull + 8 * dy, (uint32_t)g & 1u);
-                            if (l != 0) {
+                            for (int dy = 0; dy < 3; dy++) {
+                                if (K::SLICED && t == 0) mbar_wait(b_wfull + 8 * dy, (uint32_t)g & 1u);
 #pragma unroll
                                 for (int ks = 0; ks < K::KC / 2; ks++) {
                                     const uint64_t aa = a + 8 * dy + 2 * K::ROWS * ks, bb = b_l + (dy * K::KC + 2 * ks) * K::NN;
                                     if (dy == 0 && ks == 0) umma_f16c<0>(d, aa, bb, idesc); else umma_f16c<1>(d, aa, bb, idesc);
                                 }
-                            } else {                                          // stem: 16 (padded) input channels = one k-step
+                                if (K::SLICED && t == T - 1) umma_commit(b_wempty + 8 * dy);  // slice free for the next layer
+                            }
+                        } else {                                              // stem: 16 (padded) input channels = one k-step
+#pragma unroll
+                            for (int dy = 0; dy < 3; dy++) {
+                                if (K::SLICED && t == 0) mbar_wait(b_wfull + 8 * dy, (uint32_t)g & 1u);
                                 const uint64_t aa = a + 8 * dy, bb = b_l + dy * K::STEM_KC * K::NN;
                                 if (dy == 0) umma_f16c<0>(d, aa, bb, idesc); else umma_f16c<1>(d, aa, bb, idesc);
+                                if (K::SLICED && t == T - 1) umma_commit(b_wempty + 8 * dy);
                             }
-                            if (K::SLICED && t == T - 1) umma_commit(b_wempty + 8 * dy);      // slice free for the next layer
                         }
                         umma_commit(b_accfull + 8 * slot);
                         DBG_T(d3)

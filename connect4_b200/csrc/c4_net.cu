@@ -1035,11 +1035,20 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
         }
     }
     if (F == 32) {
-        C4_REQUIRE((smem_resident<32, WARPS_A>(R)) <= 227 * 1024, "c4_net_create: F=32 network too deep for the resident kernel");
-        C4_CUDA(cudaFuncSetAttribute(k_net_resident<OpFP16, 32, WARPS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_resident<32, WARPS_A>(R)));
-        C4_CUDA(cudaFuncSetAttribute(k_net_resident<OpBF16, 32, WARPS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_resident<32, WARPS_A>(R)));
+        // the mma.sync kernel for 32 filters keeps every layer's weights resident in shared memory (up to 4 residual blocks);
+        // deeper 32-filter networks run on the tcgen05 kernel only, which streams the weights layer by layer
+        const bool resident_ok = smem_resident<32, WARPS_A>(R) <= 227 * 1024;
+        if (!net->use_tc && !resident_ok) {
+            c4_net_destroy(net);
+            c4_set_error("invalid argument: c4_net_create: this 32-filter network is too deep for the mma.sync kernel (use kernel auto)");
+            return -1;
+        }
+        if (resident_ok) {
+            C4_CUDA(cudaFuncSetAttribute(k_net_resident<OpFP16, 32, WARPS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_resident<32, WARPS_A>(R)));
+            C4_CUDA(cudaFuncSetAttribute(k_net_resident<OpBF16, 32, WARPS_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_resident<32, WARPS_A>(R)));
+        }
     } else {
         C4_CUDA(cudaFuncSetAttribute(k_net_streamed<OpFP16, 64, WARPS_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_streamed<64, WARPS_B>(R)));

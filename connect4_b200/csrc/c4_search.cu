@@ -1128,14 +1128,19 @@ extern "C" int c4_ctx_set_net(c4_ctx *ctx, c4_net *net)
     C4_CUDA(cudaSetDevice(ctx->device));
     if (ctx->memo_log2 > 0) {
         // the memo caches THIS network's outputs: (re)start empty whenever the evaluator changes
-        const size_t bytes = ((size_t)1 << ctx->memo_log2) * 64;
         if (!ctx->d.memo) {
+            // the memo is a cache: when the device cannot spare the preferred size it is halved down to 2^18 entries
             uint32_t *m = nullptr;
-            if (cudaMalloc((void **)&m, bytes) != cudaSuccess) { c4_set_error("cudaMalloc of the evaluation memo failed"); return -2; }
+            while (cudaMalloc((void **)&m, ((size_t)1 << ctx->memo_log2) * 64) != cudaSuccess) {
+                cudaGetLastError();
+                m = nullptr;
+                if (--ctx->memo_log2 < 18) { c4_set_error("cudaMalloc of the evaluation memo failed"); ctx->memo_log2 = 0; return -2; }
+            }
             ctx->allocs.push_back(m);
             ctx->d.memo = m;
             ctx->d.memo_mask = (uint32_t)(((size_t)1 << ctx->memo_log2) - 1);
         }
+        const size_t bytes = ((size_t)1 << ctx->memo_log2) * 64;
         if (c4_net_uid(net) != ctx->memo_net_uid) C4_CUDA(cudaMemset(ctx->d.memo, 0, bytes));
         ctx->memo_net_uid = c4_net_uid(net);
     }

@@ -187,3 +187,47 @@ def test_tcgen05_kernel_for_64_filter_networks():
     v3, p3 = tc.evaluate_bitboards(g["c0"][perm], g["c1"][perm])
     v1, p1 = tc.evaluate_bitboards(g["c0"], g["c1"])
     assert torch.equal(v3, v1[torch.as_tensor(perm).cuda()]) and torch.equal(p3, p1[torch.as_tensor(perm).cuda()])
+
+
+@pytest.mark.parametrize("filters,residuals,fc", [(32, 1, 1), (32, 5, 2), (64, 2, 1), (64, 6, 6)])
+def test_network_geometries_with_lively_weights(filters, residuals, fc):
+    """other depths / widths than the two stock configurations, with weights and batch-norm statistics perturbed so that
+    the activations are far from the near-constant outputs of a fresh initialisation: both kernels against the fp32 torch
+    restatement of the same state dict"""
+    import torch
+    from oracle import net_ref as nr
+    from connect4_b200.neural.config import ModelConfig, NetConfig
+    from connect4_b200.neural.model import ModelWrapper, _init_state_dict
+    g = golden("net_outputs.npz")
+    torch.manual_seed(filters + residuals)
+    sd = _init_state_dict(NetConfig(filters=filters, n_fc_layers=fc, n_residuals=residuals))
+    gen = torch.Generator().manual_seed(7)
+    for k, v in sd.items():
+        if k.endswith("running_var"):
+            v.copy_(0.5 + torch.rand(v.shape, generator=gen))
+        elif k.endswith("running_mean"):
+            v.copy_(0.2 * torch.randn(v.shape, generator=gen))
+        elif "batch_norm" in k and k.endswith("weight") or (k.startswith("body.0.1") and k.endswith("weight")):
+            v.copy_(0.6 + 0.8 * torch.rand(v.shape, generator=gen))
+        elif "batch_norm" in k and k.endswith("bias") or (k.startswith("body.0.1") and k.endswith("bias")):
+            v.copy_(0.2 * torch.randn(v.shape, generator=gen))
+        elif "conv" in k and k.endswith("weight") or k == "body.0.0.weight":
+            v.mul_(2.0)
+        elif ".fc" in k and k.endswith("weight"):
+            v.mul_(2.5)
+    sdn = {k: v.numpy() for k, v in sd.items()}
+    n = 600
+    rv, rp = nr.evaluate(sdn, g["c0"][:n], g["c1"][:n])
+    assert rv.std() > 0.003 and rp.std() > 0.01                      # the positions really are told apart
+    from connect4_b200._lib import C4Error
+    for kernel in ("auto", "mma"):
+        cfg = ModelConfig(net_config=NetConfig(filters=filters, n_fc_layers=fc, n_residuals=residuals))
+        if kernel == "mma" and filters == 32 and residuals > 4:      # its weights must all be resident in shared memory
+            with pytest.raises(C4Error):
+                ModelWrapper(cfg, state_dict=sd, kernel=kernel)
+            continue
+        m = ModelWrapper(cfg, state_dict=sd, kernel=kernel)
+        v, p = m.evaluate_bitboards(g["c0"][:n], g["c1"][:n])
+        dv, dp = np.abs(v.cpu().numpy() - rv).max(), np.abs(p.cpu().numpy() - rp).max()
+        print("%df/%dr/%dfc %s: max|dvalue| %.2e max|dprior| %.2e" % (filters, residuals, fc, kernel, dv, dp))
+        assert dv < TOL and dp < TOL

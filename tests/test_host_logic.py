@@ -179,3 +179,31 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle", "").replace("by the oracle", ""), os.path.join(dirpath, f)
+
+
+def test_match_chooses_the_lock_step_path_only_for_deterministic_device_players():
+    """Match.play_batched is taken for MCTS players with device evaluators and no host randomness; everything else keeps
+    the reference's one-game-at-a-time path (match.py:42-50)"""
+    from functools import partial
+    from connect4_b200 import evaluators as evl
+    from connect4_b200.match import Match, _batchable
+    from connect4_b200.mcts import MCTS, MCTSConfig, device_kind
+    from connect4_b200.player import HumanPlayer
+
+    class FakeModel():                       # anything owning a c4_net handle is a network evaluator
+        c4_net = object()
+
+    centre = MCTS("c", MCTSConfig(50), evl.Evaluator(evl.evaluate_centre_with_prior))
+    net = MCTS("n", MCTSConfig(50), evl.Evaluator(partial(evl.evaluate_nn, model=FakeModel())))
+    bare = MCTS("b", MCTSConfig(50), FakeModel())
+    host = MCTS("h", MCTSConfig(50), evl.Evaluator(lambda board: (0.5, np.ones(7) / 7)))
+    noisy = MCTS("z", MCTSConfig(50, 19652, 1.25, 0.3, 0.25, 0), evl.Evaluator(evl.evaluate_centre_with_prior))
+    sampled = MCTS("s", MCTSConfig(50, num_sampling_moves=6), evl.Evaluator(evl.evaluate_centre_with_prior))
+    assert [device_kind(p.evaluator)[0] for p in (centre, net, bare, host)] == ["centre", "net", "net", "external"]
+    assert [_batchable(p) for p in (centre, net, bare, host, noisy, sampled, HumanPlayer("me"))] == \
+        [True, True, True, False, False, False, False]
+    m = Match(False, centre, net, plies=1, switch=True)          # 7 one-ply openings, each played twice
+    assert m.n == 7 and len(m.games) == 14
+    assert all(g._player_o.evaluator is centre.evaluator for g in m.games[:7])
+    assert all(g._player_o.evaluator is net.evaluator for g in m.games[7:])
+    assert all(g.player_to_move() is g._player_x for g in m.games)      # after one ply x is to move

@@ -1071,6 +1071,7 @@ extern "C" int c4_net_destroy(c4_net *net)
 
 extern "C" double c4_net_flops_per_position(const c4_net *net) { return net ? net->flops : 0.0; }
 unsigned long long c4_net_uid(const c4_net *net) { return net ? net->uid : 0ULL; }   // internal (not part of the C ABI)
+int c4_net_filters(const c4_net *net) { return net ? net->F : 0; }                  // internal
 
 extern "C" int c4_net_forward(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count,
                               float *out, void *stream)

@@ -30,6 +30,7 @@
 #include "c4_common.cuh"
 
 unsigned long long c4_net_uid(const c4_net *net);     // c4_net.cu (internal)
+int c4_net_filters(const c4_net *net);
 
 enum { ST_IDLE = 0, ST_READY = 1, ST_WAIT = 2, ST_DONE = 3, ST_NEWROOT = 4 };
 #define PATH_CAP 48
@@ -1145,6 +1146,11 @@ extern "C" int c4_ctx_set_net(c4_ctx *ctx, c4_net *net)
         ctx->memo_net_uid = c4_net_uid(net);
     }
     ctx->net = net;
+    // Self-play with a 64-filter network is network-bound (124 us network vs 41 us tree per pass): there the two half
+    // pools on two streams pay -- the tree pass of one half runs under the network launch of the other (+7-9 %,
+    // tools/ramp64.py) -- while with the 32-filter network the game chains are the limit and one pool is faster.
+    if (!getenv("C4_POOLS")) ctx->n_pools = (c4_net_filters(net) == 64 && ctx->max_games >= 512) ? 2 : 1;
+    if (!getenv("C4_NET_CTAS")) ctx->net_ctas = (ctx->n_pools == 2 && c4_net_filters(net) == 64) ? 96 : 112;
     return 0;
 }
 

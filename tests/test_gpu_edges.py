@@ -58,8 +58,9 @@ def test_pass_length_policy_changes_work_not_results(monkeypatch):
     model = _model()
     recs = []
     for env in ({"C4_STOP_FRAC": "0"}, {"C4_STOP_FRAC": "0.5"}, {"C4_STOP_FRAC": "0.1", "C4_CYCLE_LIMIT": "20000"},
-                {"C4_STOP_FRAC": "0.9", "C4_BUDGET": "3", "C4_CYCLE_LIMIT": "0"}):
-        for k in ("C4_STOP_FRAC", "C4_CYCLE_LIMIT", "C4_BUDGET"):
+                {"C4_STOP_FRAC": "0.9", "C4_BUDGET": "3", "C4_CYCLE_LIMIT": "0"},
+                {"C4_POOLS": "2", "C4_NET_CTAS": "96"}, {"C4_POOLS": "2", "C4_STOP_FRAC": "0.3", "C4_NET_CTAS": "148"}):
+        for k in ("C4_STOP_FRAC", "C4_CYCLE_LIMIT", "C4_BUDGET", "C4_POOLS", "C4_NET_CTAS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

@@ -30,4 +30,4 @@ while tot_ms < 6000:
     line = "t %.2f s pos/s %8.0f cum %8.0f hit %.3f evals/pass %5.0f tree %.1f us net %.1f us" % (
         tot_ms / 1e3, r["positions"] / r["device_ms"] * 1e3, tot_pos / tot_ms * 1e3,
         r["memo_hits"] / max(1, r["memo_hits"] + r["evals"]), r["evals"] / 500, r["tree_ms"] * 1e3, r["net_ms"] * 1e3)
-print("64f self-play:", line)
+print("64f self-play (half pools: %d):" % r["pools"], line)

@@ -1,3 +1,5 @@
+"""per-role cycle accounting of the tcgen05 network kernel: build with tools/build_variant.sh NAME -DC4_TC_PROFILE, run with
+C4_LIB=.../libc4b200_NAME.so C4_TC_DEBUG=1 python tools/tc_dbg.py [--net64]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -5,8 +7,12 @@ sys.path.insert(0, ROOT)
 from oracle import net_ref as nr
 from connect4_b200.neural.model import ModelWrapper
 g = np.load(os.path.join(ROOT, "tests/golden/net_outputs.npz"))
-sd = nr.load_golden_state(os.path.join(ROOT, "tests/golden/example_net_state.npz"))
-tc = ModelWrapper(state_dict=sd)
+if "--net64" in sys.argv:
+    from connect4_b200.neural.config import ModelConfig, NetConfig
+    torch.manual_seed(0)
+    tc = ModelWrapper(ModelConfig(net_config=NetConfig(filters=64, n_fc_layers=6, n_residuals=6)))
+else:
+    tc = ModelWrapper(state_dict=nr.load_golden_state(os.path.join(ROOT, "tests/golden/example_net_state.npz")))
 c0 = np.tile(g["c0"], 3)[:4096]; c1 = np.tile(g["c1"], 3)[:4096]
 for i in range(3):
     tc.evaluate_bitboards(c0, c1)

@@ -265,7 +265,7 @@ def main():
         net_share = (net_ms * pools * n_pass / args.steps) / step_ms if secs else None
         roof_tree = {"kernel": "k_advance<NET,selfplay> (warp-per-game tree pass)", "bound": "hbm", "achieved": tree_gbs,
                      "peak": peak_hbm, "unit": "GB/s", "frac": (tree_gbs / peak_hbm) if tree_gbs else None,
-                     "traffic": 53.9e6,
+                     "traffic": 55.7e6,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, ncu --set "
                                        "full capture of the profiling command (profiles/r01_advance_v3_full_raw.csv; "
                                        "shorter passes than the default run, see profiles/README.md)",

@@ -96,3 +96,13 @@ for name, fn, nbytes in (("c4_board_legal_mask", lambda: big.legal_mask(), 17), 
     ms = dev_time(fn)
     print(json.dumps({"row": "%s over %d resident positions" % (name, N), "ms": ms, "GB_per_s": N * nbytes / ms / 1e6,
                       "bytes_per_position": nbytes}))
+
+# ---- BASELINE configs[1]: the 10,000-position x 800-simulation deterministic sweep, one fused launch
+from connect4_b200.engine import Engine
+m = np.load("tests/golden/mcts_sweep_800.npz")
+eng = Engine(len(m["c0"]), MCTSConfig(800))
+def sweep():
+    eng.begin(m["c0"], m["c1"]); eng.run("centre")
+t = timed(sweep, reps=2)
+print(json.dumps({"row": "10,000 searches x 800 simulations, centre evaluator, one launch (BASELINE configs[1])", "seconds": t,
+                  "simulations_per_sec": 1e4 * 800 / t, "reference_cpu": "0.35-0.6 s per search and core (SURVEY 8d)"}))

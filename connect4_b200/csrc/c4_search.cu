@@ -7,7 +7,9 @@
 // B200 design (NOT the reference's structure):
 //  * one warp owns one game for the whole kernel; lanes 0..6 are the seven columns.  One descent level = lanes 0..6
 //    each reading their 32-byte child record (two 128-bit loads, two fully used 128-byte lines per level), fp64 PUCT
-//    per lane, warp-shuffle argmax on (score, column).
+//    per lane from select-ready fields (the side-relative mean is maintained by backup, the division by n+1 is a table
+//    reciprocal + two FMAs verified against IEEE division on the host), argmax on (score, column) by two REDUX.MAX
+//    over an order-preserving 64-bit key and one vote.
 //  * children are allocated EAGERLY when a node is evaluated (one 8-slot block), which is observably identical to the
 //    reference's lazy expand-on-second-visit (a node's children cannot be reached before its second visit) but lets
 //    the evaluation result (prior) be scattered straight into the child records.
@@ -15,7 +17,9 @@
 //    terminal result of each child is stored (2 bits), computed by the drop + 4-in-a-row test at block creation.
 //  * a game advances until it needs an evaluator answer; pending leaves of all games are compacted into one batch
 //    (atomic slot counter), evaluated by the network kernel (c4_net.cu) or the host, and consumed by the next pass.
-//    Terminal revisits need no evaluator and are played through inside the same pass (bounded by `budget`).
+//    Terminal revisits and hits of the evaluation memo (the reference's Evaluator.position_table, here a checksummed
+//    hash table in HBM) need no evaluator and are played through inside the same pass (bounded by `budget`, a cycle
+//    limit, and the share of games already waiting for the network).
 //  * all PUCT arithmetic uses explicit round-to-nearest intrinsics (__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn) so no
 //    FMA contraction can change the reference's two-rounding  pb_c*prior + value ; log() comes from a host-built
 //    table (glibc, the same libm Python's math.log calls).

@@ -4,11 +4,11 @@ import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import net_ref as nr
 from connect4_b200.neural.model import ModelWrapper
 
 g = np.load(os.path.join(ROOT, "tests/golden/net_outputs.npz"))
-sd = nr.load_golden_state(os.path.join(ROOT, "tests/golden/example_net_state.npz"))
+_z = np.load(os.path.join(ROOT, "tests/golden/example_net_state.npz"))
+sd = {k: _z[k] for k in _z.files}
 tc = ModelWrapper(state_dict=sd, kernel="auto")
 mma = ModelWrapper(state_dict=sd, kernel="mma")
 for n in (1, 2, 16, 17, 100, 148, 1536):

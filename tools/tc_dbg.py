@@ -4,7 +4,6 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import net_ref as nr
 from connect4_b200.neural.model import ModelWrapper
 g = np.load(os.path.join(ROOT, "tests/golden/net_outputs.npz"))
 if "--net64" in sys.argv:
@@ -12,7 +11,8 @@ if "--net64" in sys.argv:
     torch.manual_seed(0)
     tc = ModelWrapper(ModelConfig(net_config=NetConfig(filters=64, n_fc_layers=6, n_residuals=6)))
 else:
-    tc = ModelWrapper(state_dict=nr.load_golden_state(os.path.join(ROOT, "tests/golden/example_net_state.npz")))
+    _z = np.load(os.path.join(ROOT, "tests/golden/example_net_state.npz"))
+    tc = ModelWrapper(state_dict={k: _z[k] for k in _z.files})
 c0 = np.tile(g["c0"], 3)[:4096]; c1 = np.tile(g["c1"], 3)[:4096]
 for i in range(3):
     tc.evaluate_bitboards(c0, c1)

@@ -52,6 +52,8 @@ class Match():
                 eng = search_batch(role.config, [games[i]._board for i in idx], role.evaluator)
                 best = eng.readout(len(idx))["best"]
                 for i, mv in zip(idx, best.tolist()):
+                    if mv < 0:      # the root was never expanded (simulations == 0); Tree.best_move fails there too
+                        raise ValueError("search returned no move for a running game (simulations must be >= 1)")
                     games[i]._board.make_move(int(mv))
                     games[i].move_history = np.append(games[i].move_history, np.uint8(mv))
             live = [i for i in live if games[i]._board.result is None]

@@ -63,6 +63,9 @@ SIGNATURES = {
     "c4_selfplay_bench": (C.c_int, [vp, C.c_int, C.c_int64] + [C.POINTER(C.c_int64)] * 4 +
                           [C.POINTER(C.c_float)] * 3 + [vp]),
     "c4_selfplay_reset": (C.c_int, [vp, vp]),
+    "c4_selfplay_stream": (C.c_int, [vp, C.c_int, C.c_int, C.c_int64, C.c_double] + [C.POINTER(C.c_int64)] * 4 +
+                           [C.POINTER(C.c_float), C.POINTER(C.c_int32), vp]),
+    "c4_ctx_clear_memo": (C.c_int, [vp, vp]),
     "c4_records_augment_pack": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp]),
 }
 

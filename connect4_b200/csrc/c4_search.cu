@@ -35,6 +35,11 @@
 
 #include "c4_tree.cuh"
 
+// c4_fused.cu: the persistent engine (one launch per generation); c4_search.cu keeps the lock-step pass engine
+bool c4_fused_eligible(const c4_net *net, int max_games, int simulations);
+int c4_fused_run(const C4Dev &d, const c4_net *net, int max_games, int simulations, bool selfplay,
+                 unsigned long long stop_games, double stop_ms, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------------ the pass kernel
 // MODE: C4_EVAL_EXTERNAL / C4_EVAL_CENTRE / C4_EVAL_NET.  One warp per game slot.
 template <int MODE, bool SELFPLAY>
@@ -71,8 +76,13 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
         const int ply = SELFPLAY ? d.ply[g] : 0;
         if (MODE == C4_EVAL_NET) {
             const float *o = d.net_out + (size_t)slot * 8;
-            const float ov = (lane < 8) ? o[lane] : 0.f;
-            if (d.memo) memo_insert(d, lc0, lc1, ov, lane);
+            float ov = (lane < 8) ? o[lane] : 0.f;
+            if (__any_sync(FULL, !isfinite(ov))) {
+                // operand overflow (fp16) or NaN weights: neutral answer + a flag that makes the host call fail
+                // (the reference asserts on every evaluation, oinkoink/neural/pytorch/model.py:258-263,275-280)
+                ov = (lane < 7) ? (1.f / 7.f) : 0.5f;
+                if (lane == 0) d.ctr->net_nonfinite = 1;
+            } else if (d.memo) memo_insert(d, lc0, lc1, ov, lane);
             float pf = (lane < 7) ? ov : 0.f;
             double value = (double)__shfl_sync(FULL, ov, 7);
             apply_eval<true>(d, G, node, lc0, lc1, lage, value, 0.0, pf, is_root, ply);
@@ -200,7 +210,7 @@ __global__ void k_search_begin(C4Dev d, const u64 *c0, const u64 *c1, int n, int
     if (g == 0) {
         d.ctr->leaf_count[0][0] = 0; d.ctr->leaf_count[0][1] = 0; d.ctr->leaf_count[1][0] = 0; d.ctr->leaf_count[1][1] = 0;
         d.ctr->stop_flag[0][0] = 0; d.ctr->stop_flag[0][1] = 0; d.ctr->stop_flag[1][0] = 0; d.ctr->stop_flag[1][1] = 0;
-        d.ctr->n_done = 0;
+        d.ctr->n_done = 0; d.ctr->engine_error = 0; d.ctr->net_nonfinite = 0;
     }
     if (g >= max_games) return;
     if (g < n) {
@@ -220,6 +230,7 @@ __global__ void k_selfplay_init(C4Dev d, int max_games)
         d.ctr->leaf_count[0][0] = 0; d.ctr->leaf_count[0][1] = 0; d.ctr->leaf_count[1][0] = 0; d.ctr->leaf_count[1][1] = 0;
         d.ctr->stop_flag[0][0] = 0; d.ctr->stop_flag[0][1] = 0; d.ctr->stop_flag[1][0] = 0; d.ctr->stop_flag[1][1] = 0;
         d.ctr->games_finished = 0; d.ctr->n_records = 0; d.ctr->overflow = 0; d.ctr->n_done = 0;
+        d.ctr->engine_error = 0; d.ctr->net_nonfinite = 0;
         long long first = d.n_games_target < (long long)max_games ? d.n_games_target : (long long)max_games;
         d.ctr->next_game = (unsigned long long)first;
     }
@@ -395,6 +406,7 @@ struct c4_ctx {
     int last_pending;
     bool supplied;
     bool pool_fresh;                    // bench pool initialised
+    int pool_engine;                    // engine that owns the re-seeding pool's state: 0 none, 1 lock-step, 2 fused
     cudaEvent_t ev0, ev1;
     cudaEvent_t evs[2 * 64];            // sampled (start, stop) pairs around network launches
     cudaEvent_t eva[2 * 64];            // sampled (start, stop) pairs around tree-pass launches
@@ -487,6 +499,7 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     ctx->last_pending = 0;
     ctx->supplied = true;
     ctx->pool_fresh = false;
+    ctx->pool_engine = 0;
     memset(&ctx->d, 0, sizeof(ctx->d));
     C4Dev &d = ctx->d;
     // a warp starts no further descent in a NET pass after this many SM cycles (bounds the tail of the pass; 0 = off)
@@ -733,6 +746,23 @@ static int read_counters(c4_ctx *ctx, C4Counters *host, cudaStream_t s)
     return 0;
 }
 
+// the two device-side failure words: a network answer that was not finite, and the fused engine's watchdog
+static int check_device_errors(const C4Counters &c)
+{
+    if (c.net_nonfinite) {
+        c4_set_error("the network produced a non-finite value or prior (fp16 operand overflow or NaN weights; try "
+                     "operand_dtype='bf16'): oinkoink/neural/pytorch/model.py:258-263 asserts here");
+        return -3;
+    }
+    if (c.engine_error) { c4_set_error("fused engine watchdog: games waited for the network for seconds (internal error)"); return -4; }
+    return 0;
+}
+
+static bool use_fused(const c4_ctx *ctx, int eval_kind)
+{
+    return eval_kind == C4_EVAL_NET && c4_fused_eligible(ctx->net, ctx->max_games, ctx->cfg.simulations);
+}
+
 extern "C" int c4_search_run(c4_ctx *ctx, int eval_kind, void *stream)
 {
     C4_REQUIRE(ctx, "c4_search_run: null context");
@@ -747,14 +777,23 @@ extern "C" int c4_search_run(c4_ctx *ctx, int eval_kind, void *stream)
         C4_CUDA(cudaStreamSynchronize(s));
         return 0;
     }
+    C4Counters c;
+    if (use_fused(ctx, eval_kind)) {
+        // every search of the batch in ONE persistent launch (c4_fused.cu)
+        if ((rc = c4_fused_run(ctx->d, ctx->net, ctx->max_games, ctx->cfg.simulations, false, 0ULL, 0.0, s))) return rc;
+        if ((rc = read_counters(ctx, &c, s))) return rc;
+        if ((rc = check_device_errors(c))) return rc;
+        C4_REQUIRE((long long)c.n_done >= ctx->n_search, "c4_search_run: the fused engine left searches unfinished");
+        return 0;
+    }
     const int chunk = 32;
     for (long long it = 0;; it++) {
         for (int k = 0; k < chunk; k++) {
             if ((rc = launch_advance<false>(ctx, C4_EVAL_NET, ctx->max_games, ctx->budget_net, s))) return rc;
             if ((rc = run_net(ctx, s))) return rc;
         }
-        C4Counters c;
         if ((rc = read_counters(ctx, &c, s))) return rc;
+        if ((rc = check_device_errors(c))) return rc;
         if ((long long)c.n_done >= ctx->n_search) break;
         C4_REQUIRE(it < (1 << 20), "c4_search_run: did not terminate");
     }
@@ -871,13 +910,24 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
     ctx->pool_parity[0] = ctx->pool_parity[1] = 0;
     int rc;
     C4Counters c;
-    ctx->live_games = std::min<long long>(n_games, ctx->max_games);
-    for (long long it = 0;; it++) {
-        if ((rc = selfplay_passes(ctx, eval_kind, 64, s))) return rc;
+    ctx->pool_engine = 0;
+    if (use_fused(ctx, eval_kind)) {
+        // the whole generation in ONE persistent launch: slots go idle when no game is left to seed, CTAs leave when
+        // all their slots are idle (c4_fused.cu)
+        if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, 0ULL, 0.0, s))) return rc;
         if ((rc = read_counters(ctx, &c, s))) return rc;
-        ctx->live_games = std::max<long long>(1, std::min<long long>(n_games - (long long)c.games_finished, ctx->max_games));
-        if ((long long)c.games_finished >= n_games) break;
-        C4_REQUIRE(it < (1LL << 24), "c4_selfplay_run: did not terminate");
+        if ((rc = check_device_errors(c))) return rc;
+        C4_REQUIRE((long long)c.games_finished >= n_games, "c4_selfplay_run: the fused engine left games unfinished");
+    } else {
+        ctx->live_games = std::min<long long>(n_games, ctx->max_games);
+        for (long long it = 0;; it++) {
+            if ((rc = selfplay_passes(ctx, eval_kind, 64, s))) return rc;
+            if ((rc = read_counters(ctx, &c, s))) return rc;
+            if ((rc = check_device_errors(c))) return rc;
+            ctx->live_games = std::max<long long>(1, std::min<long long>(n_games - (long long)c.games_finished, ctx->max_games));
+            if ((long long)c.games_finished >= n_games) break;
+            C4_REQUIRE(it < (1LL << 24), "c4_selfplay_run: did not terminate");
+        }
     }
     C4_REQUIRE(c.overflow == 0, "c4_selfplay_run: records_out too small");
     *n_records_out = (int64_t)c.n_records;
@@ -902,6 +952,8 @@ extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations,
     C4_CUDA(cudaSetDevice(ctx->device));
     C4Dev &d = ctx->d;
     int rc;
+    if (ctx->pool_engine != 1) ctx->pool_fresh = false;      // the pool state of another engine cannot be continued
+    ctx->pool_engine = 1;
     if (!ctx->pool_fresh) {
         d.n_games_target = (long long)1 << 60;
         ctx->live_games = ctx->max_games;
@@ -947,6 +999,81 @@ extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations,
     }
     if (net_ms) *net_ms = n_sampled ? nsum / n_sampled : 0.f;
     if (tree_ms) *tree_ms = n_sampled ? tsum / n_sampled : 0.f;
+    return 0;
+}
+
+extern "C" int c4_ctx_clear_memo(c4_ctx *ctx, void *stream)
+{
+    C4_REQUIRE(ctx, "c4_ctx_clear_memo: null context");
+    C4_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->d.memo) C4_CUDA(cudaMemsetAsync(ctx->d.memo, 0, ((size_t)1 << ctx->memo_log2) * 64, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t stop_games, double max_ms,
+                                  int64_t *positions, int64_t *evals, int64_t *memo_hits, int64_t *games,
+                                  float *device_ms, int32_t *engine, void *stream)
+{
+    C4_REQUIRE(ctx, "c4_selfplay_stream: null context");
+    C4_REQUIRE(eval_kind == C4_EVAL_CENTRE || eval_kind == C4_EVAL_NET, "c4_selfplay_stream: eval_kind must be CENTRE or NET");
+    C4_REQUIRE(eval_kind != C4_EVAL_NET || ctx->net, "c4_selfplay_stream: no network attached (c4_ctx_set_net)");
+    C4_REQUIRE(stop_games > 0 || max_ms > 0.0, "c4_selfplay_stream: needs a game count or a time limit");
+    cudaStream_t s = (cudaStream_t)stream;
+    C4_CUDA(cudaSetDevice(ctx->device));
+    C4Dev &d = ctx->d;
+    const bool fused = use_fused(ctx, eval_kind);
+    const int eng = fused ? 2 : 1;
+    int rc;
+    if (reset || !ctx->pool_fresh || ctx->pool_engine != eng) {
+        d.n_games_target = (long long)1 << 60;
+        ctx->live_games = ctx->max_games;
+        d.game_id_base = 0; d.game_id_stride = 1;
+        d.start_c0 = nullptr; d.start_c1 = nullptr;
+        d.records_out = nullptr; d.max_records = 0;
+        k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
+        C4_CUDA(cudaGetLastError());
+        ctx->parity = 0;
+        ctx->pool_parity[0] = ctx->pool_parity[1] = 0;
+        ctx->pool_fresh = true;
+        ctx->pool_engine = eng;
+    }
+    unsigned long long before[4], after[4];
+    C4Counters c;
+    k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, d.stat_hits, ctx->max_games, ctx->stats_dev);
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 40, ctx->stats_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if ((rc = read_counters(ctx, &c, s))) return rc;
+    before[0] = ctx->pinned[40]; before[1] = ctx->pinned[41]; before[2] = c.games_finished; before[3] = ctx->pinned[42];
+    const unsigned long long games_goal = stop_games > 0 ? before[2] + (unsigned long long)stop_games : 0ULL;
+    C4_CUDA(cudaEventRecord(ctx->ev0, s));
+    if (fused) {
+        if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, games_goal, max_ms, s))) return rc;
+    } else {
+        // lock-step engine: chunks of passes with a host look at the counters in between
+        for (long long it = 0;; it++) {
+            if ((rc = selfplay_passes(ctx, eval_kind, 64, s))) return rc;
+            C4_CUDA(cudaEventRecord(ctx->ev1, s));
+            if ((rc = read_counters(ctx, &c, s))) return rc;
+            float ms = 0.f;
+            C4_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            if (games_goal && c.games_finished >= games_goal) break;
+            if (max_ms > 0.0 && ms >= max_ms) break;
+            C4_REQUIRE(it < (1LL << 24), "c4_selfplay_stream: did not terminate");
+        }
+    }
+    C4_CUDA(cudaEventRecord(ctx->ev1, s));
+    k_sum_stats<<<1, 256, 0, s>>>(d.stat_evals, d.stat_positions, d.stat_hits, ctx->max_games, ctx->stats_dev);
+    C4_CUDA(cudaMemcpyAsync(ctx->pinned + 40, ctx->stats_dev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if ((rc = read_counters(ctx, &c, s))) return rc;
+    if ((rc = check_device_errors(c))) return rc;
+    after[0] = ctx->pinned[40]; after[1] = ctx->pinned[41]; after[2] = c.games_finished; after[3] = ctx->pinned[42];
+    float ms = 0.f;
+    C4_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (evals) *evals = (int64_t)(after[0] - before[0]);
+    if (positions) *positions = (int64_t)(after[1] - before[1]);
+    if (games) *games = (int64_t)(after[2] - before[2]);
+    if (memo_hits) *memo_hits = (int64_t)(after[3] - before[3]);
+    if (device_ms) *device_ms = ms;
+    if (engine) *engine = eng;
     return 0;
 }
 

@@ -160,13 +160,14 @@ __device__ __forceinline__ void head_tail(const float *scratch, const float *hp,
 template <int F_> struct TcC;
 // SLICED: the single weight stage is refilled one dy slice at a time -- the next layer's slice dy is requested as soon as
 // the last tile of this layer has issued its dy MMAs, so the reload runs under the rest of that tile and its epilogue.
-template <> struct TcC<32> { static constexpr int F = 32, NB = 16, T = 7, ROWS = 912, WSTAGES = 3, ACC_SLOTS = 3, GROUPS = 2; static constexpr bool SLICED = false; };
-template <> struct TcC<64> { static constexpr int F = 64, NB = 6, T = 3, ROWS = 400, WSTAGES = 1, ACC_SLOTS = 1, GROUPS = 1; static constexpr bool SLICED = true; };
+template <> struct TcC<32> { static constexpr int F = 32, NB = 16, T = 7, ROWS = 912, WSTAGES = 3, ACC_SLOTS = 3, GROUPS = 2, EPI_WARPS = 16; static constexpr bool SLICED = false; };
+template <> struct TcC<64> { static constexpr int F = 64, NB = 6, T = 3, ROWS = 400, WSTAGES = 1, ACC_SLOTS = 1, GROUPS = 1, EPI_WARPS = 16; static constexpr bool SLICED = true; };
 #define TC_CH 16                       // channels per epilogue thread (one slice)
 #define TC_THREADS 576                 // warp 0 weight producer, warp 1 MMA issuer, warps 2..17 epilogue
 #define TC_EPI_WARPS 16
-template <int F_> struct TcK : TcC<F_> {
-    using C = TcC<F_>;
+// derived constants and the shared-memory map of one geometry (TcC<F> for the batch kernel, c4_fused.cu has its own)
+template <class C_> struct TcKc : C_ {
+    using C = C_;
     static constexpr int KC = C::F / 8;                                    // 16-byte k-chunks per pixel
     static constexpr int NN = 3 * C::F;                                    // N = 3 dx x F output channels
     static constexpr int SLICES = C::F / TC_CH;                            // channel slices of 16
@@ -177,7 +178,7 @@ template <int F_> struct TcK : TcC<F_> {
     static constexpr int WBARS = C::SLICED ? 3 : C::WSTAGES;               // weight barriers: per dy slice / per stage
     static constexpr int STEM_KC = C::SLICED ? KC : 2;                     // k-chunk pitch of the stem's packed weights
     static constexpr int ACC_COL0 = C::T * C::F;                           // TMEM: residual stream first, then the slots
-    static_assert(GROUP_WARPS * C::GROUPS == TC_EPI_WARPS, "16 epilogue warps");
+    static_assert(GROUP_WARPS * C::GROUPS == C::EPI_WARPS, "epilogue warps = groups x (4 lane quadrants x channel slices)");
     static_assert(ACC_COL0 + C::ACC_SLOTS * NN <= 512, "TMEM columns");
     static_assert(16 * C::T >= 7 * C::NB && C::ROWS == 128 * C::T + 16, "strip geometry");
     // shared memory map
@@ -189,6 +190,7 @@ template <int F_> struct TcK : TcC<F_> {
     __host__ __device__ static constexpr int bars(int R) { return scratch(R) + SLICES * C::NB * 128 * 4; }   // [slice][board][128]
     __host__ __device__ static constexpr int total(int R) { return bars(R) + 256; }
 };
+template <int F_> using TcK = TcKc<TcC<F_>>;
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
 {
@@ -216,11 +218,24 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// Spin until the phase completes.  A wait that lasts ~5 s of SM cycles can only be a protocol bug: trap (the launch
+// fails with an error) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    for (uint32_t it = 1;; it++) {
+        if (mbar_try(bar, parity)) return;
+        if ((it & 0xfu) == 0u && clock64() - t0 > 10000000000LL) __trap();
+    }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
@@ -362,3 +377,86 @@ __device__ __forceinline__ void tc_epilogue_layer(const EpiCtx &E, int l, int T,
     }
 }
 
+// mbarrier wait for warps that may wait LONG (the fused engine's tower idles while its SM has no leaves): after a few
+// failed polls the warp sleeps between polls so that it does not take issue slots from the tree warps of the same SM
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity)
+{
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    for (uint32_t it = 1;; it++) {
+        if (mbar_try(bar, parity)) return;
+        if (it > 8u) __nanosleep(it > 64u ? 256 : 32);
+        if ((it & 0xfu) == 0u && clock64() - t0 > 10000000000LL) __trap();
+    }
+}
+
+// The same epilogue in two steps of 8 channels: at most 40 accumulator / residual / result values are live per thread,
+// so it fits the 64 registers of the 1024-thread fused engine (c4_fused.cu) without spilling.  Every output element goes
+// through exactly the same operations in the same order as in tc_epilogue_layer (the head partial sums are carried
+// across the two steps), so both kernels produce bit-identical network answers.
+template <typename OP, typename K, int KIND>
+__device__ __forceinline__ void tc_epilogue_layer8(const EpiCtx &E, int l, int T, int c0)
+{
+    constexpr int F = K::F;
+    constexpr bool TO_RES = (KIND == 0 || KIND == 2), ADD_RES = (KIND == 2 || KIND == 3), LAST = (KIND == 3);
+    unsigned char *dst = (KIND == 1) ? E.dst_h : E.dst_x;
+    const float *bl = E.bias + l * F + TC_CH * E.half;
+#pragma unroll 1
+    for (int t = (E.group + K::GROUPS - c0 % K::GROUPS) % K::GROUPS; t < T; t += K::GROUPS) {
+        const int c = c0 + t, slot = c % K::ACC_SLOTS;
+        mbar_wait_idle(E.b_accfull + 8 * slot, (uint32_t)(c / K::ACC_SLOTS) & 1u);
+        TC_FENCE_AFTER();
+        const uint32_t ta = E.tmem_acc + slot * K::NN;
+        const uint32_t tr = E.tmem_res + F * t;
+        const bool valid = (E.valid_mask >> t) & 1u;
+        float a = 0.f, p0 = 0.f, p1 = 0.f;
+#pragma unroll
+        for (int h0 = 0; h0 < TC_CH; h0 += 8) {
+            float em[8], ez[8], ep[8], rs[8];
+            tmem_ld8(ta + h0, em);
+            tmem_ld8(ta + F + h0, ez);
+            tmem_ld8(ta + 2 * F + h0, ep);
+            if (ADD_RES) tmem_ld8(tr + h0, rs);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (h0 + 8 == TC_CH) {
+                TC_FENCE_BEFORE();
+                __syncwarp();
+                if (E.lane == 0) mbar_arrive(E.b_accempty + 8 * slot);    // accumulator slot free for the MMA warp
+            }
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                float2 m1 = make_float2(__shfl_sync(0xffffffffu, em[j], E.lm), __shfl_sync(0xffffffffu, em[j + 1], E.lm));
+                float2 q1 = make_float2(__shfl_sync(0xffffffffu, ep[j], E.lp), __shfl_sync(0xffffffffu, ep[j + 1], E.lp));
+                float2 y = __fadd2_rn(__fadd2_rn(m1, make_float2(ez[j], ez[j + 1])),
+                                      __fadd2_rn(q1, make_float2(bl[h0 + j], bl[h0 + j + 1])));
+                if (ADD_RES) y = __fadd2_rn(y, make_float2(rs[j], rs[j + 1]));
+                float2 z = __fmul2_rn(y, make_float2(LEAKY, LEAKY));
+                v[j] = fmaxf(y.x, z.x);
+                v[j + 1] = fmaxf(y.y, z.y);
+            }
+            if (TO_RES) tmem_st8(tr + h0, v);
+            if (!LAST) {
+                if (valid)
+                    *reinterpret_cast<uint4 *>(dst + (size_t)t * (128 * 16) + (size_t)(h0 / 8) * (K::ROWS * 16)) =
+                        make_uint4(OP::pack(v[0], v[1]), OP::pack(v[2], v[3]), OP::pack(v[4], v[5]), OP::pack(v[6], v[7]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    a = fmaf(v[j], E.hp[HO_VW + TC_CH * E.half + h0 + j], a);
+                    p0 = fmaf(v[j], E.hp[HO_PW + TC_CH * E.half + h0 + j], p0);
+                    p1 = fmaf(v[j], E.hp[HO_PW + F + TC_CH * E.half + h0 + j], p1);
+                }
+            }
+        }
+        if (LAST && valid) {
+            const int rb = 16 * t + E.rb0, b = rb / 7;
+            float *sc = E.scratch + b * 128 + (rb - 7 * b - 1) * 7 + (E.col8 - 1);
+            sc[0] = a; sc[42] = p0; sc[84] = p1;
+        }
+        if (TO_RES) asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        if (!LAST) TC_PROXY_FENCE();
+        __syncwarp();
+        if (E.lane == 0) mbar_arrive(E.b_epi + 8 * t);
+    }
+}

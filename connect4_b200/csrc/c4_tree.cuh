@@ -21,7 +21,9 @@ struct C4Counters {
     unsigned long long n_done;          // stand-alone searches finished
     unsigned long long overflow;        // records dropped (records_out too small)
     int leaf_count[2][2];               // [pool][parity] ping-pong leaf batch counters
-    int pad[32 - 14];
+    int engine_error;                   // fused engine: non-zero = the kernel gave up (watchdog), see c4_fused.cu
+    int net_nonfinite;                  // a network answer was not finite (fp16 operand overflow): the call fails loudly
+    int pad[32 - 16];
     int stop_flag[2][2];                // [pool][parity], on its own 128-byte line: set by the warp whose request makes
                                         // the batch reach the pass's stop count, polled (read-only) by the running warps
     int pad2[28];
@@ -135,7 +137,7 @@ __device__ __forceinline__ float seq_sum7f(float v)
 // gamma(alpha, 1) variate (Marsaglia-Tsang, with the U^(1/alpha) boost for alpha < 1); replaces np.random.gamma of
 // oinkoink/mcts.py:175 -- distributionally, not draw-for-draw (the reference's global MT19937 stream is not
 // reproducible across threads anyway).
-__device__ double c4_gamma(Philox &ph, double alpha)
+static __device__ double c4_gamma(Philox &ph, double alpha)
 {
     double a = alpha < 1.0 ? alpha + 1.0 : alpha;
     double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);

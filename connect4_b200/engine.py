@@ -202,6 +202,20 @@ class Engine():
                     net_ctas=self.lib.c4_ctx_get(self.h, 1), memo_log2=self.lib.c4_ctx_get(self.h, 4),
                     memo_hits=self.lib.c4_ctx_get(self.h, 5))
 
+    def stream(self, kind, stop_games=0, max_ms=0.0, reset=False, cold_memo=False):
+        """continuous self-play on the re-seeding pool (c4_selfplay_stream): until `stop_games` more games have finished
+        or `max_ms` device milliseconds have passed; cold_memo empties the evaluation memo first."""
+        k = {"centre": EVAL_CENTRE, "net": EVAL_NET}[kind]
+        if cold_memo:
+            _lib.check(self.lib.c4_ctx_clear_memo(self.h, _lib.stream_ptr()))
+        pos, ev, hits, games = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        ms, eng = C.c_float(0), C.c_int32(0)
+        _lib.check(self.lib.c4_selfplay_stream(self.h, k, int(bool(reset)), int(stop_games), float(max_ms), C.byref(pos),
+                                               C.byref(ev), C.byref(hits), C.byref(games), C.byref(ms), C.byref(eng),
+                                               _lib.stream_ptr()))
+        return dict(positions=pos.value, evals=ev.value, memo_hits=hits.value, games=games.value, device_ms=ms.value,
+                    engine={1: "lockstep", 2: "fused"}.get(eng.value, "?"), memo_log2=self.lib.c4_ctx_get(self.h, 4))
+
     def reset_pool(self):
         _lib.check(self.lib.c4_selfplay_reset(self.h, _lib.stream_ptr()))
 

@@ -41,6 +41,10 @@ class SelfPlayPool():
         reference's flip augmentation (neural/pytorch/data.py:78-105), packed on the device."""
         return augment_pack(self.engine.last_records_device)
 
+    def stream(self, stop_games=0, max_ms=0.0, reset=False, cold_memo=False):
+        """continuous self-play with immediate re-seeding (BASELINE configs[2]); see c4_selfplay_stream"""
+        return self.engine.stream(self.kind, stop_games, max_ms, reset, cold_memo)
+
     def throughput(self, iterations):
         """steady-state measurement: see c4_selfplay_bench in include/c4b200.h"""
         return self.engine.bench(iterations, self.kind)

@@ -186,6 +186,20 @@ int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int64_t game_id
 int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations, int64_t *positions, int64_t *evals,
                       int64_t *sims, int64_t *games, float *device_ms, float *net_ms, float *tree_ms, void *stream);
 int c4_selfplay_reset(c4_ctx *ctx, void *stream);
+/* Continuous self-play on the re-seeding pool, engine-agnostic -- the reference's free-running runtime
+ * (neural/game_pool.py:15-49 game threads + neural/inference_server.py:37-63 request loop) as ONE call:
+ * `reset` != 0 starts a fresh pool (every slot at ply 0 of a new game, counters zero); otherwise the pool continues where
+ * the last call left it.  Runs until `stop_games` more games have finished (0 = no game limit) or `max_ms` device
+ * milliseconds have passed (0 = no time limit); at least one of the two must be given.  HOST outputs (any may be NULL):
+ * positions = root moves played, evals = network evaluations, memo_hits = leaves answered by the evaluation memo, games =
+ * games finished, device_ms = CUDA-event time, engine = 2 when the fused persistent engine ran (c4_fused.cu: one launch,
+ * tree warps and the tcgen05 tower on the same SM, no pass barrier; 32-filter networks), 1 for the lock-step pass engine
+ * (env C4_ENGINE=lockstep forces it).  Records are discarded.  Synchronises the stream. */
+int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t stop_games, double max_ms, int64_t *positions,
+                       int64_t *evals, int64_t *memo_hits, int64_t *games, float *device_ms, int32_t *engine,
+                       void *stream);
+/* Empty the evaluation memo (Evaluator.position_table of a new generation, oinkoink/neural/game_pool.py:21-27). */
+int c4_ctx_clear_memo(c4_ctx *ctx, void *stream);
 
 /* Generation sink: records -> the reference's data.pth tensors with left-right flip augmentation
  * (native_to_pytorch(add_fliplr=True), neural/pytorch/data.py:78-105): boards [2n][3][6][7] f32, values [2n] f32,

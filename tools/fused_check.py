@@ -1,0 +1,56 @@
+"""fused persistent engine vs lock-step pass engine: identical records on the same generation, then the cold-memo
+config-3 throughput of both.  usage: fused_check.py [--quick] [--games N] [--sims S]"""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from connect4_b200.mcts import MCTSConfig
+from connect4_b200.neural.game_pool import SelfPlayPool
+from connect4_b200.neural.model import ModelWrapper
+
+z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests/golden/example_net_state.npz"))
+model = ModelWrapper(state_dict={k: z[k] for k in z.files})
+
+
+def gen(engine, slots, sims, n_games, seed=3):
+    os.environ["C4_ENGINE"] = engine
+    pool = SelfPlayPool(model, MCTSConfig(sims, 19652, 1.25, 0.3, 0.25, 6), concurrent_games=slots, seed=seed)
+    t0 = time.perf_counter()
+    rec = pool.generate_records(n_games)
+    dt = time.perf_counter() - t0
+    pool.engine.close()
+    order = np.lexsort((rec["ply"], rec["game_id"]))
+    raw = rec.view(np.uint8).reshape(-1, 64)[order]      # whole 64-byte records (fancy indexing of the structured
+    return raw.copy().view(rec.dtype).reshape(-1), dt     # array itself would leave the padding bytes undefined)
+
+
+for slots, sims, n in ((8, 16, 8), (64, 64, 200), (300, 200, 700)):
+    a, ta = gen("fused", slots, sims, n)
+    b, tb = gen("lockstep", slots, sims, n)
+    same = len(a) == len(b) and a.tobytes() == b.tobytes()
+    print("slots %4d sims %4d games %4d: fused %6d records %.3f s | lockstep %6d records %.3f s | identical %s" % (
+        slots, sims, n, len(a), ta, len(b), tb, same), flush=True)
+    if not same:
+        k = min(len(a), len(b))
+        bad = [i for i in range(k) if a[i].tobytes() != b[i].tobytes()][:3]
+        for i in bad:
+            print("  first diffs", i, a[i], b[i])
+            xa, xb = np.frombuffer(a[i].tobytes(), np.uint8), np.frombuffer(b[i].tobytes(), np.uint8)
+            print("   differing byte offsets", np.nonzero(xa != xb)[0].tolist(), xa[xa != xb].tolist(), xb[xa != xb].tolist())
+        sys.exit(1)
+if "--quick" in sys.argv:
+    sys.exit(0)
+slots = int(sys.argv[sys.argv.index("--games") + 1]) if "--games" in sys.argv else 4096
+sims = int(sys.argv[sys.argv.index("--sims") + 1]) if "--sims" in sys.argv else 800
+for engine in ("fused", "lockstep"):
+    os.environ["C4_ENGINE"] = engine
+    pool = SelfPlayPool(model, MCTSConfig(sims, 19652, 1.25, 0.3, 0.25, 6), concurrent_games=slots, seed=1)
+    for rep in range(2):
+        r = pool.stream(stop_games=slots, reset=True, cold_memo=True)
+        print("%-8s cold generation until %d games: %.3f s  %.0f positions/s  evals %d hit %.3f engine %s" % (
+            engine, slots, r["device_ms"] / 1e3, r["positions"] / r["device_ms"] * 1e3, r["evals"],
+            r["memo_hits"] / max(1, r["memo_hits"] + r["evals"]), r["engine"]), flush=True)
+    for rep in range(3):
+        r = pool.stream(max_ms=500.0)
+        print("%-8s warm 0.5 s: %.0f positions/s  hit %.3f" % (engine, r["positions"] / r["device_ms"] * 1e3,
+              r["memo_hits"] / max(1, r["memo_hits"] + r["evals"])), flush=True)
+    pool.engine.close()

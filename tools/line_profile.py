@@ -20,7 +20,8 @@ iS, iSrc = hdr.index("# Samples"), hdr.index("Source")
 sass = [(int(r[iS]), r[iSrc].strip()) for r in rows[2:] if len(r) > iS and r[iS].isdigit()]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cub = [f for f in os.listdir(tmp) if "c4_search" in f][0]
+want = sys.argv[4] if len(sys.argv) > 4 else "c4_search"
+cub = [f for f in os.listdir(tmp) if want in f][0]
 dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
 lines, cur, on = [], None, False
 for l in dis.splitlines():

@@ -1,23 +1,31 @@
 #!/usr/bin/env python3
 """bench.py -- self-play positions/sec at 800 sims/move (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine auto|fused|lockstep]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload (ours): BASELINE.json configs[2] -- 4096 concurrent self-play games per GPU, default NetConfig ResNet
-(32 filters / 3 residual / 4 fc; the reference's example_net weights), 800 simulations per move, AlphaZero root noise +
-6 sampled moves, 16-bit tensor-core batched leaf evaluation (fp16 operands, fp32 accumulate).  Games never interact, so with N GPUs every rank runs its own pool
-(weak scaling, no data-path collective).
+Workload (ours): BASELINE.json configs[2] as SURVEY.md 8(d) defines it -- 4096 concurrent self-play games per GPU from
+the empty board, default NetConfig ResNet (32 filters / 3 residual / 4 fc; the reference's example_net weights), 800
+simulations per move, AlphaZero root noise + 6 sampled moves, finished games re-seeded at once, run until 4096 games
+have completed -- FROM A COLD EVALUATION MEMO (the reference's position_table lives for one generation,
+oinkoink/neural/game_pool.py:21-27).  Games never interact, so with N GPUs every rank runs its own pool (weak scaling).
 
-A "step" = `--passes` lock-step passes of the pool in steady state (finished games re-seeded at once); every pass
-advances each game to its next leaf, evaluates all leaves in one network launch and backs the answers up.
+A "step" = one such generation: fresh pool, empty memo, until `--games` games have finished.
   value = positions (root moves played) of all ranks / device time (CUDA events, max over ranks), inputs resident.
-  e2e   = the same metric through the public API with HOST buffers: SelfPlayPool.generate_records() plays a whole
-          generation from host-resident start positions and returns the position records to host memory.
-  roofline = the dominant kernel of the step -- with the evaluation memo that is the tree pass k_advance (HBM class):
-          algorithmic bytes per launch (1.28 KB per simulation, SURVEY.md 8d, + 64 B per memo probe) / its mean
-          CUDA-event duration sampled inside the timed region, against the measured copy bandwidth; the network kernel's
-          TFLOP/s figure against the measured sustained bf16 peak (MEASURED_PEAKS.json) is reported as roofline_other.
+  e2e   = the same metric through the public API with HOST buffers: a whole generation of `--e2e-games` games per GPU
+          (4 pool-fulls, drain of the last games included) from pinned host start positions to host records, memo
+          cold; with N > 1 through dist.generate_sharded, i.e. the NCCL all-gather of every rank's records and the
+          device-side sort are inside the timed region.
+  generation_1200 = BASELINE.json configs[3]: the reference's example_config generation (1200 games, 64f/6r/6fc
+          network) sharded over the N GPUs incl. the all-gather; seconds and the digest of the gathered records
+          (identical for every N).
+  steady_state = the warm regime (memo filled by several seconds of play) -- context only, a real generation never
+          gets there.
+  roofline = the engine's dominant kernel.  Fused engine: ONE kernel (k_fused) holds the tree warps and the tcgen05
+          tower; its tensor-side figure (network FLOPs / kernel time vs the measured sustained bf16 peak) is `roofline`,
+          its HBM-side figure (1.28 KB per simulation + 64 B per memo probe) `roofline_other`.  Lock-step
+          engine: the tree pass / the network kernel from launch durations sampled with CUDA events.
+          `traffic` is null: no DRAM counter is read inside this run (ncu captures are under profiles/).
   cpu_baseline = the oracle port (oracle/selfplay_port.py) on the box's host cores, bounded sample (rank 0, N=1 only).
 --impl reference: the CPU port alone, all host cores, same metric / config.
 """
@@ -141,22 +149,31 @@ def run_reference(args, rank):
         "evals_per_sec": evals / secs, "gpu_launches": 0}), flush=True)
 
 
+def digest_records(rec):
+    import hashlib
+    import numpy as np
+    h = hashlib.sha256()                   # field by field: numpy leaves the 4 padding bytes of a record undefined
+    for f in rec.dtype.names:
+        h.update(np.ascontiguousarray(rec[f]).tobytes())
+    return h.hexdigest()[:16]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
-    ap.add_argument("--passes", type=int, default=2000, help="lock-step passes per step")
-    ap.add_argument("--preroll", type=int, default=0, help="untimed passes that bring the pool to steady state (0: use --preroll-seconds)")
-    ap.add_argument("--preroll-seconds", type=float, default=4.0,
-                    help="untimed device seconds of self-play before the warm-up steps (games at all plies, memo warm)")
-    ap.add_argument("--e2e-games", type=int, default=16384, help="games of the end-to-end generation (4 pool-fulls)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "fused", "lockstep"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU = games a step runs to completion")
+    ap.add_argument("--e2e-games", type=int, default=16384, help="games per GPU of the end-to-end generation (4 pool-fulls)")
+    ap.add_argument("--gen-games", type=int, default=1200, help="games of the example_config generation (configs[3])")
+    ap.add_argument("--steady-seconds", type=float, default=3.0, help="warm steady-state sample after the timed region")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip generation_1200 / steady_state / engine A-B")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -169,10 +186,14 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
+    from connect4_b200.dist import generate_sharded, shard_games
     from connect4_b200.mcts import MCTSConfig
+    from connect4_b200.neural.config import ModelConfig, NetConfig
     from connect4_b200.neural.game_pool import SelfPlayPool
     from connect4_b200.neural.model import ModelWrapper
 
+    if args.engine != "auto":
+        os.environ["C4_ENGINE"] = args.engine
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -182,119 +203,158 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_sum_max(sums, maxs):
+        a = torch.tensor(sums, dtype=torch.float64, device="cuda")
+        b = torch.tensor(maxs, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(a)
+            dist.all_reduce(b, op=dist.ReduceOp.MAX)
+        return [float(x) for x in a.tolist()], [float(x) for x in b.tolist()]
+
     z = np.load(STATE)
     model = ModelWrapper(state_dict={k: z[k] for k in z.files})
     cfg = MCTSConfig(SIMS, 19652, 1.25, 0.3, 0.25, 6)
     pool = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=1000 + rank)
 
-    # untimed: bring the pool to steady state (games at all plies), then W warm-up steps
-    done = 0
-    pre_ms = 0.0
-    while (done < args.preroll) if args.preroll > 0 else (pre_ms < args.preroll_seconds * 1e3):
-        n = min(4000, args.preroll - done) if args.preroll > 0 else 2000
-        pre_ms += pool.throughput(n)["device_ms"]
-        done += n
-    for _ in range(args.warmup):
-        pool.throughput(args.passes)
+    def step():
+        # one generation from a cold memo: fresh pool, every game from the empty board, until `games` games are done
+        return pool.stream(stop_games=args.games, reset=True, cold_memo=True)
 
+    for _ in range(args.warmup):
+        step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    tot = dict(positions=0, evals=0, device_ms=0.0, net_ms=0.0, tree_ms=0.0, games=0, memo_hits=0)
+    tot = dict(positions=0, evals=0, device_ms=0.0, games=0, memo_hits=0, launches=0)
     t_wall = time.perf_counter()
     for _ in range(args.steps):
-        r = pool.throughput(args.passes)
-        for k in ("positions", "evals", "device_ms", "games", "memo_hits"):
+        r = step()
+        for k in tot:
             tot[k] += r[k]
-        memo_log2 = r["memo_log2"]
-        tot["net_ms"] += r["net_ms"]
-        tot["tree_ms"] += r["tree_ms"]
-        pools = r["pools"]
+        engine, memo_log2 = r["engine"], r["memo_log2"]
     barrier()
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if sampler else None
-
-    # whole-job aggregate: sum of units over ranks / max device time over ranks
-    stats = torch.tensor([tot["positions"], tot["evals"], tot["games"]], dtype=torch.float64, device="cuda")
-    tmax = torch.tensor([tot["device_ms"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(stats)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    positions, evals, games = [float(x) for x in stats.tolist()]
-    secs = float(tmax.item()) / 1000.0
+    (positions, evals, games, hits), (dev_ms,) = reduce_sum_max(
+        [tot["positions"], tot["evals"], tot["games"], tot["memo_hits"]], [tot["device_ms"]])
+    secs = dev_ms / 1000.0
     value = positions / secs
 
     # end to end through the public API with host buffers: one whole generation, records back on the host
     e2e = None
     if not args.no_e2e:
-        start = (torch.zeros(args.e2e_games, dtype=torch.int64).pin_memory(),              # host-resident (pinned) inputs:
-                 torch.zeros(args.e2e_games, dtype=torch.int64).pin_memory())              # every game starts from the empty board
-        pool2 = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=5000 + rank)
+        n_e2e = args.e2e_games * world
+        start = (torch.zeros(args.e2e_games, dtype=torch.int64).pin_memory(),               # host-resident (pinned) inputs:
+                 torch.zeros(args.e2e_games, dtype=torch.int64).pin_memory())               # every game from the empty board
+        pool2 = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=5000)
         pool2.generate_records(min(64, args.e2e_games), start=(start[0][:64], start[1][:64]))   # warm the path
+        pool2.engine.clear_memo()
         barrier()
         t0 = time.perf_counter()
-        rec = pool2.generate_records(args.e2e_games, start=start)
+        if world == 1:
+            rec = pool2.generate_records(args.e2e_games, start=start)
+        else:
+            # every rank plays its share (global game ids, so the generation does not depend on N), then the NCCL
+            # all-gather of the records and the device-side sort: every rank ends with the whole generation on the host
+            rec = generate_sharded(pool2, n_e2e)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        e = torch.tensor([float(len(rec))], dtype=torch.float64, device="cuda")
-        tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(e)
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(e.item()) / float(tm.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(2 * 8 * args.e2e_games), "d2h_bytes_per_step": int(len(rec) * 64),
-               "what": "SelfPlayPool.generate_records(%d games on %d slots, host start positions) -> host records; wall "
-                       "clock of the whole generation incl. the drain of the last games" % (args.e2e_games, args.games)}
+        (_,), (dt_max,) = reduce_sum_max([0.0], [dt])
+        n_rec = len(rec)                                                     # N > 1: already the whole job's records
+        e2e = {"value": n_rec / dt_max, "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * 8 * args.e2e_games) if world == 1 else 0,
+               "d2h_bytes_per_step": int(n_rec * 64),
+               "what": ("SelfPlayPool.generate_records(%d games on %d slots, pinned host start positions) -> host records; "
+                        "cold memo; wall clock of the whole generation incl. the drain of the last games" % (
+                            args.e2e_games, args.games)) if world == 1 else
+                       ("dist.generate_sharded(%d games = %d per GPU on %d slots): generation + NCCL all-gather of all "
+                        "records + device-side sort + copy to the host on every rank; cold memo; wall clock, max over "
+                        "ranks" % (n_e2e, args.e2e_games, args.games)),
+               "records": n_rec, "seconds": dt_max, "records_sha256_16": digest_records(rec) if world > 1 else None}
         pool2.engine.close()
+        del rec
+
+    extras = {}
+    if not args.no_extras:
+        # BASELINE configs[3]: the reference's example_config generation (oinkoink/data/example_config.py:8-16) sharded over N
+        torch.manual_seed(0)                                                 # the same random-init network on every rank
+        model64 = ModelWrapper(ModelConfig(net_config=NetConfig(filters=64, n_fc_layers=6, n_residuals=6)))
+        n_local = shard_games(args.gen_games, rank, world)[0]
+        pool3 = SelfPlayPool(model64, cfg, concurrent_games=max(1, n_local), seed=0)
+        best = None
+        for rep in range(2):                                                 # the first run also warms the path
+            pool3.engine.clear_memo()
+            barrier()
+            t0 = time.perf_counter()
+            rec = generate_sharded(pool3, args.gen_games)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            (_,), (dt_max,) = reduce_sum_max([0.0], [dt])
+            best = dt_max
+        extras["generation_1200"] = {
+            "games": args.gen_games, "n_gpus": world, "net": "example_config 64f/6r/6fc (random init, torch.manual_seed(0))",
+            "seconds": best, "positions": int(len(rec)), "positions_per_sec": len(rec) / best,
+            "records_sha256_16": digest_records(rec), "scaling": "strong",
+            "what": "dist.generate_sharded: games g -> rank g % N, NCCL all-gather of the records, device-side sort, host copy"}
+        pool3.engine.close()
+        # warm regime, context only: continue one pool for a few seconds so the memo holds millions of positions
+        step()
+        t_warm = 0.0
+        while t_warm < args.steady_seconds * 1e3:
+            r = pool.stream(max_ms=500.0)
+            t_warm += r["device_ms"]
+        (wp,), (wms,) = reduce_sum_max([r["positions"]], [r["device_ms"]])
+        extras["steady_state"] = {"value": wp / wms * 1e3, "unit": UNIT,
+                                  "memo_hit_rate": r["memo_hits"] / max(1, r["memo_hits"] + r["evals"]),
+                                  "after_device_seconds_of_play": t_warm / 1e3,
+                                  "note": "memo warmed by seconds of play with one network: not reachable in a real generation"}
+        if world == 1 and args.engine == "auto":
+            other = "lockstep" if engine == "fused" else "fused"
+            os.environ["C4_ENGINE"] = other
+            p4 = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=1000)
+            rr = [p4.stream(stop_games=args.games, reset=True, cold_memo=True) for _ in range(3)][1:]
+            if rr[0]["engine"] == other:
+                extras["engine_ab"] = {"engine": other, "value": sum(x["positions"] for x in rr) / sum(x["device_ms"] for x in rr) * 1e3,
+                                       "unit": UNIT, "what": "the same cold generation on this package's other engine"}
+            p4.engine.close()
+            os.environ.pop("C4_ENGINE")
 
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
         flops = model.flops_per_position
-        n_pass = args.steps * args.passes
-        evals_per_pass = tot["evals"] / (n_pass * pools)          # per network launch (one launch per half pool per pass)
-        net_ms = tot["net_ms"] / args.steps
-        tree_ms = tot["tree_ms"] / args.steps
         step_ms = 1000.0 * secs / args.steps
-        net_tf = (evals_per_pass * flops) / (net_ms * 1e-3) / 1e12 if net_ms > 0 else None
-        # tree pass (dominant kernel, HBM class): algorithmic bytes = simulations in the launch x 1.28 KB (SURVEY.md 8d:
-        # select L*(4+28+13k) + backup 24 L + expand + leaf I/O at L = 6.5, k = 7) + 64 B per evaluation-memo probe
-        sims_per_launch = tot["positions"] * SIMS / (n_pass * pools)
-        probes_per_launch = (tot["evals"] + tot["memo_hits"]) / (n_pass * pools)
-        tree_bytes = sims_per_launch * 1280.0 + probes_per_launch * 64.0
-        tree_gbs = tree_bytes / (tree_ms * 1e-3) / 1e9 if tree_ms > 0 else None
-        tree_share = (tree_ms * pools * n_pass / args.steps) / step_ms if secs else None
-        net_share = (net_ms * pools * n_pass / args.steps) / step_ms if secs else None
-        roof_tree = {"kernel": "k_advance<NET,selfplay> (warp-per-game tree pass)", "bound": "hbm", "achieved": tree_gbs,
-                     "peak": peak_hbm, "unit": "GB/s", "frac": (tree_gbs / peak_hbm) if tree_gbs else None,
-                     "traffic": 55.7e6,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, ncu --set "
-                                       "full capture of the profiling command (profiles/r01_advance_v3_full_raw.csv; "
-                                       "shorter passes than the default run, see profiles/README.md)",
-                     "peak_source": peak_src.replace("sustained bf16", "copy bandwidth"),
-                     "algorithmic_bytes_per_launch": tree_bytes, "sims_per_launch": sims_per_launch,
-                     "ms_per_launch": tree_ms, "share_of_step": tree_share,
-                     "note": "dependent-load latency bound (one round trip per tree level), not bandwidth bound"}
-        roof_net = {"kernel": "k_net_tc<OpFP16> (tcgen05/TMEM)", "bound": "tensor", "achieved": net_tf, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": (net_tf / peak_tf) if net_tf else None, "traffic": None,
-                    "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals_per_pass,
-                    "ms_per_launch": net_ms, "share_of_step": net_share}
-        dominant_tree = (tree_share or 0) >= (net_share or 0)
+        n_launch = args.steps * world
+        tf = evals * flops / secs / 1e12 / world                              # per GPU
+        tree_bytes = positions * SIMS * 1280.0 + (evals + hits) * 64.0
+        gbs = tree_bytes / secs / 1e9 / world
+        kname = ("k_fused<OpFP16,selfplay> (persistent: tree warps + tcgen05 tower per SM, one launch per step)"
+                 if engine == "fused" else "k_advance<NET,selfplay> + k_net_tc<OpFP16,32> (lock-step passes)")
+        roof_t = {"kernel": kname, "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                  "traffic": None, "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals / n_launch,
+                  "ms_per_launch": step_ms if engine == "fused" else None,
+                  "note": "network FLOPs of the step / step time; the step is bound by instruction issue and dependent-chain "
+                          "latency (tree simulations + the tower's epilogue), not by the tensor pipe"}
+        roof_h = {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                  "traffic": None, "peak_source": peak_src.replace("sustained bf16", "copy bandwidth"),
+                  "algorithmic_bytes_per_launch": tree_bytes / n_launch, "sims_per_launch": positions * SIMS / n_launch,
+                  "note": "1.28 KB per simulation (SURVEY.md 8d) + 64 B per memo probe; dependent-load latency bound"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "games_per_gpu": args.games, "passes_per_step": args.passes,
-                       "preroll_passes": done, "preroll_device_seconds": pre_ms / 1e3, "simulations": SIMS, "evaluation_memo_log2_entries": memo_log2,
-                       "l2": "node pool (%.0f MB/GPU) + evaluation memo (%.1f GB) exceed L2; fresh leaves every pass" %
+            "config": {"workload": WORKLOAD, "games_per_gpu": args.games, "simulations": SIMS, "memo": "cold (emptied before every step)",
+                       "step": "fresh pool, finished games re-seeded at once, until %d games have completed" % args.games,
+                       "engine": engine, "evaluation_memo_log2_entries": memo_log2,
+                       "l2": "node pool (%.0f MB/GPU) + evaluation memo (%.1f GB) exceed L2; every step starts cold" %
                              (args.games * (SIMS + 2) * 256 / 1e6, (64 << memo_log2) / 1e9 if memo_log2 else 0.0)},
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": int(2 * pools * n_pass + 4 * args.steps),
-            "roofline": roof_tree if dominant_tree else roof_net,
-            "roofline_other": roof_net if dominant_tree else roof_tree,
+            "gpu_launches": int(tot["launches"] + args.steps),                  # + k_selfplay_init of every step (rank 0's count)
+            "roofline": roof_t, "roofline_other": roof_h,
             "sims_per_sec": value * SIMS, "network_evals_per_sec": evals / secs,
-            "memo_hit_rate": (tot["memo_hits"] / max(1.0, tot["memo_hits"] + tot["evals"])),
+            "memo_hit_rate": hits / max(1.0, hits + evals),
             "games_finished": games, "wall_s_timed_region": t_wall,
         }
+        line.update(extras)
         if world == 1 and not args.no_cpu:
             r, cores = cpu_port(args.cpu_seconds)
             line["cpu_baseline"] = {

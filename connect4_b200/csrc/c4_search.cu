@@ -406,6 +406,7 @@ struct c4_ctx {
     int last_pending;
     bool supplied;
     bool pool_fresh;                    // bench pool initialised
+    long long last_launches;            // kernels launched by the last c4_selfplay_stream call
     int pool_engine;                    // engine that owns the re-seeding pool's state: 0 none, 1 lock-step, 2 fused
     cudaEvent_t ev0, ev1;
     cudaEvent_t evs[2 * 64];            // sampled (start, stop) pairs around network launches
@@ -591,6 +592,7 @@ extern "C" int c4_ctx_get(c4_ctx *ctx, int key)
     case 3: return ctx->max_games;
     case 4: return ctx->d.memo ? ctx->memo_log2 : 0;
     case 5: return (int)std::min<long long>(ctx->last_memo_hits, 0x7fffffff);
+    case 6: return (int)std::min<long long>(ctx->last_launches, 0x7fffffff);
     default: return -1;
     }
 }
@@ -1045,12 +1047,15 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     before[0] = ctx->pinned[40]; before[1] = ctx->pinned[41]; before[2] = c.games_finished; before[3] = ctx->pinned[42];
     const unsigned long long games_goal = stop_games > 0 ? before[2] + (unsigned long long)stop_games : 0ULL;
     C4_CUDA(cudaEventRecord(ctx->ev0, s));
+    ctx->last_launches = 2;                                  // k_sum_stats before and after
     if (fused) {
         if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, games_goal, max_ms, s))) return rc;
+        ctx->last_launches += 1;
     } else {
         // lock-step engine: chunks of passes with a host look at the counters in between
         for (long long it = 0;; it++) {
             if ((rc = selfplay_passes(ctx, eval_kind, 64, s))) return rc;
+            ctx->last_launches += 64 * (eval_kind == C4_EVAL_NET ? 2 * ctx->n_pools : 1);
             C4_CUDA(cudaEventRecord(ctx->ev1, s));
             if ((rc = read_counters(ctx, &c, s))) return rc;
             float ms = 0.f;

@@ -33,17 +33,27 @@ def all_gather_records(records, group=None):
     return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
 
 
+def sort_records_device(rec):
+    """records (uint8 tensor [n, 64], any device) ordered by (game_id, ply): the key is read out of the raw bytes and
+    sorted where the records live, so a gathered generation is put in order on the GPU before it goes to the host"""
+    import torch
+    if rec.shape[0] == 0:
+        return rec
+    gid = rec[:, 52:56].contiguous().view(torch.int32).reshape(-1).to(torch.int64)
+    ply = rec[:, 57].to(torch.int64)
+    order = torch.argsort(gid * 64 + ply)
+    return rec.index_select(0, order)
+
+
 def generate_sharded(pool, n_games, group=None):
     """Play this rank's share of `n_games` on `pool` (SelfPlayPool) and all-gather the records of all ranks.
     Returns a numpy record array sorted by (game_id, ply) -- identical on every rank."""
-    import torch
     import torch.distributed as dist
     from .engine import RECORD_DTYPE
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
     n_local, base, stride = shard_games(n_games, rank, world)
-    pool.generate_records(n_local, game_id_base=base, game_id_stride=stride)
+    pool.generate_records(n_local, game_id_base=base, game_id_stride=stride, to_host=False)
     rec = pool.engine.last_records_device
     if world > 1:
         rec = all_gather_records(rec, group)
-    out = rec.cpu().numpy().view(RECORD_DTYPE).reshape(-1)
-    return out[np.lexsort((out["ply"], out["game_id"]))]
+    return sort_records_device(rec).cpu().numpy().view(RECORD_DTYPE).reshape(-1)

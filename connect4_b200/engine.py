@@ -174,8 +174,9 @@ class Engine():
         return out
 
     # ------------------------------------------------------------------ self-play
-    def selfplay(self, n_games, kind, game_id_base=0, game_id_stride=1, start=None):
-        """Play n_games complete games; returns the position records (numpy structured array, RECORD_DTYPE)."""
+    def selfplay(self, n_games, kind, game_id_base=0, game_id_stride=1, start=None, to_host=True):
+        """Play n_games complete games; returns the position records (numpy structured array, RECORD_DTYPE), or with
+        to_host=False leaves them on the device (`last_records_device`) and returns their number."""
         torch = self.torch
         k = {"centre": EVAL_CENTRE, "net": EVAL_NET}[kind]
         cap = int(n_games) * 42
@@ -187,6 +188,8 @@ class Engine():
         _lib.check(self.lib.c4_selfplay_run(self.h, k, int(n_games), int(game_id_base), int(game_id_stride),
                                             ptr(s0), ptr(s1), ptr(rec), cap, C.byref(n), _lib.stream_ptr()))
         self.last_records_device = rec[:n.value]
+        if not to_host:
+            return n.value
         return rec[:n.value].cpu().numpy().view(RECORD_DTYPE).reshape(-1)
 
     def bench(self, iterations, kind):
@@ -207,14 +210,19 @@ class Engine():
         or `max_ms` device milliseconds have passed; cold_memo empties the evaluation memo first."""
         k = {"centre": EVAL_CENTRE, "net": EVAL_NET}[kind]
         if cold_memo:
-            _lib.check(self.lib.c4_ctx_clear_memo(self.h, _lib.stream_ptr()))
+            self.clear_memo()
         pos, ev, hits, games = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
         ms, eng = C.c_float(0), C.c_int32(0)
         _lib.check(self.lib.c4_selfplay_stream(self.h, k, int(bool(reset)), int(stop_games), float(max_ms), C.byref(pos),
                                                C.byref(ev), C.byref(hits), C.byref(games), C.byref(ms), C.byref(eng),
                                                _lib.stream_ptr()))
         return dict(positions=pos.value, evals=ev.value, memo_hits=hits.value, games=games.value, device_ms=ms.value,
-                    engine={1: "lockstep", 2: "fused"}.get(eng.value, "?"), memo_log2=self.lib.c4_ctx_get(self.h, 4))
+                    engine={1: "lockstep", 2: "fused"}.get(eng.value, "?"), memo_log2=self.lib.c4_ctx_get(self.h, 4),
+                    launches=self.lib.c4_ctx_get(self.h, 6))
+
+    def clear_memo(self):
+        """a new generation starts with an empty evaluation memo (oinkoink/neural/game_pool.py:21-27)"""
+        _lib.check(self.lib.c4_ctx_clear_memo(self.h, _lib.stream_ptr()))
 
     def reset_pool(self):
         _lib.check(self.lib.c4_selfplay_reset(self.h, _lib.stream_ptr()))

@@ -28,9 +28,9 @@ class SelfPlayPool():
             mcts_config.num_sampling_moves > 0
         self.engine.set_rng("philox" if noisy else "none", seed=seed)
 
-    def generate_records(self, n_games, game_id_base=0, game_id_stride=1, start=None):
+    def generate_records(self, n_games, game_id_base=0, game_id_stride=1, start=None, to_host=True):
         """Play n_games games; returns the 64-byte position records (numpy, engine.RECORD_DTYPE)."""
-        return self.engine.selfplay(n_games, self.kind, game_id_base, game_id_stride, start)
+        return self.engine.selfplay(n_games, self.kind, game_id_base, game_id_stride, start, to_host)
 
     def generate(self, n_games, **kw) -> List[GameData]:
         """`game_pool(...) -> List[GameData]` of the reference."""

@@ -46,6 +46,7 @@ SIGNATURES = {
     "c4_net_destroy": (C.c_int, [vp]),
     "c4_net_forward": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp]),
     "c4_net_flops_per_position": (C.c_double, [vp]),
+    "c4_net_get": (C.c_double, [vp, C.c_int]),
     "c4_ctx_create": (C.c_int, [C.c_int, C.c_int32, C.POINTER(MCTSConfigC), C.POINTER(vp)]),
     "c4_ctx_destroy": (C.c_int, [vp]),
     "c4_ctx_set_config": (C.c_int, [vp, C.POINTER(MCTSConfigC)]),

@@ -324,7 +324,7 @@ k_net_streamed(const unsigned char *__restrict__ image, int R, const u64 *__rest
 }
 
 // global image: [L layers][WSTAGE_BYTES] weights, then biases [(1+2R)*F] fp32, then head block [HEAD_FLOATS] fp32
-template <typename OP, int F>
+template <typename OP, int F, bool CALIB = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__ c0, const u64 *__restrict__ c1, int n,
          const int *__restrict__ count, float *__restrict__ out, long long *__restrict__ dbg)
@@ -486,6 +486,7 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
         E.scratch = scratch + half * K::NB * 128;
         E.lane = lane; E.lm = (lane + 31) & 31; E.lp = (lane + 1) & 31; E.half = half; E.group = group;
         E.rb0 = 4 * quad + (lane >> 3); E.col8 = lane & 7;
+        E.calib = CALIB ? reinterpret_cast<unsigned *>(dbg) : nullptr;
         int c = 0;                                                           // global (strip, layer, tile) counter
         for (int s = 0; s < n_strips; s++) {
             const int nb = min(K::NB, my_n - s * K::NB);
@@ -512,12 +513,12 @@ k_net_tc(const unsigned char *__restrict__ image, int R, const u64 *__restrict__
             if (lane == 0 && e < K::GROUP_WARPS)                             // GROUP_WARPS arrivals per tile barrier and epoch
                 for (int t = 0; t < T; t++) mbar_arrive(b_epi + 8 * t);
 
-            tc_epilogue_layer<OP, F, 0>(E, 0, T, c); c += T;
+            tc_epilogue_layer<OP, F, 0, CALIB>(E, 0, T, c); c += T;
             for (int l = 1; l < L - 1; l += 2) {
-                tc_epilogue_layer<OP, F, 1>(E, l, T, c); c += T;
-                if (l + 1 < L - 1) { tc_epilogue_layer<OP, F, 2>(E, l + 1, T, c); c += T; }
+                tc_epilogue_layer<OP, F, 1, CALIB>(E, l, T, c); c += T;
+                if (l + 1 < L - 1) { tc_epilogue_layer<OP, F, 2, CALIB>(E, l + 1, T, c); c += T; }
             }
-            tc_epilogue_layer<OP, F, 3>(E, L - 1, T, c); c += T;
+            tc_epilogue_layer<OP, F, 3, CALIB>(E, L - 1, T, c); c += T;
 
             // ---- head tails: one warp per board
             EPI_BAR();
@@ -590,23 +591,45 @@ static size_t smem_streamed(int R)
 #define WARPS_A 8
 #define WARPS_B 6
 
-extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4_net **out)
+// blob sections in front of the heads: [4 header][stem W F*27][stem b F] + 2R x ([W F*F*9][b F])
+// The blob with the trunk running at activations * s (s = 2^-k): LeakyReLU is positively homogeneous, so scaling the stem's
+// weights and EVERY conv bias by s scales every trunk activation by exactly s (power of two: the roundings do not move),
+// and dividing the heads' 1x1 conv weights by s gives the original head inputs back.  Returns false if a scaled weight
+// does not fit the operand type (fp16: |w| > 65504).
+static bool scaled_blob(const float *blob, int64_t n, int F, int R, int k, bool fp16, std::vector<float> &out)
 {
-    C4_REQUIRE(blob && out, "c4_net_create: null pointer");
-    C4_REQUIRE(n_floats >= 4 && (int)blob[0] == 0xC4B2, "c4_net_create: bad blob magic");
-    const int F = (int)blob[1], R = (int)blob[2], n_fc = (int)blob[3] & 0xff;
-    const bool fp16 = (((int)blob[3] >> 8) & 0xff) != 1;        // header[3] = n_fc | (operand dtype << 8) | (kernel << 16)
-    const int kernel_sel = ((int)blob[3] >> 16) & 0xff;         // 0 = auto (tcgen05 when filters == 32), 1 = mma.sync
-    C4_REQUIRE(F == 32 || F == 64, "c4_net_create: filters must be 32 or 64");
-    C4_REQUIRE(R >= 1 && R <= 16, "c4_net_create: n_residuals out of range");
-    const int64_t expect = 4 + (int64_t)F * 27 + F + (int64_t)2 * R * ((int64_t)F * F * 9 + F) + F + 1 + 42 * 42 + 42 +
-                           42 + 1 + 2 + 2 * F + 2 + 7 * 84 + 7;
-    C4_REQUIRE(n_floats == expect, "c4_net_create: blob size does not match its header");
-    int ndev = 0;
-    C4_CUDA(cudaGetDeviceCount(&ndev));
-    C4_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (there is no CPU fallback)");
-    C4_CUDA(cudaSetDevice(device));
+    out.assign(blob, blob + n);
+    const float s = ldexpf(1.f, -k), inv = ldexpf(1.f, k);
+    float *p = out.data() + 4;
+    for (int i = 0; i < F * 27 + F; i++) p[i] *= s;                                // stem weights + bias
+    p += F * 27 + F;
+    for (int l = 0; l < 2 * R; l++) {
+        p += (size_t)F * F * 9;
+        for (int i = 0; i < F; i++) p[i] *= s;                                     // conv bias (BN folded)
+        p += F;
+    }
+    for (int i = 0; i < F; i++) p[i] *= inv;                                       // value head 1x1 conv weights
+    float *q = p + F + 1 + 42 * 42 + 42 + 42 + 1 + 2;
+    for (int i = 0; i < 2 * F; i++) q[i] *= inv;                                   // policy head 1x1 conv weights
+    // conv weights are the 16-bit operands (biases and heads stay fp32): every one must be finite and fit the operand type
+    const float lim = fp16 ? 65504.f : 3.38e38f;
+    const float *w = out.data() + 4;
+    for (int i = 0; i < F * 27; i++)
+        if (!(fabsf(w[i]) <= lim)) return false;
+    w += F * 27 + F;
+    for (int l = 0; l < 2 * R; l++) {
+        for (size_t i = 0; i < (size_t)F * F * 9; i++)
+            if (!(fabsf(w[i]) <= lim)) return false;
+        w += (size_t)F * F * 9 + F;
+    }
+    return true;
+}
 
+// (re)build and upload the device images of the network from a (scaled) blob
+static int upload_images(c4_net *net, const float *blob)
+{
+    const int F = net->F, R = net->R;
+    const bool fp16 = net->fp16;
     const size_t total = (F == 32) ? ImageA<32>::total(R) : ImageA<64>::total(R);
     const size_t stem_b = (F == 32) ? ImageA<32>::stem_bytes() : ImageA<64>::stem_bytes();
     const size_t conv_b = (F == 32) ? ImageA<32>::conv_bytes() : ImageA<64>::conv_bytes();
@@ -637,19 +660,9 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
     hp[HO_PB] = *p++; hp[HO_PB + 1] = *p++;
     memcpy(hp + HO_POLW, p, 7 * 84 * 4); p += 7 * 84;
     memcpy(hp + HO_POLB, p, 7 * 4); p += 7;
-
-    static unsigned long long next_uid = 1;
-    c4_net *net = new c4_net();
-    net->uid = next_uid++;
-    net->device = device; net->F = F; net->R = R; net->n_fc = n_fc; net->fp16 = fp16;
     net->image_bytes = total;
-    net->flops = 2.0 * (42.0 * 27 * F + 2.0 * R * 42 * 9 * F * F + 42.0 * F + (double)n_fc * 42 * 42 + 42 + 42.0 * F * 2 +
-                        84.0 * 7);
-    if (cudaMalloc(&net->image, total) != cudaSuccess) { delete net; c4_set_error("cudaMalloc failed"); return -2; }
+    if (!net->image && cudaMalloc(&net->image, total) != cudaSuccess) { c4_set_error("cudaMalloc failed"); return -2; }
     C4_CUDA(cudaMemcpy(net->image, img.data(), total, cudaMemcpyHostToDevice));
-    const int tc_smem = (F == 32) ? TcK<32>::total(R) : TcK<64>::total(R);
-    net->use_tc = kernel_sel != 1 && tc_smem <= 227 * 1024;
-    net->image_tc = nullptr;
     if (net->use_tc) {
         // tcgen05 image: per layer [dy][k-chunk][n = dx*F + co][8 ci] 16-bit, K-major SWIZZLE_NONE core matrices
         const int L = 1 + 2 * R;
@@ -672,8 +685,83 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
             q += (size_t)F * cin * 9 + F;
         }
         memcpy(tc.data() + (size_t)L * stage, bias, small_bytes);               // biases + head block, as in image A
-        if (cudaMalloc(&net->image_tc, tc.size()) != cudaSuccess) { delete net; c4_set_error("cudaMalloc failed"); return -2; }
+        if (!net->image_tc && cudaMalloc(&net->image_tc, tc.size()) != cudaSuccess) { c4_set_error("cudaMalloc failed"); return -2; }
         C4_CUDA(cudaMemcpy(net->image_tc, tc.data(), tc.size(), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// Largest |activation| any trunk layer produces on a fixed set of 512 calibration positions (random stones of both colours,
+// 0..40 plies, deterministic), measured with the tcgen05 kernel itself.  Inf / NaN come back as a huge value.
+static int calibrate_range(c4_net *net, float *max_abs)
+{
+    const int n = 512;
+    std::vector<u64> c0(n), c1(n);
+    u64 rng = 0x9E3779B97F4A7C15ULL;
+    for (int i = 0; i < n; i++) {
+        int h[7] = {0, 0, 0, 0, 0, 0, 0};
+        u64 a = 0, b = 0;
+        rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
+        const int plies = (int)((rng >> 33) % 41);
+        for (int k = 0; k < plies; k++) {
+            rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
+            int col = (int)((rng >> 33) % 7);
+            for (int t = 0; t < 7 && h[col] == 6; t++) col = (col + 1) % 7;
+            if (h[col] == 6) break;
+            const u64 bit = 1ULL << (7 * col + h[col]++);
+            if (k & 1) b |= bit; else a |= bit;
+        }
+        c0[i] = a; c1[i] = b;
+    }
+    u64 *d0 = nullptr, *d1 = nullptr;
+    float *out = nullptr;
+    unsigned *mx = nullptr;
+    C4_CUDA(cudaMalloc(&d0, n * 8)); C4_CUDA(cudaMalloc(&d1, n * 8)); C4_CUDA(cudaMalloc(&out, n * 32));
+    C4_CUDA(cudaMalloc(&mx, 64));
+    C4_CUDA(cudaMemcpy(d0, c0.data(), n * 8, cudaMemcpyHostToDevice));
+    C4_CUDA(cudaMemcpy(d1, c1.data(), n * 8, cudaMemcpyHostToDevice));
+    C4_CUDA(cudaMemset(mx, 0, 64));
+    const int tc_smem = net->F == 32 ? TcK<32>::total(net->R) : TcK<64>::total(net->R);
+    auto k = net->F == 32 ? k_net_tc<OpFP16, 32, true> : k_net_tc<OpFP16, 64, true>;
+    C4_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem));
+    k<<<32, TC_THREADS, tc_smem>>>((const unsigned char *)net->image_tc, net->R, d0, d1, n, nullptr, out,
+                                   reinterpret_cast<long long *>(mx));
+    C4_CUDA(cudaGetLastError());
+    unsigned bits = 0;
+    C4_CUDA(cudaMemcpy(&bits, mx, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d0); cudaFree(d1); cudaFree(out); cudaFree(mx);
+    memcpy(max_abs, &bits, 4);
+    return 0;
+}
+
+extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4_net **out)
+{
+    C4_REQUIRE(blob && out, "c4_net_create: null pointer");
+    C4_REQUIRE(n_floats >= 4 && (int)blob[0] == 0xC4B2, "c4_net_create: bad blob magic");
+    const int F = (int)blob[1], R = (int)blob[2], n_fc = (int)blob[3] & 0xff;
+    const bool fp16 = (((int)blob[3] >> 8) & 0xff) != 1;        // header[3] = n_fc | (operand dtype << 8) | (kernel << 16)
+    const int kernel_sel = ((int)blob[3] >> 16) & 0xff;         // 0 = auto (tcgen05 when filters == 32), 1 = mma.sync
+    C4_REQUIRE(F == 32 || F == 64, "c4_net_create: filters must be 32 or 64");
+    C4_REQUIRE(R >= 1 && R <= 16, "c4_net_create: n_residuals out of range");
+    const int64_t expect = 4 + (int64_t)F * 27 + F + (int64_t)2 * R * ((int64_t)F * F * 9 + F) + F + 1 + 42 * 42 + 42 +
+                           42 + 1 + 2 + 2 * F + 2 + 7 * 84 + 7;
+    C4_REQUIRE(n_floats == expect, "c4_net_create: blob size does not match its header");
+    int ndev = 0;
+    C4_CUDA(cudaGetDeviceCount(&ndev));
+    C4_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (there is no CPU fallback)");
+    C4_CUDA(cudaSetDevice(device));
+
+    static unsigned long long next_uid = 1;
+    c4_net *net = new c4_net();
+    net->uid = next_uid++;
+    net->device = device; net->F = F; net->R = R; net->n_fc = n_fc; net->fp16 = fp16;
+    net->image = nullptr; net->image_tc = nullptr;
+    net->scale_log2 = 0; net->calib_max = 0.f;
+    net->flops = 2.0 * (42.0 * 27 * F + 2.0 * R * 42 * 9 * F * F + 42.0 * F + (double)n_fc * 42 * 42 + 42 + 42.0 * F * 2 +
+                        84.0 * 7);
+    const int tc_smem = (F == 32) ? TcK<32>::total(R) : TcK<64>::total(R);
+    net->use_tc = kernel_sel != 1 && tc_smem <= 227 * 1024;
+    if (net->use_tc) {
         if (F == 32) {
             C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpFP16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem));
             C4_CUDA(cudaFuncSetAttribute(k_net_tc<OpBF16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem));
@@ -703,6 +791,33 @@ extern "C" int c4_net_create(int device, const float *blob, int64_t n_floats, c4
         C4_CUDA(cudaFuncSetAttribute(k_net_streamed<OpBF16, 64, WARPS_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_streamed<64, WARPS_B>(R)));
     }
+
+    // fp16 operands have 5 exponent bits: a trunk whose activations (or BN-folded weights) leave +-65504 would turn into
+    // Inf / NaN.  The trunk is therefore run at activations * 2^-k, k chosen here: calibrate on 512 positions with the
+    // kernel itself and keep a 16x margin.  Networks in the usual range (the reference's checkpoint peaks below 4) get
+    // k = 0, i.e. exactly the unscaled arithmetic.  What calibration cannot foresee is caught at run time: a non-finite
+    // network answer never enters a tree and makes the engine call fail (c4_search.cu / c4_fused.cu).
+    std::vector<float> sb;
+    int rc = 0, k = 0;
+    bool ok = false;
+    for (int attempt = 0; attempt < 12 && !ok; attempt++) {
+        if (!scaled_blob(blob, n_floats, F, R, k, fp16, sb)) { k += 12; continue; }     // a weight overflows fp16
+        if ((rc = upload_images(net, sb.data()))) { c4_net_destroy(net); return rc; }
+        if (!fp16 || !net->use_tc || getenv("C4_NET_NO_CALIBRATION")) { ok = true; break; }
+        float m = 0.f;
+        if ((rc = calibrate_range(net, &m))) { c4_net_destroy(net); return rc; }
+        net->calib_max = m;
+        if (m <= 4096.f) ok = true;                                                    // NaN compares false
+        else if (m < 3.0e38f) k += (int)ceilf(log2f(m / 2048.f));
+        else k += 12;
+    }
+    if (!ok) {
+        c4_net_destroy(net);
+        c4_set_error("invalid argument: c4_net_create: this network's weights / activations do not fit fp16 operands at any "
+                     "power-of-two scale (NaN weights?); use operand_dtype='bf16'");
+        return -1;
+    }
+    net->scale_log2 = k;
     *out = net;
     return 0;
 }
@@ -711,13 +826,26 @@ extern "C" int c4_net_destroy(c4_net *net)
 {
     if (!net) return 0;
     cudaSetDevice(net->device);
-    cudaFree(net->image);
+    if (net->image) cudaFree(net->image);
     if (net->image_tc) cudaFree(net->image_tc);
     delete net;
     return 0;
 }
 
 extern "C" double c4_net_flops_per_position(const c4_net *net) { return net ? net->flops : 0.0; }
+extern "C" double c4_net_get(const c4_net *net, int key)
+{
+    if (!net) return -1.0;
+    switch (key) {
+    case 0: return net->F;
+    case 1: return net->R;
+    case 2: return net->fp16 ? 0.0 : 1.0;
+    case 3: return net->scale_log2;
+    case 4: return net->use_tc ? 1.0 : 0.0;
+    case 5: return net->calib_max;
+    default: return -1.0;
+    }
+}
 unsigned long long c4_net_uid(const c4_net *net) { return net ? net->uid : 0ULL; }   // internal (not part of the C ABI)
 int c4_net_filters(const c4_net *net) { return net ? net->F : 0; }                  // internal
 

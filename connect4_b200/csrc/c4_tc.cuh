@@ -37,6 +37,8 @@ struct c4_net {
     void *image;          // device: smem image (kernel A) / per-layer weight images (kernel B)
     size_t image_bytes;
     double flops;
+    int scale_log2;       // fp16 operands: the trunk runs at activations * 2^-scale_log2 (chosen by calibration at creation)
+    float calib_max;      // largest |activation| (scaled units) the calibration positions produced
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -307,9 +309,10 @@ struct EpiCtx {
     float *scratch;           // + slice * NB * 128
     uint32_t valid_mask;      // bit t: this thread's row of tile t is a real pixel of a board of this strip
     int lane, lm, lp, half, group, rb0, col8;
+    unsigned *calib;          // calibration launches only: running max of the bits of |activation|
 };
 
-template <typename OP, int F, int KIND>
+template <typename OP, int F, int KIND, bool CALIB = false>
 __device__ __forceinline__ void tc_epilogue_layer(const EpiCtx &E, int l, int T, int c0)
 {
     using K = TcK<F>;
@@ -347,6 +350,13 @@ __device__ __forceinline__ void tc_epilogue_layer(const EpiCtx &E, int l, int T,
             v[j + 1] = fmaxf(y.y, z.y);
         }
         const bool valid = (E.valid_mask >> t) & 1u;
+        if (CALIB && valid) {
+            // range calibration (c4_net_create): integer max of the bit patterns, so Inf / NaN read as "too large"
+            unsigned mu = 0u;
+#pragma unroll
+            for (int j = 0; j < TC_CH; j++) mu = max(mu, __float_as_uint(fabsf(v[j])));
+            atomicMax(E.calib, mu);
+        }
         if (TO_RES) tmem_st16(tr, v);
         if (!LAST) {
             if (valid) {

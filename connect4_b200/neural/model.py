@@ -101,6 +101,12 @@ class ModelWrapper():
     def flops_per_position(self):
         return float(_lib.load().c4_net_flops_per_position(self.c4_net))
 
+    @property
+    def trunk_scale_log2(self):
+        """k of the power-of-two trunk scale 2^-k chosen at creation so that fp16 operands cannot overflow (0 for
+        networks in the usual activation range; see c4_net_get in include/c4b200.h)"""
+        return int(_lib.load().c4_net_get(self.c4_net, 3))
+
     # ---- evaluator protocol
     def __call__(self, input_: Union[Board, List[Board]]):
         if isinstance(input_, Board):

@@ -79,6 +79,12 @@ int c4_net_forward(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t 
                    void *stream);
 /* FLOPs (2*MAC, convs + linears) per position of this network: the roofline numerator */
 double c4_net_flops_per_position(const c4_net *net);
+/* Network read-out: key 0 = filters, 1 = residual blocks, 2 = operand type of the conv GEMMs (0 fp16, 1 bf16), 3 = k of
+ * the power-of-two trunk scale 2^-k chosen at creation so that fp16 operands cannot overflow (0 for networks in the usual
+ * range: exactly the unscaled arithmetic), 4 = 1 if the tcgen05 kernel runs it, 5 = largest |activation| (scaled units)
+ * of the 512 calibration positions.  A non-finite network answer at run time never enters a search tree and makes the
+ * engine call fail (the reference asserts: oinkoink/neural/pytorch/model.py:258-263,275-280). */
+double c4_net_get(const c4_net *net, int key);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Search / self-play engine (replaces mcts.search + MCTS.make_move, oinkoink/mcts.py:78-202; tree.py:61-147;

@@ -231,3 +231,90 @@ def test_network_geometries_with_lively_weights(filters, residuals, fc):
         dv, dp = np.abs(v.cpu().numpy() - rv).max(), np.abs(p.cpu().numpy() - rp).max()
         print("%df/%dr/%dfc %s: max|dvalue| %.2e max|dprior| %.2e" % (filters, residuals, fc, kernel, dv, dp))
         assert dv < TOL and dp < TOL
+
+
+def _scaled_trunk_state(c):
+    """the reference's checkpoint with every trunk activation multiplied by c and the heads' 1x1 convs divided by c: the
+    same function (LeakyReLU is positively homogeneous), but fp32 activations of the order of 4 * c"""
+    import torch
+    from oracle import net_ref as nr
+    sd = {k: torch.as_tensor(np.array(v)).clone() for k, v in nr.load_golden_state(os.path.join(GOLDEN, "example_net_state.npz")).items()}
+    sd["body.0.1.weight"] *= c
+    sd["body.0.1.bias"] *= c
+    n_res = len({k.split(".")[2] for k in sd if k.startswith("body.1.")})
+    for i in range(n_res):
+        for j in (1, 2):
+            sd["body.1.%d.batch_norm%d.running_mean" % (i, j)] *= c
+            sd["body.1.%d.batch_norm%d.bias" % (i, j)] *= c
+    sd["value_head.conv1.weight"] /= c
+    sd["policy_head.conv1.weight"] /= c
+    return sd
+
+
+def test_fp16_operands_cannot_overflow_trunk_scale_chosen_at_creation(monkeypatch):
+    """a network whose fp32 activations exceed 1e5 (fp16 tops out at 65504): c4_net_create calibrates a power-of-two trunk
+    scale, the outputs stay within 1e-2 of the fp32 torch restatement; without the calibration the same network overflows
+    and the engine call FAILS -- a non-finite answer never reaches a tree (reference: model.py:258-263 asserts)"""
+    from connect4_b200._lib import C4Error
+    from connect4_b200.engine import Engine
+    from connect4_b200.mcts import MCTSConfig
+    from connect4_b200.neural.game_pool import SelfPlayPool
+    from connect4_b200.neural.model import ModelWrapper
+    from oracle import net_ref as nr
+    sd = _scaled_trunk_state(3.0e5)
+    g = golden("net_outputs.npz")
+    c0, c1 = g["c0"], g["c1"]
+    rv, rp = nr.evaluate(sd, c0, c1)
+    assert np.abs(rv - g["value"]).max() < 1e-4                      # same function as the checkpoint (fp32 torch)
+    m = ModelWrapper(state_dict=sd)
+    assert m.trunk_scale_log2 >= 8
+    v, p = m.evaluate_bitboards(c0, c1)
+    assert np.isfinite(v.cpu().numpy()).all()
+    assert np.abs(v.cpu().numpy() - rv).max() < 1e-2 and np.abs(p.cpu().numpy() - rp).max() < 1e-2
+    assert ModelWrapper(state_dict=nr.load_golden_state(os.path.join(GOLDEN, "example_net_state.npz"))).trunk_scale_log2 == 0
+    # the calibrated network plays
+    pool = SelfPlayPool(m, MCTSConfig(24, 19652, 1.25, 0.3, 0.25, 6), concurrent_games=8, seed=1)
+    assert len(pool.generate_records(8)) >= 56
+    pool.engine.close()
+    # without calibration the operands overflow: loud failure on every engine path, never NaN into a tree
+    # (trunk factor 2e5: the BN-folded stem weights, at most 0.25 in the checkpoint, still fit fp16 -- at 3e5 the weight
+    #  guard of c4_net_create alone would already scale the trunk)
+    monkeypatch.setenv("C4_NET_NO_CALIBRATION", "1")
+    bad = ModelWrapper(state_dict=_scaled_trunk_state(2.0e5))
+    assert bad.trunk_scale_log2 == 0
+    assert not np.isfinite(bad.evaluate_bitboards(c0[:64], c1[:64])[0].cpu().numpy()).all()
+    with pytest.raises(AssertionError):
+        from connect4_b200.board import Board
+        bad(Board())
+    for engine in ("fused", "lockstep"):
+        monkeypatch.setenv("C4_ENGINE", engine)
+        pool = SelfPlayPool(bad, MCTSConfig(24, 19652, 1.25, 0.3, 0.25, 6), concurrent_games=8, seed=1)
+        with pytest.raises(C4Error, match="non-finite"):
+            pool.generate_records(8)
+        pool.engine.close()
+        eng = Engine(8, MCTSConfig(24))
+        eng.set_net(bad)
+        eng.begin(c0[:8], c1[:8])
+        with pytest.raises(C4Error, match="non-finite"):
+            eng.run("net")
+        eng.close()
+
+
+def test_nan_weights_fail_loudly():
+    """NaN in a head weight (invisible to the range calibration of the trunk): every answer is NaN -> error code"""
+    import torch
+    from connect4_b200._lib import C4Error
+    from connect4_b200.mcts import MCTSConfig
+    from connect4_b200.neural.game_pool import SelfPlayPool
+    from connect4_b200.neural.model import ModelWrapper
+    from oracle import net_ref as nr
+    sd = {k: torch.as_tensor(np.array(v)).clone() for k, v in nr.load_golden_state(os.path.join(GOLDEN, "example_net_state.npz")).items()}
+    sd["policy_head.fc1.weight"][3, 5] = float("nan")
+    bad = ModelWrapper(state_dict=sd)
+    pool = SelfPlayPool(bad, MCTSConfig(16, 19652, 1.25, 0.3, 0.25, 6), concurrent_games=4, seed=1)
+    with pytest.raises(C4Error, match="non-finite"):
+        pool.generate_records(4)
+    pool.engine.close()
+    sd["body.0.0.weight"][0, 0, 0, 0] = float("nan")                 # NaN in the trunk: refused at creation
+    with pytest.raises(C4Error):
+        ModelWrapper(state_dict=sd)

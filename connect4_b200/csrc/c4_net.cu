@@ -848,6 +848,7 @@ extern "C" double c4_net_get(const c4_net *net, int key)
 }
 unsigned long long c4_net_uid(const c4_net *net) { return net ? net->uid : 0ULL; }   // internal (not part of the C ABI)
 int c4_net_filters(const c4_net *net) { return net ? net->F : 0; }                  // internal
+int c4_net_device(const c4_net *net) { return net ? net->device : -1; }             // internal
 
 extern "C" int c4_net_forward(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count,
                               float *out, void *stream)
@@ -863,6 +864,7 @@ int c4_net_forward_ex(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64
     C4_REQUIRE(n >= 0 && n < (1LL << 31), "c4_net_forward: n out of range");
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
+    C4_CUDA(cudaSetDevice(net->device));
     if (net->use_tc) {
         int grid = (int)std::min<int64_t>(std::max(1, std::min(max_ctas, 148)), n);
         auto k = net->F == 32 ? (net->fp16 ? k_net_tc<OpFP16, 32> : k_net_tc<OpBF16, 32>)

@@ -600,6 +600,7 @@ extern "C" int c4_ctx_get(c4_ctx *ctx, int key)
 extern "C" int c4_ctx_set_net(c4_ctx *ctx, c4_net *net)
 {
     C4_REQUIRE(ctx, "c4_ctx_set_net: null context");
+    C4_REQUIRE(!net || c4_net_device(net) == ctx->device, "c4_ctx_set_net: the network lives on another CUDA device than the context");
     C4_CUDA(cudaSetDevice(ctx->device));
     if (ctx->memo_log2 > 0) {
         // the memo caches THIS network's outputs: (re)start empty whenever the evaluator changes
@@ -898,6 +899,9 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
     C4_REQUIRE(eval_kind == C4_EVAL_CENTRE || eval_kind == C4_EVAL_NET, "c4_selfplay_run: eval_kind must be CENTRE or NET");
     C4_REQUIRE(eval_kind != C4_EVAL_NET || ctx->net, "c4_selfplay_run: no network attached (c4_ctx_set_net)");
     C4_REQUIRE(n_games >= 0 && max_records >= 0, "c4_selfplay_run: negative size");
+    C4_REQUIRE(ctx->d.rng_mode != C4_RNG_NONE || (!ctx->d.noise_on && ctx->d.n_sampling <= 0),
+               "c4_selfplay_run: the config asks for root noise or sampled moves but no RNG is set (c4_ctx_set_rng): every "
+               "slot would play the same game");
     cudaStream_t s = (cudaStream_t)stream;
     C4_CUDA(cudaSetDevice(ctx->device));
     C4Dev &d = ctx->d;
@@ -1020,6 +1024,8 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     C4_REQUIRE(eval_kind == C4_EVAL_CENTRE || eval_kind == C4_EVAL_NET, "c4_selfplay_stream: eval_kind must be CENTRE or NET");
     C4_REQUIRE(eval_kind != C4_EVAL_NET || ctx->net, "c4_selfplay_stream: no network attached (c4_ctx_set_net)");
     C4_REQUIRE(stop_games > 0 || max_ms > 0.0, "c4_selfplay_stream: needs a game count or a time limit");
+    C4_REQUIRE(ctx->d.rng_mode != C4_RNG_NONE || (!ctx->d.noise_on && ctx->d.n_sampling <= 0),
+               "c4_selfplay_stream: the config asks for root noise or sampled moves but no RNG is set (c4_ctx_set_rng)");
     cudaStream_t s = (cudaStream_t)stream;
     C4_CUDA(cudaSetDevice(ctx->device));
     C4Dev &d = ctx->d;

@@ -8,6 +8,7 @@
 
 unsigned long long c4_net_uid(const c4_net *net);     // c4_net.cu (internal)
 int c4_net_filters(const c4_net *net);
+int c4_net_device(const c4_net *net);
 
 enum { ST_IDLE = 0, ST_READY = 1, ST_WAIT = 2, ST_DONE = 3, ST_NEWROOT = 4 };
 #define PATH_CAP 48

@@ -9,6 +9,8 @@ Evaluator dispatch (see evaluators.Evaluator.device_kind):
 """
 from typing import Callable, List, Tuple
 
+import collections
+
 import numpy as np
 
 from .board import Board
@@ -29,23 +31,39 @@ class MCTSConfig():
         self.num_sampling_moves = num_sampling_moves
 
 
-_ENGINES = {}
+_ENGINES = collections.OrderedDict()          # (capacity, simulations, device, network tag) -> Engine, LRU first
+_MAX_ENGINES = 4
 
 
 def _engine(config, n, tag=None):
-    """engines are cached per (capacity, simulations, network): creating one allocates the node pool, and a context
-    keeps the evaluation memo of the network it last ran"""
+    """Engines are cached per (capacity, simulations, CUDA device, network): creating one allocates the node pool and the
+    evaluation memo, and two networks that alternate (a Match of a new against an old network, the reference's `_match`,
+    neural/training.py:176-207) each keep their memo.  The cache is a small LRU: an evicted engine is closed at once (node
+    pool and memo returned to the device), so a training loop that brings a new network every generation holds at most
+    _MAX_ENGINES contexts, and no cached engine keeps a reference to a network (`tag` is only a number; c4_ctx_set_net
+    compares the network's unique id and empties the memo if a recycled tag ever meets another network)."""
+    import torch
+    from . import _lib
     from .engine import Engine
+    _lib.require_gpu()                        # no CPU fallback: fail here, before anything touches the CUDA runtime
     cap = 1
     while cap < n:
         cap *= 2
-    key = (cap, int(config.simulations), tag)
-    eng = _ENGINES.get(key)
+    key = (cap, int(config.simulations), torch.cuda.current_device(), tag)
+    eng = _ENGINES.pop(key, None)
     if eng is None:
+        while len(_ENGINES) >= _MAX_ENGINES:
+            _ENGINES.popitem(last=False)[1].close()
         eng = Engine(cap, config)
-        _ENGINES[key] = eng
+    _ENGINES[key] = eng                       # most recently used last
     eng.set_config(config)
     return eng
+
+
+def release_engines():
+    """close every cached engine (device memory of the node pools and evaluation memos)"""
+    while _ENGINES:
+        _ENGINES.popitem()[1].close()
 
 
 def _host_evaluator(evaluator):
@@ -86,7 +104,10 @@ def search_batch(config: MCTSConfig, boards: List[Board], evaluator, noise=None)
         eng.run("centre")
     elif kind == "net":
         eng.set_net(model)
-        eng.run("net")
+        try:
+            eng.run("net")
+        finally:
+            eng.net = None                        # the cache must not keep the caller's network alive
     else:
         eng.run_external(_host_evaluator(evaluator))
     return eng

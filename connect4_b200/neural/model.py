@@ -129,11 +129,12 @@ class ModelWrapper():
         """uint64 bitboards (numpy or CUDA int64 tensors) -> (values f32 [n], priors f32 [n,7]) CUDA tensors."""
         import torch
         from ..engine import _u64_tensor
-        t0, t1 = _u64_tensor(c0), _u64_tensor(c1)
+        t0, t1 = _u64_tensor(c0, self.device.index), _u64_tensor(c1, self.device.index)
         n = int(t0.numel())
-        out = torch.empty((n, 8), dtype=torch.float32, device="cuda")
-        _lib.check(_lib.load().c4_net_forward(self.c4_net, _lib.ptr(t0), _lib.ptr(t1), n, None, _lib.ptr(out),
-                                              _lib.stream_ptr()))
+        out = torch.empty((n, 8), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().c4_net_forward(self.c4_net, _lib.ptr(t0), _lib.ptr(t1), n, None, _lib.ptr(out),
+                                                  _lib.stream_ptr()))
         return out[:, 7].contiguous(), out[:, :7].contiguous()
 
     # ---- evaluation pass over a labelled set (model.py:180-198,307-342; TrainingLoop._evaluate, training.py:156-171)

@@ -26,6 +26,7 @@ _CLASS_MAP = {
     ("oinkoink.utils", "Side"): Side,
 }
 _LOCK = threading.Lock()
+_MISSING = object()
 
 
 class _ReferenceUnpickler(pickle.Unpickler):
@@ -49,11 +50,18 @@ class _ReferenceNamespace():
     def __enter__(self):
         self.fake = []
         self.cls = {}
+        self.saved = []                      # (module object, attribute, previous value or _MISSING)
+        before = set(sys.modules)
         try:
             for (mod, name) in _CLASS_MAP:
                 self.cls[(mod, name)] = getattr(importlib.import_module(mod), name)
             return self
         except Exception:
+            # a partly importable reference (e.g. its `anytree` dependency missing): drop what this attempt imported, so
+            # that no real module is left half-initialised, and fall back to stand-ins
+            for m in set(sys.modules) - before:
+                if m == "oinkoink" or m.startswith("oinkoink."):
+                    sys.modules.pop(m, None)
             self.cls = {}
         for (mod, name), ours in _CLASS_MAP.items():
             parts = mod.split(".")
@@ -68,11 +76,19 @@ class _ReferenceNamespace():
                 stub = ours.__bases__[0](name, {k: v.value for k, v in ours.__members__.items()}, module=mod)
             else:
                 stub = type(name, (object,), {"__module__": mod, "__qualname__": name})
-            setattr(sys.modules[mod], name, stub)
+            target = sys.modules[mod]
+            self.saved.append((target, name, getattr(target, name, _MISSING)))     # a real module loaded earlier keeps its
+            setattr(target, name, stub)                                             # own class after __exit__
             self.cls[(mod, name)] = stub
         return self
 
     def __exit__(self, *a):
+        for target, name, prev in reversed(self.saved):
+            if prev is _MISSING:
+                if hasattr(target, name):
+                    delattr(target, name)
+            else:
+                setattr(target, name, prev)
         for m in reversed(self.fake):
             sys.modules.pop(m, None)
 

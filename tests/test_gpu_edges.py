@@ -166,3 +166,34 @@ def test_full_size_generation_properties():
         parts.append(q.generate_records(2048, game_id_base=r, game_id_stride=2))
         q.engine.close()
     _same_records(rec, _sorted(np.concatenate(parts)))
+
+
+def test_selfplay_without_rng_is_refused_when_the_config_needs_one():
+    """a config with root noise / sampled moves and no RNG would make every slot play the same game: refused"""
+    from connect4_b200._lib import C4Error
+    from connect4_b200.engine import Engine
+    from connect4_b200.mcts import MCTSConfig
+    eng = Engine(4, MCTSConfig(8, 19652, 1.25, 0.3, 0.25, 6))
+    with pytest.raises(C4Error, match="RNG"):
+        eng.selfplay(2, "centre")
+    eng.set_rng("philox", seed=1)
+    assert len(eng.selfplay(2, "centre")) >= 14
+    eng.close()
+
+
+def test_search_engine_cache_is_bounded():
+    """mcts.search caches its device contexts in a small LRU and closes what it evicts (one leaked context per
+    network / configuration)"""
+    from connect4_b200 import mcts
+    from connect4_b200.board import Board
+    from connect4_b200.evaluators import Evaluator, evaluate_centre_with_prior
+    mcts.release_engines()
+    closed = []
+    for sims in range(5, 5 + mcts._MAX_ENGINES + 3):
+        t = mcts.search(mcts.MCTSConfig(sims), Board(), Evaluator(evaluate_centre_with_prior))
+        assert t.root.data.search_value.visit_count == sims + 1
+        closed.append(len(mcts._ENGINES))
+    assert max(closed) == mcts._MAX_ENGINES
+    first = next(iter(mcts._ENGINES.values()))
+    mcts.release_engines()
+    assert not mcts._ENGINES and first.h is None

@@ -51,28 +51,27 @@ struct TcFz {
                          GROUPS = FZ_GROUPS, EPI_WARPS = 8 * FZ_GROUPS;
     static constexpr bool SLICED = false;
 };
-typedef TcKc<TcFz> FzK;
+typedef TcKc<TcFz> FzK32;
+// 64 filters (the reference's example_config network): the batch kernel's geometry as it is -- 6-board strips, one
+// 72 KB weight stage refilled slice by slice, 16 epilogue warps (4 lane quadrants x 4 channel slices)
+typedef TcKc<TcC<64>> FzK64;
 
 #define FZ_THREADS 1024
-#define FZ_EPI_WARPS (8 * FZ_GROUPS)
-#define FZ_NET_WARPS (FZ_EPI_WARPS + 2)                   // epilogue warps, producer, issuer
-#define FZ_TREE_WARPS (FZ_THREADS / 32 - FZ_NET_WARPS)
 // Warp ids = issue priority (the SM's arbiter prefers HIGH warp ids): the single-thread issuer and producer on top; then
 // the tree warps (their simulations are dependent chains -- every lost issue slot is latency of a game) and the epilogue
 // warps at the bottom (FZ_TREE_HIGH), or the other way round.
 #ifndef FZ_TREE_HIGH
 #define FZ_TREE_HIGH 1
 #endif
-#if FZ_TREE_HIGH
-#define FZ_EPI_WARP0 0
-#define FZ_TREE_WARP0 FZ_EPI_WARPS
-#else
-#define FZ_TREE_WARP0 0
-#define FZ_EPI_WARP0 FZ_TREE_WARPS
-#endif
-#define FZ_PRODUCER (FZ_THREADS / 32 - 2)
-#define FZ_ISSUER (FZ_THREADS / 32 - 1)
-#define FZ_EPI_BAR() asm volatile("bar.sync 1, %0;\n" :: "n"(32 * FZ_EPI_WARPS) : "memory")
+template <class K> struct FzW {
+    static constexpr int EPI_WARPS = K::EPI_WARPS;
+    static constexpr int TREE_WARPS = FZ_THREADS / 32 - 2 - EPI_WARPS;
+    static constexpr int EPI_WARP0 = FZ_TREE_HIGH ? 0 : TREE_WARPS;
+    static constexpr int TREE_WARP0 = FZ_TREE_HIGH ? EPI_WARPS : 0;
+    static constexpr int PRODUCER = FZ_THREADS / 32 - 2, ISSUER = FZ_THREADS / 32 - 1;
+    static constexpr int BOARDS_PER_WARP = (K::NB + EPI_WARPS - 1) / EPI_WARPS;
+};
+#define FZ_EPI_BAR() asm volatile("bar.sync 1, %0;\n" :: "n"(32 * W::EPI_WARPS) : "memory")
 #define FZ_GC_MAX 128                                     // game slots per CTA
 #define FZ_QCAP 128                                       // leaf ring entries (>= FZ_GC_MAX: one pending leaf per game)
 #define FZ_WATCHDOG_CYCLES 6000000000LL                   // ~3 s without a runnable game while games wait = protocol bug
@@ -86,7 +85,7 @@ struct FzParams {
     const int *host_abort;              // mapped host word: non-zero = the host gave up waiting, leave at once
     int *dbg;                           // [CTA][32 warps] last checkpoint of every warp (host-side hang diagnosis), or null
     unsigned long long *prof;           // [16] cycle / event sums of CTA 0 (C4_FZ_DEBUG), or null
-    int tree_warps;                     // tree warps that work (<= FZ_TREE_WARPS; tuning knob C4_FZ_TREE_WARPS)
+    int tree_warps;                     // tree warps that work (tuning knob C4_FZ_TREE_WARPS)
 };
 
 struct FzCtl {
@@ -106,9 +105,9 @@ struct FzCtl {
 #define FZ_PROF(i, v) do { if (P.prof && blockIdx.x == 0 && lane == 0) atomicAdd(&P.prof[i], (unsigned long long)(v)); } while (0)
 #define FZ_DBG(code) do { if (P.dbg && lane == 0) *reinterpret_cast<volatile int *>(&P.dbg[blockIdx.x * 32 + warp]) = (code); } while (0)
 
-__host__ __device__ static constexpr int fz_ctl_off(int R) { return (FzK::total(R) + 15) & ~15; }
-__host__ __device__ static constexpr int fz_tab_off(int R) { return (fz_ctl_off(R) + (int)sizeof(FzCtl) + 15) & ~15; }
-__host__ __device__ static constexpr int fz_total(int R, int table_entries) { return fz_tab_off(R) + 3 * 8 * table_entries; }
+template <class K> __host__ __device__ constexpr int fz_ctl_off(int R) { return (K::total(R) + 15) & ~15; }
+template <class K> __host__ __device__ constexpr int fz_tab_off(int R) { return (fz_ctl_off<K>(R) + (int)sizeof(FzCtl) + 15) & ~15; }
+template <class K> __host__ __device__ constexpr int fz_total(int R, int table_entries) { return fz_tab_off<K>(R) + 3 * 8 * table_entries; }
 
 __device__ __forceinline__ unsigned long long fz_globaltimer()
 {
@@ -249,12 +248,12 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, FzCtl *S, int g, int
     __syncwarp();
 }
 
-template <typename OP, bool SELFPLAY>
+template <typename OP, class K, bool SELFPLAY>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams P)
 {
-    using K = FzK;
-    constexpr int F = 32;
+    using W = FzW<K>;
+    constexpr int F = K::F;
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = 1 + 2 * R;
     const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -272,8 +271,8 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
     const uint32_t b_accfull = b_wempty + 8 * K::WBARS, b_accempty = b_accfull + 8 * K::ACC_SLOTS;
     const uint32_t b_epi = b_accempty + 8 * K::ACC_SLOTS;                   // T barriers
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * K::WBARS + 2 * K::ACC_SLOTS + K::T);
-    FzCtl *S = reinterpret_cast<FzCtl *>(smem + fz_ctl_off(R));
-    double *tab = reinterpret_cast<double *>(smem + fz_tab_off(R));
+    FzCtl *S = reinterpret_cast<FzCtl *>(smem + fz_ctl_off<K>(R));
+    double *tab = reinterpret_cast<double *>(smem + fz_tab_off<K>(R));
 
     // ---- one-time setup
     for (int i = threadIdx.x; i < 2 * K::ACT_BYTES / 16; i += blockDim.x)
@@ -294,7 +293,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
         for (int i = 0; i < K::T; i++) mbar_init(b_epi + 8 * i, K::GROUP_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (warp == FZ_PRODUCER) {
+    if (warp == W::PRODUCER) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -307,11 +306,37 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
     const uint32_t tmem = *tmem_slot;
     const unsigned long long t_begin = fz_globaltimer();
 
-    if (warp == FZ_PRODUCER) {
+    if (warp == W::PRODUCER) {
         // ================= weight producer: layer g of the endless (strip, layer) sequence -> ring stage g % WSTAGES.
         // It runs up to WSTAGES layers ahead of the issuer, i.e. the first layers of the NEXT strip are already on chip
         // while the tower idles.
-        if (lane == 0) {
+        if (lane == 0 && K::SLICED) {
+            // one weight stage, refilled one dy slice at a time: slice dy of layer g is requested as soon as the issuer has
+            // released slice dy of layer g - 1 (c4_net.cu)
+            int g = 0, last[3] = {-1, -1, -1};
+            bool live = true;
+            for (; live; g++) {
+                FZ_DBG(0x100000 | g);
+                for (int dy = 0; dy < 3 && live; dy++) {
+                    if (g > 0) {
+                        const uint32_t bar = b_wempty + 8 * dy, par = (uint32_t)(g - 1) & 1u;
+                        for (uint32_t it = 0; !mbar_try(bar, par); it++) {
+                            if (it > 4u) __nanosleep(it > 64u ? 500 : 100);
+                            if ((it & 15u) == 15u && (ld_vol(&S->quit) || ld_vol(&S->abort))) { live = false; break; }
+                        }
+                        if (!live) break;
+                    }
+                    mbar_expect_tx(b_wfull + 8 * dy, K::WSLICE_BYTES);
+                    bulk_g2s(smem_u32(sW + dy * K::WSLICE_BYTES), image + (size_t)(g % L) * K::WSTAGE_BYTES + dy * K::WSLICE_BYTES,
+                             K::WSLICE_BYTES, b_wfull + 8 * dy);
+                    last[dy] = g;
+                }
+            }
+            FZ_DBG(0x1f0000 | g);
+            for (int dy = 0; dy < 3; dy++)                                        // no bulk copy in flight at exit
+                if (last[dy] >= 0) mbar_wait(b_wfull + 8 * dy, (uint32_t)last[dy] & 1u);
+            FZ_DBG(0x1ff000);
+        } else if (lane == 0) {
             int g = 0;
             bool live = true;
             for (; live; g++) {
@@ -334,7 +359,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
             for (int i = max(0, g - K::WSTAGES); i < g; i++) mbar_wait(b_wfull + 8 * (i % K::WSTAGES), (uint32_t)(i / K::WSTAGES) & 1u);
             FZ_DBG(0x1ff000);
         }
-    } else if (warp == FZ_ISSUER) {
+    } else if (warp == W::ISSUER) {
         // ================= MMA issuer (one thread): the strip loop of k_net_tc with strips that arrive at run time
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)OP::FMT << 7) | ((uint32_t)OP::FMT << 10) |
@@ -351,7 +376,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
                 for (int l = 0; l < L && live; l++, g++) {
                     const int st = g % K::WSTAGES;
                     FZ_DBG(0x210000 | ((s & 0xff) << 8) | l);
-                    if (!fz_wait(b_wfull + 8 * st, (uint32_t)(g / K::WSTAGES) & 1u, &S->abort)) { live = false; break; }
+                    if (!K::SLICED && !fz_wait(b_wfull + 8 * st, (uint32_t)(g / K::WSTAGES) & 1u, &S->abort)) { live = false; break; }
                     const uint32_t wbase = smem_u32(sW + st * K::WSTAGE_BYTES);
                     const uint32_t abase = smem_u32((l == 0 || (l & 1) == 0) ? sH : sX);   // stem and conv2 read H
                     const uint64_t a_l = umma_desc(abase, K::ROWS * 16, 128);
@@ -370,22 +395,27 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
                         if (l != 0) {
 #pragma unroll
                             for (int dy = 0; dy < 3; dy++) {
+                                if (K::SLICED && t == 0 && !fz_wait(b_wfull + 8 * dy, (uint32_t)g & 1u, &S->abort)) { live = false; break; }
 #pragma unroll
                                 for (int ks = 0; ks < K::KC / 2; ks++) {
                                     const uint64_t aa = a + 8 * dy + 2 * K::ROWS * ks, bb = b_l + (dy * K::KC + 2 * ks) * K::NN;
                                     if (dy == 0 && ks == 0) umma_f16c<0>(dcol, aa, bb, idesc); else umma_f16c<1>(dcol, aa, bb, idesc);
                                 }
+                                if (K::SLICED && t == T - 1) umma_commit(b_wempty + 8 * dy);  // slice free for the next layer
                             }
                         } else {                                              // stem: 16 (padded) input channels = one k-step
 #pragma unroll
                             for (int dy = 0; dy < 3; dy++) {
+                                if (K::SLICED && t == 0 && !fz_wait(b_wfull + 8 * dy, (uint32_t)g & 1u, &S->abort)) { live = false; break; }
                                 const uint64_t aa = a + 8 * dy, bb = b_l + dy * K::STEM_KC * K::NN;
                                 if (dy == 0) umma_f16c<0>(dcol, aa, bb, idesc); else umma_f16c<1>(dcol, aa, bb, idesc);
+                                if (K::SLICED && t == T - 1) umma_commit(b_wempty + 8 * dy);
                             }
                         }
+                        if (!live) break;
                         umma_commit(b_accfull + 8 * slot);
                     }
-                    if (live) umma_commit(b_wempty + 8 * st);
+                    if (live && !K::SLICED) umma_commit(b_wempty + 8 * st);
                 }
                 // observe the LAST epilogue phase of tile 0 too: a parity wait only tells "not the phase in progress", so
                 // with a one-tile strip the wait for the next strip's input phase (same parity as this strip's phase L - 1)
@@ -394,10 +424,10 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
             }
             FZ_DBG(0x2ff000);
         }
-    } else if (warp >= FZ_EPI_WARP0 && warp < FZ_EPI_WARP0 + FZ_EPI_WARPS) {
+    } else if (warp >= W::EPI_WARP0 && warp < W::EPI_WARP0 + W::EPI_WARPS) {
         // ================= epilogue warps (+ the dispatcher in the first of them)
-        const int e = warp - FZ_EPI_WARP0, quad = warp & 3, half = (e >> 2) % K::SLICES, group = e / K::GROUP_WARPS;
-        const int et = threadIdx.x - 32 * FZ_EPI_WARP0;                      // 0..511
+        const int e = warp - W::EPI_WARP0, quad = warp & 3, half = (e >> 2) % K::SLICES, group = e / K::GROUP_WARPS;
+        const int et = threadIdx.x - 32 * W::EPI_WARP0;                      // 0..511
         EpiCtx E;
         E.b_accfull = b_accfull; E.b_accempty = b_accempty; E.b_epi = b_epi;
         E.tmem_acc = tmem + ((uint32_t)(quad * 32) << 16) + K::ACC_COL0 + TC_CH * half;
@@ -450,9 +480,9 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
             const int nb = ld_vol(&S->strip_nb);
             // (one board per epilogue warp at most: the dispatcher overwrites strip_game for the next strip while other
             //  warps are still in their head tails, so the game of THIS warp's board is read now)
-            int my_gl[(K::NB + FZ_EPI_WARPS - 1) / FZ_EPI_WARPS];
+            int my_gl[W::BOARDS_PER_WARP];
 #pragma unroll
-            for (int i = 0; i < (K::NB + FZ_EPI_WARPS - 1) / FZ_EPI_WARPS; i++) my_gl[i] = S->strip_game[(e + i * FZ_EPI_WARPS) & 15];
+            for (int i = 0; i < W::BOARDS_PER_WARP; i++) my_gl[i] = S->strip_game[(e + i * W::EPI_WARPS) & 15];
             const long long t_d1 = clock64();
             FZ_DBG(0x310000 | nb);
             if (nb == 0) {                                                   // quit: wake the issuer so it reads strip_nb == 0
@@ -467,7 +497,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
                 if (E.col8 != 0 && rb - 7 * b != 0 && b < nb) E.valid_mask |= 1u << t;
             }
             // ---- input planes (Board.to_array) -> channels 0..15 of H
-            for (int i = et; i < nb * 42; i += 32 * FZ_EPI_WARPS) {
+            for (int i = et; i < nb * 42; i += 32 * W::EPI_WARPS) {
                 const int b = i / 42, px = i - b * 42, r = px / 7, col = px - r * 7;
                 const u64 a0 = S->strip_c0[b], a1 = S->strip_c1[b];
                 const int bit = 7 * col + (5 - r);
@@ -498,8 +528,8 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
             FZ_EPI_BAR();
             const long long t_d3 = clock64();
 #pragma unroll
-            for (int bi = 0; bi < (K::NB + FZ_EPI_WARPS - 1) / FZ_EPI_WARPS; bi++) {
-                const int b = e + bi * FZ_EPI_WARPS;
+            for (int bi = 0; bi < W::BOARDS_PER_WARP; bi++) {
+                const int b = e + bi * W::EPI_WARPS;
                 if (b >= nb) break;
                 float *sc = scratch + b * 128;
                 for (int i = lane; i < 126; i += 32) {
@@ -532,7 +562,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
         // ================= tree warps
         C4Dev d = dg;
         if (P.table_entries) { d.pbc = tab; d.sqt = tab + P.table_entries; d.rcp = tab + 2 * P.table_entries; }
-        const int tw = warp - FZ_TREE_WARP0;
+        const int tw = warp - W::TREE_WARP0;
         int rot = (tw * 9) % Gc;
         bool idle = false;
         long long idle_t0 = 0;
@@ -592,11 +622,11 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
         }
         __syncwarp();
         FZ_DBG(0x4ff000);
-        if (lane == 0 && atomicAdd(&S->tree_exited, 1) == FZ_TREE_WARPS - 1) { __threadfence_block(); st_vol(&S->quit, 1); }
+        if (lane == 0 && atomicAdd(&S->tree_exited, 1) == W::TREE_WARPS - 1) { __threadfence_block(); st_vol(&S->quit, 1); }
     }
     TC_FENCE_BEFORE();
     __syncthreads();
-    if (warp == FZ_PRODUCER) {
+    if (warp == W::PRODUCER) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem) : "memory");
     }
@@ -606,13 +636,19 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
 // internal interface used by c4_search.cu
 bool c4_fused_eligible(const c4_net *net, int max_games, int simulations)
 {
-    if (!net || net->F != 32 || !net->use_tc || !net->image_tc) return false;
-    if (getenv("C4_ENGINE") && !strcmp(getenv("C4_ENGINE"), "lockstep")) return false;
+    if (!net || (net->F != 32 && net->F != 64) || !net->use_tc || !net->image_tc) return false;
+    const char *want = getenv("C4_ENGINE");                  // "fused" / "lockstep" force an engine, anything else = auto
+    if (want && !strcmp(want, "lockstep")) return false;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
     const int grid = std::min(sms, max_games);
-    if ((max_games + grid - 1) / grid > FZ_GC_MAX) return false;
-    return fz_total(net->R, 0) <= 227 * 1024;
+    const int per_cta = (max_games + grid - 1) / grid;
+    if (per_cta > FZ_GC_MAX) return false;
+    // auto: the fused engine up to 32 games per SM (4,736 on a B200).  Measured crossover (profiles/README.md): 2x the
+    // lock-step engine at 256 games, 1.3x at 1,024, level at 4,096; with 8,192 games and more the lock-step pass, which gives
+    // every phase the whole SM, is ahead (386k vs 315k positions/s)
+    if (!(want && !strcmp(want, "fused")) && per_cta > 32) return false;
+    return (net->F == 32 ? fz_total<FzK32>(net->R, 0) : fz_total<FzK64>(net->R, 0)) <= 227 * 1024;
 }
 
 // Run the pool until every game slot is idle / done, `stop_games` games have finished (counter in d.ctr) or `stop_ms`
@@ -643,18 +679,24 @@ int c4_fused_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     P.n_slots = max_games;
     // PUCT tables in shared memory: off by default -- without them the CTA fits the 164 KB shared-memory configuration and
     // the SM keeps 92 KB of L1 for the node records, which is worth more (profiles/README.md)
-    P.table_entries = (getenv("C4_FZ_SMEM_TABLES") && fz_total(net->R, simulations + 2) <= 227 * 1024) ? simulations + 2 : 0;
+    const bool f32 = net->F == 32;
+    auto total = [&](int entries) { return f32 ? fz_total<FzK32>(net->R, entries) : fz_total<FzK64>(net->R, entries); };
+    P.table_entries = (getenv("C4_FZ_SMEM_TABLES") && total(simulations + 2) <= 227 * 1024) ? simulations + 2 : 0;
     P.stop_games = stop_games;
     P.stop_ns = stop_ms > 0.0 ? (unsigned long long)(stop_ms * 1e6) : 0ULL;
     P.host_abort = d_abort;
     P.dbg = dbg;
     P.prof = prof;
-    P.tree_warps = getenv("C4_FZ_TREE_WARPS") ? std::max(1, std::min(FZ_TREE_WARPS, atoi(getenv("C4_FZ_TREE_WARPS")))) : FZ_TREE_WARPS;
+    const int tree_warps = f32 ? FzW<FzK32>::TREE_WARPS : FzW<FzK64>::TREE_WARPS;
+    P.tree_warps = getenv("C4_FZ_TREE_WARPS") ? std::max(1, std::min(tree_warps, atoi(getenv("C4_FZ_TREE_WARPS")))) : tree_warps;
     if (prof) C4_CUDA(cudaMemsetAsync(prof, 0, 16 * sizeof(unsigned long long), stream));
-    const int smem = fz_total(net->R, P.table_entries);
+    const int smem = total(P.table_entries);
     const int grid = std::min(sms, max_games);
-    auto k = selfplay ? (net->fp16 ? k_fused<OpFP16, true> : k_fused<OpBF16, true>)
-                      : (net->fp16 ? k_fused<OpFP16, false> : k_fused<OpBF16, false>);
+    void (*k)(const C4Dev, const unsigned char *, int, FzParams);
+    if (f32) k = selfplay ? (net->fp16 ? k_fused<OpFP16, FzK32, true> : k_fused<OpBF16, FzK32, true>)
+                          : (net->fp16 ? k_fused<OpFP16, FzK32, false> : k_fused<OpBF16, FzK32, false>);
+    else k = selfplay ? (net->fp16 ? k_fused<OpFP16, FzK64, true> : k_fused<OpBF16, FzK64, true>)
+                      : (net->fp16 ? k_fused<OpFP16, FzK64, false> : k_fused<OpBF16, FzK64, false>);
     C4_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<grid, FZ_THREADS, smem, stream>>>(d, (const unsigned char *)net->image_tc, net->R, P);
     C4_CUDA(cudaGetLastError());

@@ -45,3 +45,24 @@ def test_shard_and_allgather_world2():
     assert np.array_equal(a, b) and a.shape == (21, 64)
     assert sorted(set(a[:, 0].tolist())) == list(range(7))       # every game exactly once
     assert a[:12, 0].tolist() == [0, 0, 0, 2, 2, 2, 4, 4, 4, 6, 6, 6]  # rank order preserved
+
+
+def test_sort_records_device_orders_by_game_and_ply():
+    """the gathered generation is put in (game_id, ply) order where it lives (dist.sort_records_device): same order as the
+    host lexsort, whole 64-byte records moved"""
+    import numpy as np
+    import torch
+    from connect4_b200.dist import sort_records_device
+    from connect4_b200.engine import RECORD_DTYPE
+    rng = np.random.default_rng(3)
+    n = 5000
+    rec = np.zeros(n, dtype=RECORD_DTYPE)
+    pairs = rng.permutation(np.array([(g, p) for g in range(250) for p in range(20)]))
+    rec["game_id"], rec["ply"] = pairs[:, 0], pairs[:, 1]
+    rec["c0"] = rng.integers(0, 1 << 49, n)
+    raw = torch.as_tensor(rec.view(np.uint8).reshape(n, 64).copy())
+    out = sort_records_device(raw).numpy().view(RECORD_DTYPE).reshape(-1)
+    ref = rec[np.lexsort((rec["ply"], rec["game_id"]))]
+    for f in ("game_id", "ply", "c0"):
+        assert (out[f] == ref[f]).all()
+    assert sort_records_device(raw[:0]).shape == (0, 64)

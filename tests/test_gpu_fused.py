@@ -146,3 +146,18 @@ def test_fused_games_equal_reference_games_with_injected_randomness(monkeypatch)
             assert o.legal_mask(c0, c1) >> int(r["move"]) & 1
             c0, c1, res = o.drop(c0, c1, int(r["move"]))
         assert res != -1 and res == int(recs[-1]["result"]) and int(recs[0]["n_moves"]) == len(recs)
+
+
+@pytest.mark.parametrize("slots,sims,n", [(6, 16, 10), (150, 32, 300)])
+def test_fused_engine_with_the_64_filter_network(monkeypatch, slots, sims, n):
+    """the reference's example_config network (64 filters / 6 residual blocks / 6 fc layers, oinkoink/data/example_config.py)
+    runs on the fused engine with the 64-filter tower geometry (6-board strips, weight stage refilled slice by slice)"""
+    import torch
+    from connect4_b200.neural.config import ModelConfig, NetConfig
+    from connect4_b200.neural.model import ModelWrapper
+    torch.manual_seed(0)
+    model = ModelWrapper(ModelConfig(net_config=NetConfig(filters=64, n_fc_layers=6, n_residuals=6)))
+    a = _generate(monkeypatch, "fused", model, _cfg(sims), slots, n)
+    b = _generate(monkeypatch, "lockstep", model, _cfg(sims), slots, n)
+    assert sorted(set(a["game_id"].tolist())) == list(range(n))
+    _same(a, b)

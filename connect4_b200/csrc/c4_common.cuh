@@ -28,6 +28,24 @@ void c4_set_error(const std::string &msg);
         }                                                                                              \
     } while (0)
 
+// ---------------------------------------------------------------- device-side checks
+// compute-sanitizer is closed on the GPU pool this was developed on, so the index arithmetic of the engines carries its
+// own bounds checks: a build with -DC4_CHECKED (tools/build_variant.sh checked -DC4_CHECKED) traps with file:line when one
+// fails; the product build compiles them away.  tools/sanitize_case.py is the workload they are run on.
+#ifdef C4_CHECKED
+#include <stdio.h>
+#define C4_DEV_ASSERT(cond)                                                                                         \
+    do {                                                                                                            \
+        if (!(cond)) {                                                                                              \
+            printf("C4_DEV_ASSERT failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                               \
+            __trap();                                                                                               \
+        }                                                                                                           \
+    } while (0)
+#else
+#define C4_DEV_ASSERT(cond) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------- bitboard constants (oinkoink/board.py:9-32)
 #define C4_W 7
 #define C4_H 6

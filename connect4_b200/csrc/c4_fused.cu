@@ -24,6 +24,21 @@
 //     needs 200 KB, which leaves only ~28 KB of L1 for the node records (DESIGN.md discusses the trade).
 // Every inter-warp hand-off is CTA-local (shared-memory words + mbarriers), bounded by a watchdog that makes the call
 // fail with an error code instead of hanging the device.
+//
+// Lock-free hand-offs, all inside one CTA (what a race checker would flag, and why each is safe):
+//   * status[gl]: claimed by a tree warp with atomicCAS (READY / ANSWERED / NEWROOT -> RUNNING); written back by the
+//     owner only (RUNNING -> WAIT / READY / IDLE / DONE) after a __threadfence_block(); flipped WAIT -> ANSWERED by the one
+//     epilogue warp that holds the game's board, after the answer is in ans[gl] and a fence.  WAIT is published BEFORE the
+//     leaf enters the ring, so an answer can never be overwritten by a late WAIT.
+//   * leaf ring: slot reserved with atomicAdd(q_tail); entry written; fence; q_seq[idx] = slot + 1.  The dispatcher reads
+//     q_seq with volatile loads and takes only the leading run of complete entries.  Capacity >= games per CTA and a game has
+//     at most one leaf pending, so a slot is never reused before it was consumed (C4_DEV_ASSERT in fz_run_game).
+//   * strip_*: written by the dispatcher before the epilogue warps' named barrier, read after it; each warp copies the game
+//     of its board into a register at once, because the dispatcher refills strip_game for the next strip while other warps
+//     are still in their head tails.
+//   * stop / quit / abort: monotone 0 -> 1 flags, volatile stores and loads; seeing one late costs one more simulation or
+//     poll, never a result.
+//   * the evaluation memo in HBM is shared by all CTAs: see memo_insert in c4_tree.cuh (checksummed entries).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -142,10 +157,12 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, FzCtl *S, int g, int
     G.c0 = d.root_c0[g]; G.c1 = d.root_c1[g];
     G.age = c4_age(G.c0, G.c1);
 
+    C4_DEV_ASSERT(gl >= 0 && gl < FZ_GC_MAX && G.n_blocks >= 1 && G.n_blocks <= d.blocks_per_game && G.sims_done <= d.sims);
     if (st == FZ_ANSWERED) {
         // consume the evaluator's answer for the pending leaf (oinkoink/mcts.py:129-135), then backpropagate
         const uint32_t node = (uint32_t)d.pending_node[g];
         const int plen = d.path_len[g];
+        C4_DEV_ASSERT(plen >= 0 && plen <= PATH_CAP && node < (uint32_t)G.n_blocks * C4_SLOTS);
         const u64 lc0 = d.pend_c0[g], lc1 = d.pend_c1[g];
         const bool is_root = (plen == 0);
         const float ov = (lane < 8) ? S->ans[gl][lane] : 0.f;
@@ -240,6 +257,7 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, FzCtl *S, int g, int
             S->t_push[gl] = clock64();
             const unsigned slot = atomicAdd(&S->q_tail, 1u);
             const unsigned idx = slot % FZ_QCAP;
+            C4_DEV_ASSERT(slot - *reinterpret_cast<volatile unsigned *>(&S->q_head) < FZ_QCAP);   // one pending leaf per game
             S->q_c0[idx] = rc0; S->q_c1[idx] = rc1; S->q_game[idx] = gl;
             __threadfence_block();
             *reinterpret_cast<volatile unsigned *>(&S->q_seq[idx]) = slot + 1u;
@@ -541,6 +559,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
                 }
                 __syncwarp();
                 const int gl = my_gl[bi];
+                C4_DEV_ASSERT(gl >= 0 && gl < Gc && ld_vol(&S->status[gl]) == ST_WAIT);
                 float *ans = S->ans[gl];
                 head_tail(sc, hp, ans, lane);
                 const float o = (lane < 8) ? ans[lane] : 0.f;

@@ -183,7 +183,10 @@ __device__ __forceinline__ uint32_t memo_payload_digest(uint32_t w, int lane)
     for (int off = 4; off >= 1; off >>= 1) x ^= __shfl_xor_sync(FULL, x, off);
     return __shfl_sync(FULL, x, 0);
 }
-// store {c0, c1, out[8]} (lane l < 8 holds out[l]); one coalesced 64-byte store
+// store {c0, c1, out[8]} (lane l < 8 holds out[l]); one coalesced 64-byte store.
+// INTENTIONAL RACE (1 of 3 in the lock-step engine): warps of different games may write the same slot at the same time, and a
+// reader may see a half-written entry.  No lock: the 64-bit checksum over key AND payload turns every torn or mixed entry
+// into a miss, and two writers of the same key write identical bytes.
 __device__ __forceinline__ void memo_insert(const C4Dev &d, u64 c0, u64 c1, float out_lane, int lane)
 {
     const uint32_t w = __float_as_uint(out_lane);
@@ -268,6 +271,7 @@ __device__ __forceinline__ void apply_eval(const C4Dev &d, Game &G, uint32_t nod
         }
     }
     const uint32_t blk = (uint32_t)G.n_blocks;
+    C4_DEV_ASSERT((int)blk < d.blocks_per_game && node < blk * C4_SLOTS);
     G.n_blocks++;
     C4Node *slot = G.gp + (size_t)blk * C4_SLOTS + lane;
     if (lane < 7) {
@@ -342,6 +346,7 @@ __device__ __forceinline__ Leaf descend(const C4Dev &d, const Game &G)
     uint32_t visits = ra.visits, meta = ra.meta;
     while (!(meta & C4_META_TERMINAL) && visits > 0u) {
         const uint32_t blk = c4_meta_child_block(meta);
+        C4_DEV_ASSERT(blk > 0u && (int)blk < G.n_blocks && L.depth < PATH_CAP - 1);
         const C4Node *cn = G.gp + (size_t)blk * C4_SLOTS + (lane & 7);
         C4NodeA a = ld_a(cn);
         C4NodeB b = ld_b(cn);
@@ -377,6 +382,7 @@ __device__ __forceinline__ Leaf descend(const C4Dev &d, const Game &G)
         const uint32_t mlo = __reduce_max_sync(FULL, cand ? lo : 0u);
         const unsigned win = __ballot_sync(FULL, cand && lo == mlo);
         const int col = 31 - __clz((int)win);
+        C4_DEV_ASSERT(win != 0u && col < 7);
         visits = __shfl_sync(FULL, a.visits, col);
         meta = __shfl_sync(FULL, a.meta, col);
         // replay the move on the register-resident board
@@ -457,7 +463,12 @@ __device__ __forceinline__ void emit_request(const C4Dev &d, Game &G, int pool, 
 {
     int slot = 0;
     if (G.lane == 0) {
+        // INTENTIONAL RACES (2 and 3 of 3 in the lock-step engine): the leaf counter is bumped with an atomic while the
+        // network kernel of the PREVIOUS pass may still read its ping-pong twin (two counters per pool, reset one pass late),
+        // and the stop flag is a plain store polled with plain loads: a warp that sees it one simulation late only plays
+        // one more simulation of its own game -- pass length never changes results (tests/test_gpu_edges.py)
         const int k = atomicAdd(&d.ctr->leaf_count[pool][parity], 1);               // a pool's batch lives at [g0, g0 + n)
+        C4_DEV_ASSERT(k >= 0 && g0 + k < g0 + (1 << 20));
         if (stop_count > 0 && k + 1 == stop_count) d.ctr->stop_flag[pool][parity] = 1;
         slot = g0 + k;
     }
@@ -485,6 +496,7 @@ __device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
     child_values(a, exists, side, v_side, v_abs);
     double pol = normalise_policy(lane < 7 ? v_side : 0.0, exists);
     int ply = d.ply[G.g];
+    C4_DEV_ASSERT(ply >= 0 && ply < MAX_PLY && exists == (lane < 7 && ((c4_legal_mask(G.c0, G.c1) >> lane) & 1)));
     int mv;
     if (G.age < d.n_sampling && d.rng_mode != C4_RNG_NONE) {
         double u;
@@ -512,6 +524,7 @@ __device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
         rec->move = (int8_t)mv; rec->ply = (int8_t)ply; rec->n_moves = 0; rec->result = C4_RES_NONE; rec->reserved = 0;
         d.stat_positions[G.g] += 1ULL;
     }
+    C4_DEV_ASSERT(mv >= 0 && mv < 7 && ((c4_legal_mask(G.c0, G.c1) >> mv) & 1));
     int res = c4_drop(G.c0, G.c1, G.age, mv);
     G.age++;
     ply++;

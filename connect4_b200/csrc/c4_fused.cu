@@ -39,6 +39,12 @@
 //   * stop / quit / abort: monotone 0 -> 1 flags, volatile stores and loads; seeing one late costs one more simulation or
 //     poll, never a result.
 //   * the evaluation memo in HBM is shared by all CTAs: see memo_insert in c4_tree.cuh (checksummed entries).
+//
+// Not in this engine: the de-duplication of evaluations in flight (PENDING tags in the memo, c4_tree.cuh) that the lock-step
+// engine uses.  It was built here too (a parked game re-probes the memo with exponential back-off) and removed 27 % of the
+// network evaluations of the benchmark generation, but the re-probing tree warps slowed the tower on the same SM by more
+// than the saved evaluations were worth (252k vs 265k positions/s in the same build, profiles/README.md); a PENDING tag
+// written by the other engine simply reads as a miss here.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -663,10 +669,11 @@ bool c4_fused_eligible(const c4_net *net, int max_games, int simulations)
     const int grid = std::min(sms, max_games);
     const int per_cta = (max_games + grid - 1) / grid;
     if (per_cta > FZ_GC_MAX) return false;
-    // auto: the fused engine up to 32 games per SM (4,736 on a B200).  Measured crossover (profiles/README.md): 2x the
-    // lock-step engine at 256 games, 1.3x at 1,024, level at 4,096; with 8,192 games and more the lock-step pass, which gives
-    // every phase the whole SM, is ahead (386k vs 315k positions/s)
-    if (!(want && !strcmp(want, "fused")) && per_cta > 32) return false;
+    // auto: the fused engine up to 16 games per SM (2,368 on a B200).  Measured crossover, cold generation, positions/s
+    // (profiles/README.md): 256 games 52k vs 23k (lock-step), 1,024 games 123k vs 96k, 2,048 games 189k vs 181k, 4,096 games
+    // 291k vs 318k, 8,192 games 315k vs 427k -- with many games per SM the lock-step pass, which gives every phase the
+    // whole SM and de-duplicates the evaluations in flight, is ahead
+    if (!(want && !strcmp(want, "fused")) && per_cta > 16) return false;
     return (net->F == 32 ? fz_total<FzK32>(net->R, 0) : fz_total<FzK64>(net->R, 0)) <= 227 * 1024;
 }
 

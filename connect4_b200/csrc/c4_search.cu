@@ -41,6 +41,22 @@ int c4_fused_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
                  unsigned long long stop_games, double stop_ms, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ the pass kernel
+// A game needs an evaluation that is not in the memo: park the leaf, then either append it to the pool's batch (ST_WAIT) or,
+// if another game claimed the same position a moment ago, wait for that game's answer (ST_WAITMEMO; c4_tree.cuh).
+template <int MODE>
+__device__ __forceinline__ int request_or_wait(const C4Dev &d, Game &G, int pool, int g0, int parity, int stop_count, u64 c0,
+                                               u64 c1, uint32_t node, int path_len, uint32_t path_lo, uint32_t path_hi,
+                                               int probe, u64 seen)
+{
+    save_pending(d, G, c0, c1, node, path_len, path_lo, path_hi);
+    if (MODE == C4_EVAL_NET && d.memo && d.memo_dedup && (probe == MEMO_PENDING || !memo_claim(d, c0, c1, seen, G.lane))) {
+        if (G.lane == 0) count_busy(d, pool, parity, stop_count);
+        return ST_WAITMEMO;
+    }
+    emit_request(d, G, pool, g0, parity, c0, c1, stop_count);
+    return ST_WAIT;
+}
+
 // MODE: C4_EVAL_EXTERNAL / C4_EVAL_CENTRE / C4_EVAL_NET.  One warp per game slot.
 template <int MODE, bool SELFPLAY>
 #ifndef C4_ADV_MIN_BLOCKS
@@ -51,7 +67,9 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
     const int gi = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int g = g0 + gi;
     const int lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { d.ctr->leaf_count[pool][parity ^ 1] = 0; d.ctr->stop_flag[pool][parity ^ 1] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        d.ctr->leaf_count[pool][parity ^ 1] = 0; d.ctr->busy_count[pool][parity ^ 1] = 0; d.ctr->stop_flag[pool][parity ^ 1] = 0;
+    }
     if (gi >= n_games) return;
     const long long t_start = clock64();
     int st = d.status[g];
@@ -65,9 +83,8 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
     G.c0 = d.root_c0[g]; G.c1 = d.root_c1[g];
     G.age = c4_age(G.c0, G.c1);
 
-    if (st == ST_WAIT) {
+    if (st == ST_WAIT || st == ST_WAITMEMO) {
         // consume the evaluator's answer for the pending leaf (oinkoink/mcts.py:129-135), then backpropagate
-        const int slot = d.pending_slot[g];
         const uint32_t node = (uint32_t)d.pending_node[g];
         const int plen = d.path_len[g];
         const u64 lc0 = d.pend_c0[g], lc1 = d.pend_c1[g];
@@ -75,14 +92,35 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
         const bool is_root = (plen == 0);
         const int ply = SELFPLAY ? d.ply[g] : 0;
         if (MODE == C4_EVAL_NET) {
-            const float *o = d.net_out + (size_t)slot * 8;
-            float ov = (lane < 8) ? o[lane] : 0.f;
-            if (__any_sync(FULL, !isfinite(ov))) {
-                // operand overflow (fp16) or NaN weights: neutral answer + a flag that makes the host call fail
-                // (the reference asserts on every evaluation, oinkoink/neural/pytorch/model.py:258-263,275-280)
-                ov = (lane < 7) ? (1.f / 7.f) : 0.5f;
-                if (lane == 0) d.ctr->net_nonfinite = 1;
-            } else if (d.memo) memo_insert(d, lc0, lc1, ov, lane);
+            float ov;
+            if (st == ST_WAIT) {
+                const float *o = d.net_out + (size_t)d.pending_slot[g] * 8;
+                ov = (lane < 8) ? o[lane] : 0.f;
+                if (__any_sync(FULL, !isfinite(ov))) {
+                    // operand overflow (fp16) or NaN weights: neutral answer + a flag that makes the host call fail
+                    // (the reference asserts on every evaluation, oinkoink/neural/pytorch/model.py:258-263,275-280)
+                    ov = (lane < 7) ? (1.f / 7.f) : 0.5f;
+                    if (lane == 0) d.ctr->net_nonfinite = 1;
+                }
+                if (d.memo) memo_insert(d, lc0, lc1, ov, lane);          // replaces this game's PENDING tag
+            } else {
+                // the leaf was being evaluated for another game.  Its owner consumes the answer at the start of this very
+                // pass and puts it into the memo a microsecond or two from now: look a few times (bounded -- the owner's
+                // warp may not be running yet), then leave it for the next pass
+                u64 seen;
+                int pr = memo_probe(d, lc0, lc1, ov, lane, seen);
+                for (int k = 0; k < 6 && pr == MEMO_PENDING; k++) { __nanosleep(500); pr = memo_probe(d, lc0, lc1, ov, lane, seen); }
+                if (pr == MEMO_HIT) {
+                    if (lane == 0) d.stat_hits[g] += 1ULL;
+                } else if (pr == MEMO_PENDING || !memo_claim(d, lc0, lc1, seen, lane)) {
+                    if (lane == 0) count_busy(d, pool, parity, stop_count);       // still waiting: nothing changes
+                    return;
+                } else {                            // the tag is gone (a colliding key took the entry): evaluate it ourselves
+                    emit_request(d, G, pool, g0, parity, lc0, lc1, stop_count);
+                    if (lane == 0) d.status[g] = ST_WAIT;
+                    return;
+                }
+            }
             float pf = (lane < 7) ? ov : 0.f;
             double value = (double)__shfl_sync(FULL, ov, 7);
             apply_eval<true>(d, G, node, lc0, lc1, lage, value, 0.0, pf, is_root, ply);
@@ -93,6 +131,7 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
                 G.sims_done++;
             }
         } else if (MODE == C4_EVAL_EXTERNAL) {
+            const int slot = d.pending_slot[g];
             double value = d.ext_value[slot];
             if (d.ext_prior_dtype == 1) {
                 float pf = (lane < 7) ? ((const float *)d.ext_prior)[(size_t)slot * 7 + lane] : 0.f;
@@ -128,7 +167,9 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
                 st = ST_READY;
             } else {
                 float ov;
-                if (MODE == C4_EVAL_NET && d.memo && memo_lookup(d, G.c0, G.c1, ov, lane)) {
+                u64 seen = 0;
+                const int pr = (MODE == C4_EVAL_NET && d.memo) ? memo_probe(d, G.c0, G.c1, ov, lane, seen) : MEMO_MISS;
+                if (pr == MEMO_HIT) {
                     // the new root was evaluated before (usually as a leaf of the previous move's search)
                     const int ply = SELFPLAY ? d.ply[g] : 0;
                     apply_eval<true>(d, G, 0u, G.c0, G.c1, G.age, (double)__shfl_sync(FULL, ov, 7), 0.0,
@@ -136,8 +177,7 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
                     if (lane == 0) d.stat_hits[g] += 1ULL;
                     st = ST_READY;
                 } else {
-                    emit_request(d, G, pool, g0, parity, G.c0, G.c1, 0u, 0, 0u, 0u, stop_count);
-                    st = ST_WAIT;
+                    st = request_or_wait<MODE>(d, G, pool, g0, parity, stop_count, G.c0, G.c1, 0u, 0, 0u, 0u, pr, seen);
                     break;
                 }
             }
@@ -180,9 +220,12 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
             G.sims_done++;
             continue;
         }
+        int pr = MEMO_MISS;
+        u64 seen = 0;
         if (MODE == C4_EVAL_NET && d.memo) {
             float ov;
-            if (memo_lookup(d, L.c0, L.c1, ov, lane)) {
+            pr = memo_probe(d, L.c0, L.c1, ov, lane, seen);
+            if (pr == MEMO_HIT) {
                 const double value = (double)__shfl_sync(FULL, ov, 7);
                 apply_eval<true>(d, G, L.node, L.c0, L.c1, L.age, value, 0.0, (lane < 7) ? ov : 0.f, false, 0);
                 backup(G, L.path_lo, L.path_hi, L.depth, value);
@@ -191,8 +234,7 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
                 continue;
             }
         }
-        emit_request(d, G, pool, g0, parity, L.c0, L.c1, L.node, L.depth + 1, L.path_lo, L.path_hi, stop_count);
-        st = ST_WAIT;
+        st = request_or_wait<MODE>(d, G, pool, g0, parity, stop_count, L.c0, L.c1, L.node, L.depth + 1, L.path_lo, L.path_hi, pr, seen);
         break;
     }
     if (lane == 0) {
@@ -209,6 +251,7 @@ __global__ void k_search_begin(C4Dev d, const u64 *c0, const u64 *c1, int n, int
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) {
         d.ctr->leaf_count[0][0] = 0; d.ctr->leaf_count[0][1] = 0; d.ctr->leaf_count[1][0] = 0; d.ctr->leaf_count[1][1] = 0;
+        d.ctr->busy_count[0][0] = 0; d.ctr->busy_count[0][1] = 0; d.ctr->busy_count[1][0] = 0; d.ctr->busy_count[1][1] = 0;
         d.ctr->stop_flag[0][0] = 0; d.ctr->stop_flag[0][1] = 0; d.ctr->stop_flag[1][0] = 0; d.ctr->stop_flag[1][1] = 0;
         d.ctr->n_done = 0; d.ctr->engine_error = 0; d.ctr->net_nonfinite = 0;
     }
@@ -228,6 +271,7 @@ __global__ void k_selfplay_init(C4Dev d, int max_games)
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) {
         d.ctr->leaf_count[0][0] = 0; d.ctr->leaf_count[0][1] = 0; d.ctr->leaf_count[1][0] = 0; d.ctr->leaf_count[1][1] = 0;
+        d.ctr->busy_count[0][0] = 0; d.ctr->busy_count[0][1] = 0; d.ctr->busy_count[1][0] = 0; d.ctr->busy_count[1][1] = 0;
         d.ctr->stop_flag[0][0] = 0; d.ctr->stop_flag[0][1] = 0; d.ctr->stop_flag[1][0] = 0; d.ctr->stop_flag[1][1] = 0;
         d.ctr->games_finished = 0; d.ctr->n_records = 0; d.ctr->overflow = 0; d.ctr->n_done = 0;
         d.ctr->engine_error = 0; d.ctr->net_nonfinite = 0;
@@ -318,6 +362,16 @@ __global__ void k_sum_stats(const unsigned long long *evals, const unsigned long
         __syncthreads();
     }
     if (threadIdx.x == 0) { out[0] = se[0]; out[1] = sp[0]; out[2] = sh[0]; }
+}
+
+// occupied entries of the evaluation memo (diagnostics: distinct positions evaluated ~ occupied entries)
+__global__ void k_memo_count(const uint32_t *memo, size_t n_entries, unsigned long long *out)
+{
+    unsigned long long c = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += (size_t)gridDim.x * blockDim.x)
+        c += (memo[i * 16 + 12] | memo[i * 16 + 13]) != 0u;
+    for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // generation sink: native_to_pytorch(add_fliplr=True) (oinkoink/neural/pytorch/data.py:78-105); originals first, then
@@ -593,6 +647,15 @@ extern "C" int c4_ctx_get(c4_ctx *ctx, int key)
     case 4: return ctx->d.memo ? ctx->memo_log2 : 0;
     case 5: return (int)std::min<long long>(ctx->last_memo_hits, 0x7fffffff);
     case 6: return (int)std::min<long long>(ctx->last_launches, 0x7fffffff);
+    case 7: {                                           // occupied entries of the evaluation memo (synchronises the device)
+        if (!ctx->d.memo) return 0;
+        cudaSetDevice(ctx->device);
+        cudaMemset(ctx->stats_dev + 3, 0, sizeof(unsigned long long));
+        k_memo_count<<<148 * 8, 256>>>(ctx->d.memo, (size_t)1 << ctx->memo_log2, ctx->stats_dev + 3);
+        unsigned long long h = 0;
+        if (cudaMemcpy(&h, ctx->stats_dev + 3, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return (int)std::min<unsigned long long>(h, 0x7fffffffULL);
+    }
     default: return -1;
     }
 }
@@ -621,6 +684,7 @@ extern "C" int c4_ctx_set_net(c4_ctx *ctx, c4_net *net)
         ctx->memo_net_uid = c4_net_uid(net);
     }
     ctx->net = net;
+    ctx->d.memo_dedup = (ctx->d.memo && !getenv("C4_MEMO_NO_DEDUP")) ? 1 : 0;
     // Self-play with a 64-filter network is network-bound (124 us network vs 41 us tree per pass): there the two half
     // pools on two streams pay -- the tree pass of one half runs under the network launch of the other (+7-9 %,
     // tools/ramp64.py) -- while with the 32-filter network the game chains are the limit and one pool is faster.

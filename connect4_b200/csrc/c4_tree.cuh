@@ -10,7 +10,8 @@ unsigned long long c4_net_uid(const c4_net *net);     // c4_net.cu (internal)
 int c4_net_filters(const c4_net *net);
 int c4_net_device(const c4_net *net);
 
-enum { ST_IDLE = 0, ST_READY = 1, ST_WAIT = 2, ST_DONE = 3, ST_NEWROOT = 4 };
+enum { ST_IDLE = 0, ST_READY = 1, ST_WAIT = 2, ST_DONE = 3, ST_NEWROOT = 4,
+       ST_WAITMEMO = 7 };     // the leaf is being evaluated for ANOTHER game: re-probe the memo instead of asking again
 #define PATH_CAP 48
 #define MAX_PLY 42
 #define FULL 0xffffffffu
@@ -22,9 +23,10 @@ struct C4Counters {
     unsigned long long n_done;          // stand-alone searches finished
     unsigned long long overflow;        // records dropped (records_out too small)
     int leaf_count[2][2];               // [pool][parity] ping-pong leaf batch counters
+    int busy_count[2][2];               // ... leaves + games that wait for another game's leaf (the pass's stop rule)
     int engine_error;                   // fused engine: non-zero = the kernel gave up (watchdog), see c4_fused.cu
     int net_nonfinite;                  // a network answer was not finite (fp16 operand overflow): the call fails loudly
-    int pad[32 - 16];
+    int pad[32 - 20];
     int stop_flag[2][2];                // [pool][parity], on its own 128-byte line: set by the warp whose request makes
                                         // the batch reach the pass's stop count, polled (read-only) by the running warps
     int pad2[28];
@@ -66,6 +68,7 @@ struct C4Dev {
     // network's answer is consumed.  Pure cache: a hit returns bit-identical numbers to a network evaluation.
     uint32_t *memo;                     // [memo_mask + 1][16] words, or nullptr
     uint32_t memo_mask;
+    int memo_dedup;                     // a game that misses claims the entry (PENDING tag): later askers wait for its answer
     unsigned long long *stat_hits;      // [G]
     // evaluator answers
     const float *net_out;               // [G][8] {prior[7], value}
@@ -212,6 +215,55 @@ __device__ __forceinline__ bool memo_lookup(const C4Dev &d, u64 c0, u64 c1, floa
     const uint32_t dig = memo_payload_digest(w, lane);
     out_lane = __uint_as_float(w);
     return k0 == c0 && k1 == c1 && chk == memo_check(c0, c1, dig);
+}
+
+// ---- de-duplication of evaluations in flight.  Measured on the benchmark generation (tools/memo_dups.py): 1.45 network
+// evaluations per DISTINCT position (2.3 in the first 256 games) -- thousands of games walk the same openings at the same
+// time, and all of them miss the memo until the first answer is in.  So the game that misses first CLAIMS the entry: it
+// swaps a PENDING tag (a function of the key, bit 0 clear -- checksums have bit 0 set, empty entries are 0) into the
+// entry's check word with a 64-bit CAS and asks the network; every later asker finds the tag, parks its leaf
+// (ST_WAITMEMO) and re-probes until the owner's answer has replaced the tag.  Pure work elimination: a waiter ends up with
+// the bit-identical numbers it would have got from its own evaluation.  No dead end: whoever wins a claim evaluates and
+// inserts; if a colliding key overwrites the tag or the entry, the waiters simply miss and claim again.
+enum { MEMO_MISS = 0, MEMO_HIT = 1, MEMO_PENDING = 2 };
+__device__ __forceinline__ u64 memo_pending_tag(u64 c0, u64 c1)
+{
+    return (memo_mix(c1 * 0x9E3779B97F4A7C15ULL ^ memo_mix(c0 + 0xD6E8FEB86659FD93ULL)) & ~3ULL) | 2ULL;
+}
+// like memo_lookup, three-valued; `seen` = the check word that was read (the CAS of memo_claim expects it)
+__device__ __forceinline__ int memo_probe(const C4Dev &d, u64 c0, u64 c1, float &out_lane, int lane, u64 &seen)
+{
+    const uint32_t *e = d.memo + (size_t)memo_index(c0, c1, d.memo_mask) * 16;
+    const uint32_t v = (lane < 16) ? __ldcg(e + lane) : 0u;
+    const u64 k0 = (u64)__shfl_sync(FULL, v, 0) | ((u64)__shfl_sync(FULL, v, 1) << 32);
+    const u64 k1 = (u64)__shfl_sync(FULL, v, 2) | ((u64)__shfl_sync(FULL, v, 3) << 32);
+    const u64 chk = (u64)__shfl_sync(FULL, v, 12) | ((u64)__shfl_sync(FULL, v, 13) << 32);
+    const uint32_t w = __shfl_sync(FULL, v, (lane + 4) & 31);
+    const uint32_t dig = memo_payload_digest(w, lane);
+    out_lane = __uint_as_float(w);
+    seen = chk;
+    if (k0 == c0 && k1 == c1 && chk == memo_check(c0, c1, dig)) return MEMO_HIT;
+#ifdef C4_NO_DEDUP_BUILD
+    return MEMO_MISS;
+#else
+    return (d.memo_dedup && chk == memo_pending_tag(c0, c1)) ? MEMO_PENDING : MEMO_MISS;
+#endif
+}
+// after a MEMO_MISS: true = this game evaluates the position (it won the claim, or the slot is contended by another key
+// and nothing is marked), false = another game claimed the same position a moment ago: wait for its answer
+__device__ __forceinline__ bool memo_claim(const C4Dev &d, u64 c0, u64 c1, u64 seen, int lane)
+{
+    int own = 1;
+#ifdef C4_NO_DEDUP_BUILD
+    return true;
+#endif
+    if (lane == 0) {
+        unsigned long long *chk = reinterpret_cast<unsigned long long *>(d.memo + (size_t)memo_index(c0, c1, d.memo_mask) * 16 + 12);
+        const u64 tag = memo_pending_tag(c0, c1);
+        const u64 old = atomicCAS(chk, (unsigned long long)seen, (unsigned long long)tag);
+        own = !(old != seen && old == tag);
+    }
+    return __shfl_sync(FULL, own, 0) != 0;
 }
 
 struct Game {
@@ -457,11 +509,27 @@ __device__ __forceinline__ int sample_child(double v, bool exists, int lane, dou
     return 31 - __clz(m);
 }
 
+// the pass's stop rule: one more game of the pool waits (for the network, or for another game's leaf)
+__device__ __forceinline__ void count_busy(const C4Dev &d, int pool, int parity, int stop_count)
+{
+    const int b = atomicAdd(&d.ctr->busy_count[pool][parity], 1);
+    if (stop_count > 0 && b + 1 == stop_count) d.ctr->stop_flag[pool][parity] = 1;
+}
+// park the pending leaf of a game (consumed when the answer is there): node, board, path
+__device__ __forceinline__ void save_pending(const C4Dev &d, const Game &G, u64 c0, u64 c1, uint32_t node, int path_len,
+                                             uint32_t path_lo, uint32_t path_hi)
+{
+    if (G.lane == 0) {
+        d.pend_c0[G.g] = c0; d.pend_c1[G.g] = c1;
+        d.pending_node[G.g] = (int)node; d.path_len[G.g] = path_len;
+    }
+    if (G.lane < path_len) d.path[(size_t)G.g * PATH_CAP + G.lane] = path_lo;
+    if (G.lane + 32 < path_len) d.path[(size_t)G.g * PATH_CAP + G.lane + 32] = path_hi;
+}
+// append a (parked) leaf to the pool's batch
 __device__ __forceinline__ void emit_request(const C4Dev &d, Game &G, int pool, int g0, int parity, u64 c0, u64 c1,
-                                             uint32_t node, int path_len, uint32_t path_lo, uint32_t path_hi,
                                              int stop_count = 0)
 {
-    int slot = 0;
     if (G.lane == 0) {
         // INTENTIONAL RACES (2 and 3 of 3 in the lock-step engine): the leaf counter is bumped with an atomic while the
         // network kernel of the PREVIOUS pass may still read its ping-pong twin (two counters per pool, reset one pass late),
@@ -469,18 +537,12 @@ __device__ __forceinline__ void emit_request(const C4Dev &d, Game &G, int pool, 
         // one more simulation of its own game -- pass length never changes results (tests/test_gpu_edges.py)
         const int k = atomicAdd(&d.ctr->leaf_count[pool][parity], 1);               // a pool's batch lives at [g0, g0 + n)
         C4_DEV_ASSERT(k >= 0 && g0 + k < g0 + (1 << 20));
-        if (stop_count > 0 && k + 1 == stop_count) d.ctr->stop_flag[pool][parity] = 1;
-        slot = g0 + k;
-    }
-    slot = __shfl_sync(FULL, slot, 0);
-    if (G.lane == 0) {
+        count_busy(d, pool, parity, stop_count);
+        const int slot = g0 + k;
         d.leaf_c0[slot] = c0; d.leaf_c1[slot] = c1; d.leaf_game[slot] = G.g;
-        d.pend_c0[G.g] = c0; d.pend_c1[G.g] = c1;
-        d.pending_node[G.g] = (int)node; d.pending_slot[G.g] = slot; d.path_len[G.g] = path_len;
+        d.pending_slot[G.g] = slot;
         d.stat_evals[G.g] += 1ULL;
     }
-    if (G.lane < path_len) d.path[(size_t)G.g * PATH_CAP + G.lane] = path_lo;
-    if (G.lane + 32 < path_len) d.path[(size_t)G.g * PATH_CAP + G.lane + 32] = path_hi;
 }
 
 // End of a search inside a self-play game: pick the move, log the position, play it, finish / re-seed the game.

@@ -224,13 +224,16 @@ def main():
         step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    tot = dict(positions=0, evals=0, device_ms=0.0, games=0, memo_hits=0, launches=0)
+    tot = dict(positions=0, evals=0, device_ms=0.0, games=0, memo_hits=0, launches=0, passes=0)
+    tree_ms_sum = net_ms_sum = 0.0
     t_wall = time.perf_counter()
     for _ in range(args.steps):
         r = step()
         for k in tot:
             tot[k] += r[k]
         engine, memo_log2 = r["engine"], r["memo_log2"]
+        tree_ms_sum += r["tree_ms"]
+        net_ms_sum += r["net_ms"]
     barrier()
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if sampler else None
@@ -326,17 +329,40 @@ def main():
         tf = evals * flops / secs / 1e12 / world                              # per GPU
         tree_bytes = positions * SIMS * 1280.0 + (evals + hits) * 64.0
         gbs = tree_bytes / secs / 1e9 / world
-        kname = ("k_fused<OpFP16,selfplay> (persistent: tree warps + tcgen05 tower per SM, one launch per step)"
-                 if engine == "fused" else "k_advance<NET,selfplay> + k_net_tc<OpFP16,32> (lock-step passes)")
-        roof_t = {"kernel": kname, "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                  "traffic": None, "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals / n_launch,
-                  "ms_per_launch": step_ms if engine == "fused" else None,
-                  "note": "network FLOPs of the step / step time; the step is bound by instruction issue and dependent-chain "
-                          "latency (tree simulations + the tower's epilogue), not by the tensor pipe"}
-        roof_h = {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
-                  "traffic": None, "peak_source": peak_src.replace("sustained bf16", "copy bandwidth"),
-                  "algorithmic_bytes_per_launch": tree_bytes / n_launch, "sims_per_launch": positions * SIMS / n_launch,
-                  "note": "1.28 KB per simulation (SURVEY.md 8d) + 64 B per memo probe; dependent-load latency bound"}
+        if engine == "fused":
+            kname = "k_fused<OpFP16,selfplay> (persistent: tree warps + tcgen05 tower per SM, one launch per step)"
+            roof_t = {"kernel": kname, "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                      "traffic": None, "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals / n_launch,
+                      "ms_per_launch": step_ms, "share_of_step": 1.0,
+                      "note": "network FLOPs of the step / step time; the step is bound by instruction issue and dependent-chain "
+                              "latency (tree simulations + the tower's epilogue), not by the tensor pipe"}
+            roof_h = {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                      "traffic": None, "peak_source": peak_src.replace("sustained bf16", "copy bandwidth"),
+                      "algorithmic_bytes_per_launch": tree_bytes / n_launch, "sims_per_launch": positions * SIMS / n_launch,
+                      "note": "1.28 KB per simulation (SURVEY.md 8d) + 64 B per memo probe; dependent-load latency bound"}
+        else:
+            # lock-step engine: per-launch figures of rank 0 from the launches sampled with CUDA events inside the timed steps
+            passes = max(1, tot["passes"])
+            tree_ms, net_ms = tree_ms_sum / args.steps, net_ms_sum / args.steps
+            sims_l = tot["positions"] * SIMS / passes
+            bytes_l = sims_l * 1280.0 + (tot["evals"] + tot["memo_hits"]) / passes * 64.0
+            evals_l = tot["evals"] / passes
+            t_gbs = bytes_l / (tree_ms * 1e-3) / 1e9 if tree_ms > 0 else 0.0
+            n_tf = evals_l * flops / (net_ms * 1e-3) / 1e12 if net_ms > 0 else 0.0
+            dev_ms_rank0 = max(1e-9, tot["device_ms"])
+            roof_h = {"kernel": "k_advance<NET,selfplay> (warp-per-game tree pass)", "bound": "hbm", "achieved": t_gbs,
+                      "peak": peak_hbm, "unit": "GB/s", "frac": t_gbs / peak_hbm, "traffic": None,
+                      "peak_source": peak_src.replace("sustained bf16", "copy bandwidth"),
+                      "algorithmic_bytes_per_launch": bytes_l, "sims_per_launch": sims_l, "ms_per_launch": tree_ms,
+                      "share_of_step": tree_ms * passes / dev_ms_rank0,
+                      "note": "1.28 KB per simulation (SURVEY.md 8d) + 64 B per memo probe; dependent-load latency bound, not "
+                              "bandwidth bound"}
+            roof_t = {"kernel": "k_net_tc<OpFP16,32> (tcgen05/TMEM)", "bound": "tensor", "achieved": n_tf, "peak": peak_tf,
+                      "unit": "TFLOP/s", "frac": n_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                      "flops_per_eval": flops, "evals_per_launch": evals_l, "ms_per_launch": net_ms,
+                      "share_of_step": net_ms * passes / dev_ms_rank0}
+            if roof_h["share_of_step"] >= roof_t["share_of_step"]:
+                roof_t, roof_h = roof_h, roof_t                       # `roofline` = the kernel with the larger share
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,

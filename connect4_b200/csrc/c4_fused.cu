@@ -322,7 +322,12 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     __syncthreads();                                                      // FzCtl zeroed before the statuses go in
-    for (int i = threadIdx.x; i < FZ_GC_MAX; i += blockDim.x) S->status[i] = (i < Gc) ? dg.status[g0 + i] : ST_IDLE;
+    // (a game the lock-step engine parked on another game's evaluation, ST_WAITMEMO, has applied nothing yet: it simply
+    //  descends to that leaf again)
+    for (int i = threadIdx.x; i < FZ_GC_MAX; i += blockDim.x) {
+        const int st0 = (i < Gc) ? dg.status[g0 + i] : ST_IDLE;
+        S->status[i] = st0 == ST_WAITMEMO ? (int)ST_READY : st0;
+    }
     TC_PROXY_FENCE();
     TC_FENCE_BEFORE();
     __syncthreads();
@@ -659,22 +664,31 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
 
 // ------------------------------------------------------------------------------------------------ host side
 // internal interface used by c4_search.cu
-bool c4_fused_eligible(const c4_net *net, int max_games, int simulations)
+// can the fused engine run this network on a pool of this size at all?
+bool c4_fused_supported(const c4_net *net, int max_games)
 {
     if (!net || (net->F != 32 && net->F != 64) || !net->use_tc || !net->image_tc) return false;
-    const char *want = getenv("C4_ENGINE");                  // "fused" / "lockstep" force an engine, anything else = auto
-    if (want && !strcmp(want, "lockstep")) return false;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
     const int grid = std::min(sms, max_games);
-    const int per_cta = (max_games + grid - 1) / grid;
-    if (per_cta > FZ_GC_MAX) return false;
+    if ((max_games + grid - 1) / grid > FZ_GC_MAX) return false;
+    return (net->F == 32 ? fz_total<FzK32>(net->R, 0) : fz_total<FzK64>(net->R, 0)) <= 227 * 1024;
+}
+
+// ... and is it the engine to use for `live_games` games in flight?  env C4_ENGINE = "fused" / "lockstep" forces one.
+bool c4_fused_eligible(const c4_net *net, int max_games, long long live_games)
+{
+    const char *want = getenv("C4_ENGINE");
+    if (want && !strcmp(want, "lockstep")) return false;
+    if (!c4_fused_supported(net, max_games)) return false;
+    if (want && !strcmp(want, "fused")) return true;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // auto: the fused engine up to 16 games per SM (2,368 on a B200).  Measured crossover, cold generation, positions/s
     // (profiles/README.md): 256 games 52k vs 23k (lock-step), 1,024 games 123k vs 96k, 2,048 games 189k vs 181k, 4,096 games
     // 291k vs 318k, 8,192 games 315k vs 427k -- with many games per SM the lock-step pass, which gives every phase the
     // whole SM and de-duplicates the evaluations in flight, is ahead
-    if (!(want && !strcmp(want, "fused")) && per_cta > 16) return false;
-    return (net->F == 32 ? fz_total<FzK32>(net->R, 0) : fz_total<FzK64>(net->R, 0)) <= 227 * 1024;
+    return live_games <= 16LL * sms;
 }
 
 // Run the pool until every game slot is idle / done, `stop_games` games have finished (counter in d.ctr) or `stop_ms`

@@ -36,7 +36,7 @@
 #include "c4_tree.cuh"
 
 // c4_fused.cu: the persistent engine (one launch per generation); c4_search.cu keeps the lock-step pass engine
-bool c4_fused_eligible(const c4_net *net, int max_games, int simulations);
+bool c4_fused_eligible(const c4_net *net, int max_games, long long live_games);
 int c4_fused_run(const C4Dev &d, const c4_net *net, int max_games, int simulations, bool selfplay,
                  unsigned long long stop_games, double stop_ms, cudaStream_t stream);
 
@@ -50,7 +50,7 @@ __device__ __forceinline__ int request_or_wait(const C4Dev &d, Game &G, int pool
 {
     save_pending(d, G, c0, c1, node, path_len, path_lo, path_hi);
     if (MODE == C4_EVAL_NET && d.memo && d.memo_dedup && (probe == MEMO_PENDING || !memo_claim(d, c0, c1, seen, G.lane))) {
-        if (G.lane == 0) count_busy(d, pool, parity, stop_count);
+        if (G.lane == 0) { count_busy(d, pool, parity, stop_count); d.pending_slot[G.g] = 0; }   // looks at the memo so far
         return ST_WAITMEMO;
     }
     emit_request(d, G, pool, g0, parity, c0, c1, stop_count);
@@ -112,9 +112,10 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
                 for (int k = 0; k < 6 && pr == MEMO_PENDING; k++) { __nanosleep(500); pr = memo_probe(d, lc0, lc1, ov, lane, seen); }
                 if (pr == MEMO_HIT) {
                     if (lane == 0) d.stat_hits[g] += 1ULL;
-                } else if (pr == MEMO_PENDING || !memo_claim(d, lc0, lc1, seen, lane)) {
-                    if (lane == 0) count_busy(d, pool, parity, stop_count);       // still waiting: nothing changes
-                    return;
+                } else if (budget < 0 || (d.pending_slot[g] < WAITMEMO_PATIENCE &&
+                                          (pr == MEMO_PENDING || !memo_claim(d, lc0, lc1, seen, lane)))) {
+                    if (lane == 0) { count_busy(d, pool, parity, stop_count); d.pending_slot[g] += 1; }   // still waiting
+                    return;                         // (a consume-only pass never asks for anything new)
                 } else {                            // the tag is gone (a colliding key took the entry): evaluate it ourselves
                     emit_request(d, G, pool, g0, parity, lc0, lc1, stop_count);
                     if (lane == 0) d.status[g] = ST_WAIT;
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(128, C4_ADV_MIN_BLOCKS) k_advance(C4Dev d, int
     bool first_descent_done = false;
     int waiting_seen = 0;
     for (;;) {
+        if (budget < 0) break;                                            // consume-only pass (hand-over to the fused engine)
         if (st == ST_NEWROOT) {
             // Tree(board) + evaluate root (oinkoink/mcts.py:98-105): fresh pool, root = node 0 of block 0
             G.n_blocks = 1;
@@ -461,6 +463,8 @@ struct c4_ctx {
     bool supplied;
     bool pool_fresh;                    // bench pool initialised
     long long last_launches;            // kernels launched by the last c4_selfplay_stream call
+    float last_tree_ms, last_net_ms;    // lock-step engine: mean sampled launch durations of the last c4_selfplay_stream call
+    long long last_passes;
     int pool_engine;                    // engine that owns the re-seeding pool's state: 0 none, 1 lock-step, 2 fused
     cudaEvent_t ev0, ev1;
     cudaEvent_t evs[2 * 64];            // sampled (start, stop) pairs around network launches
@@ -647,6 +651,9 @@ extern "C" int c4_ctx_get(c4_ctx *ctx, int key)
     case 4: return ctx->d.memo ? ctx->memo_log2 : 0;
     case 5: return (int)std::min<long long>(ctx->last_memo_hits, 0x7fffffff);
     case 6: return (int)std::min<long long>(ctx->last_launches, 0x7fffffff);
+    case 8: return (int)(ctx->last_tree_ms * 1e6f);     // ns, mean tree-pass launch of the last stream call (lock-step)
+    case 9: return (int)(ctx->last_net_ms * 1e6f);      // ns, mean network launch
+    case 10: return (int)std::min<long long>(ctx->last_passes, 0x7fffffff);
     case 7: {                                           // occupied entries of the evaluation memo (synchronises the device)
         if (!ctx->d.memo) return 0;
         cudaSetDevice(ctx->device);
@@ -757,6 +764,7 @@ extern "C" int c4_search_begin(c4_ctx *ctx, const uint64_t *c0, const uint64_t *
     ctx->d.n_games_target = 0;
     ctx->d.records_out = nullptr;
     ctx->pool_fresh = false;
+    ctx->d.memo_epoch++;
     k_search_begin<<<(ctx->max_games + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->d, (const u64 *)c0,
                                                                                    (const u64 *)c1, n, ctx->max_games);
     C4_CUDA(cudaGetLastError());
@@ -825,9 +833,9 @@ static int check_device_errors(const C4Counters &c)
     return 0;
 }
 
-static bool use_fused(const c4_ctx *ctx, int eval_kind)
+static bool use_fused(const c4_ctx *ctx, int eval_kind, long long live_games)
 {
-    return eval_kind == C4_EVAL_NET && c4_fused_eligible(ctx->net, ctx->max_games, ctx->cfg.simulations);
+    return eval_kind == C4_EVAL_NET && c4_fused_eligible(ctx->net, ctx->max_games, live_games);
 }
 
 extern "C" int c4_search_run(c4_ctx *ctx, int eval_kind, void *stream)
@@ -845,7 +853,7 @@ extern "C" int c4_search_run(c4_ctx *ctx, int eval_kind, void *stream)
         return 0;
     }
     C4Counters c;
-    if (use_fused(ctx, eval_kind)) {
+    if (use_fused(ctx, eval_kind, ctx->n_search)) {
         // every search of the batch in ONE persistent launch (c4_fused.cu)
         if ((rc = c4_fused_run(ctx->d, ctx->net, ctx->max_games, ctx->cfg.simulations, false, 0ULL, 0.0, s))) return rc;
         if ((rc = read_counters(ctx, &c, s))) return rc;
@@ -906,9 +914,9 @@ extern "C" int c4_search_export_tree(c4_ctx *ctx, int32_t game, void *nodes_out,
 // tree pass of one half overlaps the network launch of the other; the network launch is capped at net_ctas CTAs so
 // the tree blocks find free SMs.
 static int selfplay_passes(c4_ctx *ctx, int eval_kind, int n_passes, cudaStream_t s, int sample_every = 0,
-                           int *n_sampled = nullptr)
+                           int *n_sampled = nullptr, int first_sample = 0)
 {
-    int rc, ns = 0;
+    int rc, ns = first_sample;
     const bool two = ctx->n_pools == 2 && eval_kind == C4_EVAL_NET;
     if (two) {
         C4_CUDA(cudaEventRecord(ctx->ev_fork, s));
@@ -974,6 +982,7 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
     d.start_c0 = (const u64 *)start_c0; d.start_c1 = (const u64 *)start_c1;
     d.records_out = records_out; d.max_records = max_records;
     ctx->pool_fresh = false;
+    d.memo_epoch++;
     k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
     C4_CUDA(cudaGetLastError());
     ctx->parity = 0;
@@ -981,7 +990,7 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
     int rc;
     C4Counters c;
     ctx->pool_engine = 0;
-    if (use_fused(ctx, eval_kind)) {
+    if (use_fused(ctx, eval_kind, std::min<long long>(n_games, ctx->max_games))) {
         // the whole generation in ONE persistent launch: slots go idle when no game is left to seed, CTAs leave when
         // all their slots are idle (c4_fused.cu)
         if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, 0ULL, 0.0, s))) return rc;
@@ -996,6 +1005,24 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
             if ((rc = check_device_errors(c))) return rc;
             ctx->live_games = std::max<long long>(1, std::min<long long>(n_games - (long long)c.games_finished, ctx->max_games));
             if ((long long)c.games_finished >= n_games) break;
+            if (use_fused(ctx, eval_kind, ctx->live_games)) {
+                // the drain of a generation: few games are left in flight, and a pass costs the same launches and the same
+                // network latency for 500 games as for 4,096.  Hand the pool over to the fused engine: one consume-only
+                // pass (every answered leaf is applied, nothing new is requested), then one persistent launch to the end.
+                if (ctx->n_pools == 2 && eval_kind == C4_EVAL_NET) {
+                    for (int p = 0; p < 2; p++) {
+                        int g0, n;
+                        pool_range(ctx, p, &g0, &n);
+                        ctx->pool_parity[p] ^= 1;
+                        if ((rc = launch_advance_pool<true>(ctx, eval_kind, g0, n, p, ctx->pool_parity[p], -1, s))) return rc;
+                    }
+                } else if ((rc = launch_advance<true>(ctx, eval_kind, ctx->max_games, -1, s))) return rc;
+                if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, 0ULL, 0.0, s))) return rc;
+                if ((rc = read_counters(ctx, &c, s))) return rc;
+                if ((rc = check_device_errors(c))) return rc;
+                C4_REQUIRE((long long)c.games_finished >= n_games, "c4_selfplay_run: the fused engine left games unfinished");
+                break;
+            }
             C4_REQUIRE(it < (1LL << 24), "c4_selfplay_run: did not terminate");
         }
     }
@@ -1030,7 +1057,8 @@ extern "C" int c4_selfplay_bench(c4_ctx *ctx, int eval_kind, int64_t iterations,
         d.game_id_base = 0; d.game_id_stride = 1;
         d.start_c0 = nullptr; d.start_c1 = nullptr;
         d.records_out = nullptr; d.max_records = 0;
-        k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
+        d.memo_epoch++;
+    k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
         C4_CUDA(cudaGetLastError());
         ctx->parity = 0;
         ctx->pool_parity[0] = ctx->pool_parity[1] = 0;
@@ -1093,7 +1121,7 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     cudaStream_t s = (cudaStream_t)stream;
     C4_CUDA(cudaSetDevice(ctx->device));
     C4Dev &d = ctx->d;
-    const bool fused = use_fused(ctx, eval_kind);
+    const bool fused = use_fused(ctx, eval_kind, ctx->max_games);
     const int eng = fused ? 2 : 1;
     int rc;
     if (reset || !ctx->pool_fresh || ctx->pool_engine != eng) {
@@ -1102,7 +1130,8 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
         d.game_id_base = 0; d.game_id_stride = 1;
         d.start_c0 = nullptr; d.start_c1 = nullptr;
         d.records_out = nullptr; d.max_records = 0;
-        k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
+        d.memo_epoch++;
+    k_selfplay_init<<<(ctx->max_games + 127) / 128, 128, 0, s>>>(d, ctx->max_games);
         C4_CUDA(cudaGetLastError());
         ctx->parity = 0;
         ctx->pool_parity[0] = ctx->pool_parity[1] = 0;
@@ -1118,14 +1147,20 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     const unsigned long long games_goal = stop_games > 0 ? before[2] + (unsigned long long)stop_games : 0ULL;
     C4_CUDA(cudaEventRecord(ctx->ev0, s));
     ctx->last_launches = 2;                                  // k_sum_stats before and after
+    ctx->last_tree_ms = ctx->last_net_ms = 0.f;
+    ctx->last_passes = 0;
+    int n_sampled = 0;
     if (fused) {
         if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, games_goal, max_ms, s))) return rc;
         ctx->last_launches += 1;
     } else {
         // lock-step engine: chunks of passes with a host look at the counters in between
         for (long long it = 0;; it++) {
-            if ((rc = selfplay_passes(ctx, eval_kind, 64, s))) return rc;
+            // one pass of every chunk is bracketed with CUDA events (<= 64 samples over the call): launch durations of the
+            // tree pass and the network kernel for the roofline figures
+            if ((rc = selfplay_passes(ctx, eval_kind, 64, s, it < N_SAMPLES ? 64 : 0, &n_sampled, n_sampled))) return rc;
             ctx->last_launches += 64 * (eval_kind == C4_EVAL_NET ? 2 * ctx->n_pools : 1);
+            ctx->last_passes += 64;
             C4_CUDA(cudaEventRecord(ctx->ev1, s));
             if ((rc = read_counters(ctx, &c, s))) return rc;
             float ms = 0.f;
@@ -1143,6 +1178,17 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     after[0] = ctx->pinned[40]; after[1] = ctx->pinned[41]; after[2] = c.games_finished; after[3] = ctx->pinned[42];
     float ms = 0.f;
     C4_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (!fused && n_sampled > 0) {
+        float nsum = 0.f, tsum = 0.f;
+        for (int i = 0; i < n_sampled; i++) {
+            float t = 0.f;
+            if (eval_kind == C4_EVAL_NET) { C4_CUDA(cudaEventElapsedTime(&t, ctx->evs[2 * i], ctx->evs[2 * i + 1])); nsum += t; }
+            C4_CUDA(cudaEventElapsedTime(&t, ctx->eva[2 * i], ctx->eva[2 * i + 1]));
+            tsum += t;
+        }
+        ctx->last_tree_ms = tsum / n_sampled;
+        ctx->last_net_ms = nsum / n_sampled;
+    }
     if (evals) *evals = (int64_t)(after[0] - before[0]);
     if (positions) *positions = (int64_t)(after[1] - before[1]);
     if (games) *games = (int64_t)(after[2] - before[2]);

@@ -69,6 +69,8 @@ struct C4Dev {
     uint32_t *memo;                     // [memo_mask + 1][16] words, or nullptr
     uint32_t memo_mask;
     int memo_dedup;                     // a game that misses claims the entry (PENDING tag): later askers wait for its answer
+    uint32_t memo_epoch;                // mixed into the PENDING tags: a new pool / search batch never waits on the tags of an
+                                        // abandoned one (their owners are gone and would never answer)
     unsigned long long *stat_hits;      // [G]
     // evaluator answers
     const float *net_out;               // [G][8] {prior[7], value}
@@ -224,11 +226,14 @@ __device__ __forceinline__ bool memo_lookup(const C4Dev &d, u64 c0, u64 c1, floa
 // entry's check word with a 64-bit CAS and asks the network; every later asker finds the tag, parks its leaf
 // (ST_WAITMEMO) and re-probes until the owner's answer has replaced the tag.  Pure work elimination: a waiter ends up with
 // the bit-identical numbers it would have got from its own evaluation.  No dead end: whoever wins a claim evaluates and
-// inserts; if a colliding key overwrites the tag or the entry, the waiters simply miss and claim again.
+// inserts; if a colliding key overwrites the tag or the entry, the waiters simply miss and claim again; the tags carry the
+// epoch of the pool that wrote them, so the tags of an abandoned pool (a stream that was stopped and reset: their owners
+// will never answer) read as plain misses; and a waiter that has looked WAITMEMO_PATIENCE times asks for itself.
+#define WAITMEMO_PATIENCE 64
 enum { MEMO_MISS = 0, MEMO_HIT = 1, MEMO_PENDING = 2 };
-__device__ __forceinline__ u64 memo_pending_tag(u64 c0, u64 c1)
+__device__ __forceinline__ u64 memo_pending_tag(const C4Dev &d, u64 c0, u64 c1)
 {
-    return (memo_mix(c1 * 0x9E3779B97F4A7C15ULL ^ memo_mix(c0 + 0xD6E8FEB86659FD93ULL)) & ~3ULL) | 2ULL;
+    return (memo_mix(c1 * 0x9E3779B97F4A7C15ULL ^ memo_mix(c0 + 0xD6E8FEB86659FD93ULL + ((u64)d.memo_epoch << 50))) & ~3ULL) | 2ULL;
 }
 // like memo_lookup, three-valued; `seen` = the check word that was read (the CAS of memo_claim expects it)
 __device__ __forceinline__ int memo_probe(const C4Dev &d, u64 c0, u64 c1, float &out_lane, int lane, u64 &seen)
@@ -246,7 +251,7 @@ __device__ __forceinline__ int memo_probe(const C4Dev &d, u64 c0, u64 c1, float 
 #ifdef C4_NO_DEDUP_BUILD
     return MEMO_MISS;
 #else
-    return (d.memo_dedup && chk == memo_pending_tag(c0, c1)) ? MEMO_PENDING : MEMO_MISS;
+    return (d.memo_dedup && chk == memo_pending_tag(d, c0, c1)) ? MEMO_PENDING : MEMO_MISS;
 #endif
 }
 // after a MEMO_MISS: true = this game evaluates the position (it won the claim, or the slot is contended by another key
@@ -259,7 +264,7 @@ __device__ __forceinline__ bool memo_claim(const C4Dev &d, u64 c0, u64 c1, u64 s
 #endif
     if (lane == 0) {
         unsigned long long *chk = reinterpret_cast<unsigned long long *>(d.memo + (size_t)memo_index(c0, c1, d.memo_mask) * 16 + 12);
-        const u64 tag = memo_pending_tag(c0, c1);
+        const u64 tag = memo_pending_tag(d, c0, c1);
         const u64 old = atomicCAS(chk, (unsigned long long)seen, (unsigned long long)tag);
         own = !(old != seen && old == tag);
     }

@@ -113,7 +113,9 @@ int c4_ctx_set_net(c4_ctx *ctx, c4_net *net);                    /* evaluator fo
  * network launch of the other; env C4_POOLS), 1 = CTA cap of a half-pool network launch (env C4_NET_CTAS),
  * 2 = terminal re-visits played through per pass (env C4_BUDGET), 3 = max_games, 4 = log2(entries) of the evaluation
  * memo (0 = off; env C4_MEMO_LOG2), 5 = memo hits during the last c4_selfplay_bench call, 6 = kernels launched by the
- * last c4_selfplay_stream call, 7 = occupied entries of the evaluation memo (~ distinct positions evaluated so far).
+ * last c4_selfplay_stream call, 7 = occupied entries of the evaluation memo (~ distinct positions evaluated so far),
+ * 8 / 9 = mean duration in ns of the tree-pass / network launches sampled with CUDA events during the last
+ * c4_selfplay_stream call of the lock-step engine, 10 = its number of passes.
  * The evaluation memo mirrors Evaluator.position_table (oinkoink/evaluators.py:18-25; shared by all games of a
  * process for a whole generation, neural/game_pool.py:21-27): network outputs are cached by position and re-used across
  * moves and games; it is emptied by c4_ctx_set_net.  A hit is bit-identical to a network evaluation. */

@@ -1,5 +1,4 @@
-export C4_FZ_TIMEOUT_S=60
-timeout 200 python tools/fused_check.py --quick 2>&1 | tail -3
-for n in 1024 2048 4096; do for e in fused lockstep; do C4_ENGINE=$e timeout 100 python tools/fused_prof.py $n $n 2>&1 | tail -1 | cut -c1-130; done; done
-C4_ENGINE=lockstep timeout 100 python tools/fused_prof.py 8192 8192 2>&1 | tail -1 | cut -c1-130
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+export C4_FZ_TIMEOUT_S=120
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+timeout 400 python bench.py --no-cpu > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"
+python tools/show_bench.py gpurun_out/bench_default.json

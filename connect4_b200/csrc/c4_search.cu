@@ -463,6 +463,9 @@ struct c4_ctx {
     bool supplied;
     bool pool_fresh;                    // bench pool initialised
     long long last_launches;            // kernels launched by the last c4_selfplay_stream call
+    cudaGraphExec_t chunk_graph[2];     // 64 lock-step passes of the re-seeding / generation pool captured once (no per-launch
+    unsigned long long chunk_key[2][4]; // host work, no gaps between the 128 launches); re-captured when its parameters change;
+                                        // [1] = the same with the launches of pass 32 bracketed by events (eva / evs [0..1])
     float last_tree_ms, last_net_ms;    // lock-step engine: mean sampled launch durations of the last c4_selfplay_stream call
     long long last_passes;
     int pool_engine;                    // engine that owns the re-seeding pool's state: 0 none, 1 lock-step, 2 fused
@@ -559,6 +562,8 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
     ctx->supplied = true;
     ctx->pool_fresh = false;
     ctx->pool_engine = 0;
+    ctx->chunk_graph[0] = ctx->chunk_graph[1] = nullptr;
+    memset(ctx->chunk_key, 0, sizeof(ctx->chunk_key));
     memset(&ctx->d, 0, sizeof(ctx->d));
     C4Dev &d = ctx->d;
     // a warp starts no further descent in a NET pass after this many SM cycles (bounds the tail of the pass; 0 = off)
@@ -622,6 +627,7 @@ extern "C" int c4_ctx_destroy(c4_ctx *ctx)
 {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
+    for (int i = 0; i < 2; i++) if (ctx->chunk_graph[i]) cudaGraphExecDestroy(ctx->chunk_graph[i]);
     for (void *p : ctx->allocs) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) {
@@ -714,6 +720,16 @@ extern "C" int c4_ctx_set_rng(c4_ctx *ctx, int mode, uint64_t seed, double *nois
 int c4_net_forward_ex(c4_net *net, const uint64_t *c0, const uint64_t *c1, int64_t n, const int32_t *count, float *out,
                       void *stream, int max_ctas);
 
+// a NET self-play pass ends once this many games of the pool wait (stop_frac of the live games; steps of 64 so that the
+// captured launch graphs survive the slow decline of the live games in the drain of a generation)
+static int pass_stop_count(const c4_ctx *ctx, int n_games)
+{
+    if (ctx->stop_frac <= 0.0) return 0;
+    const long long live = std::min<long long>(ctx->live_games, (long long)n_games);
+    const int stop = std::max(1, (int)(ctx->stop_frac * (double)live));
+    return stop > 64 ? stop & ~63 : stop;
+}
+
 // one tree pass over games [g0, g0 + n_games) of pool `pool`
 template <bool SP>
 static int launch_advance_pool(c4_ctx *ctx, int mode, int g0, int n_games, int pool, int parity, int budget, cudaStream_t s)
@@ -724,8 +740,7 @@ static int launch_advance_pool(c4_ctx *ctx, int mode, int g0, int n_games, int p
     case C4_EVAL_EXTERNAL: k_advance<C4_EVAL_EXTERNAL, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, 0LL, 0); break;
     case C4_EVAL_CENTRE: k_advance<C4_EVAL_CENTRE, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, 0LL, 0); break;
     case C4_EVAL_NET: {
-        long long live = std::min<long long>(ctx->live_games, (long long)n_games);
-        int stop = (SP && ctx->stop_frac > 0.0) ? std::max(1, (int)(ctx->stop_frac * (double)live)) : 0;
+        const int stop = SP ? pass_stop_count(ctx, n_games) : 0;
         k_advance<C4_EVAL_NET, SP><<<blocks, threads, 0, s>>>(ctx->d, g0, n_games, pool, parity, budget, ctx->cycle_limit, stop);
         break;
     }
@@ -914,9 +929,11 @@ extern "C" int c4_search_export_tree(c4_ctx *ctx, int32_t game, void *nodes_out,
 // tree pass of one half overlaps the network launch of the other; the network launch is capped at net_ctas CTAs so
 // the tree blocks find free SMs.
 static int selfplay_passes(c4_ctx *ctx, int eval_kind, int n_passes, cudaStream_t s, int sample_every = 0,
-                           int *n_sampled = nullptr, int first_sample = 0)
+                           int *n_sampled = nullptr, int first_sample = 0, bool capturing = false)
 {
     int rc, ns = first_sample;
+    // (inside a stream capture an event that is read from the host afterwards must be recorded as an external one)
+    const unsigned ev_flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
     const bool two = ctx->n_pools == 2 && eval_kind == C4_EVAL_NET;
     if (two) {
         C4_CUDA(cudaEventRecord(ctx->ev_fork, s));
@@ -925,15 +942,15 @@ static int selfplay_passes(c4_ctx *ctx, int eval_kind, int n_passes, cudaStream_
     for (int k = 0; k < n_passes; k++) {
         const bool sample = sample_every > 0 && (k % sample_every) == sample_every / 2 && ns < N_SAMPLES;
         if (!two) {
-            if (sample) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns], s));
+            if (sample) C4_CUDA(cudaEventRecordWithFlags(ctx->eva[2 * ns], s, ev_flags));
             if (eval_kind == C4_EVAL_CENTRE) {
                 if ((rc = launch_advance<true>(ctx, C4_EVAL_CENTRE, ctx->max_games, 512, s))) return rc;
-                if (sample) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], s));
+                if (sample) C4_CUDA(cudaEventRecordWithFlags(ctx->eva[2 * ns + 1], s, ev_flags));
             } else {
                 if ((rc = launch_advance<true>(ctx, C4_EVAL_NET, ctx->max_games, ctx->budget_net, s))) return rc;
-                if (sample) { C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], s)); C4_CUDA(cudaEventRecord(ctx->evs[2 * ns], s)); }
+                if (sample) { C4_CUDA(cudaEventRecordWithFlags(ctx->eva[2 * ns + 1], s, ev_flags)); C4_CUDA(cudaEventRecordWithFlags(ctx->evs[2 * ns], s, ev_flags)); }
                 if ((rc = run_net(ctx, s))) return rc;
-                if (sample) C4_CUDA(cudaEventRecord(ctx->evs[2 * ns + 1], s));
+                if (sample) C4_CUDA(cudaEventRecordWithFlags(ctx->evs[2 * ns + 1], s, ev_flags));
             }
         } else {
             for (int p = 0; p < 2; p++) {
@@ -942,13 +959,13 @@ static int selfplay_passes(c4_ctx *ctx, int eval_kind, int n_passes, cudaStream_
                 pool_range(ctx, p, &g0, &n);
                 ctx->pool_parity[p] ^= 1;
                 const bool smp = sample && p == 0;
-                if (smp) C4_CUDA(cudaEventRecord(ctx->eva[2 * ns], ps));
+                if (smp) C4_CUDA(cudaEventRecordWithFlags(ctx->eva[2 * ns], ps, ev_flags));
                 if ((rc = launch_advance_pool<true>(ctx, C4_EVAL_NET, g0, n, p, ctx->pool_parity[p], ctx->budget_net, ps))) return rc;
-                if (smp) { C4_CUDA(cudaEventRecord(ctx->eva[2 * ns + 1], ps)); C4_CUDA(cudaEventRecord(ctx->evs[2 * ns], ps)); }
+                if (smp) { C4_CUDA(cudaEventRecordWithFlags(ctx->eva[2 * ns + 1], ps, ev_flags)); C4_CUDA(cudaEventRecordWithFlags(ctx->evs[2 * ns], ps, ev_flags)); }
                 if ((rc = c4_net_forward_ex(ctx->net, (const uint64_t *)(ctx->d.leaf_c0 + g0), (const uint64_t *)(ctx->d.leaf_c1 + g0),
                                             n, &ctx->d.ctr->leaf_count[p][ctx->pool_parity[p]], ctx->net_out + (size_t)g0 * 8, ps,
                                             ctx->net_ctas))) return rc;
-                if (smp) C4_CUDA(cudaEventRecord(ctx->evs[2 * ns + 1], ps));
+                if (smp) C4_CUDA(cudaEventRecordWithFlags(ctx->evs[2 * ns + 1], ps, ev_flags));
             }
         }
         if (sample) ns++;
@@ -960,6 +977,49 @@ static int selfplay_passes(c4_ctx *ctx, int eval_kind, int n_passes, cudaStream_
         }
     }
     if (n_sampled) *n_sampled = ns;
+    return 0;
+}
+
+// One chunk of 64 lock-step passes.  With one pool and the network evaluator the 128 launches are replayed from a CUDA
+// graph captured the first time (and again whenever a launch parameter changes: the stop count follows the number of
+// live games in the drain of a generation, the kernel arguments hold the context's device pointers and RNG settings): the
+// launches then follow each other on the device without host work in between.  C4_NO_GRAPH=1 keeps the plain launches.
+static int selfplay_chunk(c4_ctx *ctx, int eval_kind, cudaStream_t s, bool sampled = false)
+{
+    static const bool no_graph = getenv("C4_NO_GRAPH") != nullptr;
+    const bool two = ctx->n_pools == 2 && eval_kind == C4_EVAL_NET;
+    int ns = 0;
+    if (no_graph || two || eval_kind != C4_EVAL_NET || ctx->parity != 0)
+        return selfplay_passes(ctx, eval_kind, 64, s, sampled ? 64 : 0, &ns, 0);
+    const int gi = sampled ? 1 : 0;
+    const int stop = pass_stop_count(ctx, ctx->max_games);
+    // everything the captured kernel arguments depend on (C4Dev is passed by value)
+    unsigned long long h = 1469598103934665603ULL;
+    const unsigned char *raw = reinterpret_cast<const unsigned char *>(&ctx->d);
+    for (size_t i = 0; i < sizeof(C4Dev); i++) h = (h ^ raw[i]) * 1099511628211ULL;
+    const unsigned long long key[4] = {h, (unsigned long long)stop | ((unsigned long long)ctx->budget_net << 32),
+                                       (unsigned long long)ctx->cycle_limit, c4_net_uid(ctx->net)};
+    // capture and replay on an internal stream (the caller's may be the legacy default stream, which cannot be captured),
+    // forked from / joined to the caller's stream with events
+    cudaStream_t cs = ctx->pool_stream[0];
+    if (!ctx->chunk_graph[gi] || memcmp(key, ctx->chunk_key[gi], sizeof(key))) {
+        if (ctx->chunk_graph[gi]) { cudaGraphExecDestroy(ctx->chunk_graph[gi]); ctx->chunk_graph[gi] = nullptr; }
+        cudaGraph_t g = nullptr;
+        C4_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        int rc = selfplay_passes(ctx, eval_kind, 64, cs, sampled ? 64 : 0, &ns, 0, true);
+        cudaError_t e = cudaStreamEndCapture(cs, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        C4_CUDA(e);
+        e = cudaGraphInstantiate(&ctx->chunk_graph[gi], g, 0);
+        cudaGraphDestroy(g);
+        C4_CUDA(e);
+        memcpy(ctx->chunk_key[gi], key, sizeof(key));
+    }
+    C4_CUDA(cudaEventRecord(ctx->ev_fork, s));
+    C4_CUDA(cudaStreamWaitEvent(cs, ctx->ev_fork, 0));
+    C4_CUDA(cudaGraphLaunch(ctx->chunk_graph[gi], cs));
+    C4_CUDA(cudaEventRecord(ctx->ev_join[0], cs));
+    C4_CUDA(cudaStreamWaitEvent(s, ctx->ev_join[0], 0));
     return 0;
 }
 
@@ -1000,7 +1060,7 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
     } else {
         ctx->live_games = std::min<long long>(n_games, ctx->max_games);
         for (long long it = 0;; it++) {
-            if ((rc = selfplay_passes(ctx, eval_kind, 64, s))) return rc;
+            if ((rc = selfplay_chunk(ctx, eval_kind, s))) return rc;
             if ((rc = read_counters(ctx, &c, s))) return rc;
             if ((rc = check_device_errors(c))) return rc;
             ctx->live_games = std::max<long long>(1, std::min<long long>(n_games - (long long)c.games_finished, ctx->max_games));
@@ -1150,21 +1210,31 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     ctx->last_tree_ms = ctx->last_net_ms = 0.f;
     ctx->last_passes = 0;
     int n_sampled = 0;
+    float tree_sum = 0.f, net_sum = 0.f;
     if (fused) {
         if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, games_goal, max_ms, s))) return rc;
         ctx->last_launches += 1;
     } else {
         // lock-step engine: chunks of passes with a host look at the counters in between
         for (long long it = 0;; it++) {
-            // one pass of every chunk is bracketed with CUDA events (<= 64 samples over the call): launch durations of the
+            // one pass of some chunks is bracketed with CUDA events (<= 64 samples over the call): launch durations of the
             // tree pass and the network kernel for the roofline figures
-            if ((rc = selfplay_passes(ctx, eval_kind, 64, s, it < N_SAMPLES ? 64 : 0, &n_sampled, n_sampled))) return rc;
+            // (every 8th chunk, up to 64 of them, carries event records around the launches of its pass 32)
+            const bool sampled = (it & 7) == 3 && n_sampled < N_SAMPLES;
+            if ((rc = selfplay_chunk(ctx, eval_kind, s, sampled))) return rc;
             ctx->last_launches += 64 * (eval_kind == C4_EVAL_NET ? 2 * ctx->n_pools : 1);
             ctx->last_passes += 64;
             C4_CUDA(cudaEventRecord(ctx->ev1, s));
             if ((rc = read_counters(ctx, &c, s))) return rc;
             float ms = 0.f;
             C4_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            if (sampled) {
+                float t = 0.f;
+                C4_CUDA(cudaEventElapsedTime(&t, ctx->eva[0], ctx->eva[1]));
+                tree_sum += t;
+                if (eval_kind == C4_EVAL_NET) { C4_CUDA(cudaEventElapsedTime(&t, ctx->evs[0], ctx->evs[1])); net_sum += t; }
+                n_sampled++;
+            }
             if (games_goal && c.games_finished >= games_goal) break;
             if (max_ms > 0.0 && ms >= max_ms) break;
             C4_REQUIRE(it < (1LL << 24), "c4_selfplay_stream: did not terminate");
@@ -1179,15 +1249,8 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     float ms = 0.f;
     C4_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (!fused && n_sampled > 0) {
-        float nsum = 0.f, tsum = 0.f;
-        for (int i = 0; i < n_sampled; i++) {
-            float t = 0.f;
-            if (eval_kind == C4_EVAL_NET) { C4_CUDA(cudaEventElapsedTime(&t, ctx->evs[2 * i], ctx->evs[2 * i + 1])); nsum += t; }
-            C4_CUDA(cudaEventElapsedTime(&t, ctx->eva[2 * i], ctx->eva[2 * i + 1]));
-            tsum += t;
-        }
-        ctx->last_tree_ms = tsum / n_sampled;
-        ctx->last_net_ms = nsum / n_sampled;
+        ctx->last_tree_ms = tree_sum / n_sampled;
+        ctx->last_net_ms = net_sum / n_sampled;
     }
     if (evals) *evals = (int64_t)(after[0] - before[0]);
     if (positions) *positions = (int64_t)(after[1] - before[1]);

@@ -112,7 +112,8 @@ struct FzParams {
 struct FzCtl {
     unsigned q_tail, q_head;            // leaf ring: requests reserved / consumed
     int quit, abort, stop, tree_exited;
-    int strip_nb, pad0;
+    int strip_nb;
+    int wake;                           // bumped whenever a game becomes runnable or a flag changes: idle tree warps poll this one word
     int strip_game[16];
     u64 strip_c0[16], strip_c1[16];
     unsigned q_seq[FZ_QCAP];            // slot number + 1 once the entry is complete
@@ -259,6 +260,7 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, FzCtl *S, int g, int
     if (lane == 0) {
         __threadfence_block();
         st_vol(&S->status[gl], st);                                       // WAIT must be visible before the request is
+        if (st == ST_IDLE || st == ST_DONE) atomicAdd(&S->wake, 1);       // idle warps re-check whether anything is left
         if (request) {
             S->t_push[gl] = clock64();
             const unsigned slot = atomicAdd(&S->q_tail, 1u);
@@ -475,17 +477,17 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
             if (e == 0) {
                 const unsigned head = S->q_head;                             // written by this warp only
                 if (lane == 0 && !ld_vol(&S->stop)) {
-                    if (P.stop_games && __ldcg(&dg.ctr->games_finished) >= P.stop_games) st_vol(&S->stop, 1);
-                    if (P.stop_ns && fz_globaltimer() - t_begin > P.stop_ns) st_vol(&S->stop, 1);
+                    if (P.stop_games && __ldcg(&dg.ctr->games_finished) >= P.stop_games) { st_vol(&S->stop, 1); atomicAdd(&S->wake, 1); }
+                    if (P.stop_ns && fz_globaltimer() - t_begin > P.stop_ns) { st_vol(&S->stop, 1); atomicAdd(&S->wake, 1); }
                 }
                 int k = 0;
                 for (uint32_t it = 1;; it++) {
                     if (*reinterpret_cast<volatile unsigned *>(&S->q_tail) == head) {     // nothing requested: one word read
                         if (ld_vol(&S->quit) | ld_vol(&S->abort)) break;
-                        if ((it & 1023u) == 0u && lane == 0 && *reinterpret_cast<const volatile int *>(P.host_abort)) st_vol(&S->abort, 1);
+                        if ((it & 1023u) == 0u && lane == 0 && *reinterpret_cast<const volatile int *>(P.host_abort)) { st_vol(&S->abort, 1); atomicAdd(&S->wake, 1); }
                         if ((it & 31u) == 0u && lane == 0 && !ld_vol(&S->stop)) {
-                            if (P.stop_games && __ldcg(&dg.ctr->games_finished) >= P.stop_games) st_vol(&S->stop, 1);
-                            if (P.stop_ns && fz_globaltimer() - t_begin > P.stop_ns) st_vol(&S->stop, 1);
+                            if (P.stop_games && __ldcg(&dg.ctr->games_finished) >= P.stop_games) { st_vol(&S->stop, 1); atomicAdd(&S->wake, 1); }
+                            if (P.stop_ns && fz_globaltimer() - t_begin > P.stop_ns) { st_vol(&S->stop, 1); atomicAdd(&S->wake, 1); }
                         }
                         __nanosleep(it > 32u ? 400 : 100);
                         continue;
@@ -581,7 +583,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
                     if (lane == 0) dg.ctr->net_nonfinite = 1;
                 }
                 __syncwarp();
-                if (lane == 0) { S->t_ans[gl] = clock64(); __threadfence_block(); st_vol(&S->status[gl], FZ_ANSWERED); }
+                if (lane == 0) { S->t_ans[gl] = clock64(); __threadfence_block(); st_vol(&S->status[gl], FZ_ANSWERED); atomicAdd(&S->wake, 1); }
             }
             if (e == 0) {
                 FZ_PROF(0, 1); FZ_PROF(1, nb); FZ_PROF(2, t_d1 - t_d0); FZ_PROF(3, t_d2 - t_d1); FZ_PROF(4, t_d3 - t_d2);
@@ -598,6 +600,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
         long long idle_t0 = 0;
         uint32_t idle_it = 0;
         for (; tw < P.tree_warps;) {
+            const int seen = ld_vol(&S->wake);                             // read BEFORE the scan: no wake-up is lost
             const int aborting = ld_vol(&S->abort);
             const int stop = ld_vol(&S->stop) | aborting;
             FZ_DBG(0x400000);
@@ -640,15 +643,23 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
             }
             if (n_wait == 0 && n_ans == 0 && (stop || n_ready == 0)) break;    // nothing left that needs this warp
             FZ_DBG(0x430000 | (n_wait << 8) | n_ans);
+            // idle: wait until something is published.  ONE shared-memory word is polled (an ncu instruction profile of the
+            // first version, which re-scanned the status array every 0.25-2 us, showed 45 % of the kernel's executed
+            // instructions in that loop -- taken from the tower on the same SM).
             if (!idle) { idle = true; idle_t0 = clock64(); idle_it = 0; }
-            else if ((++idle_it & 1023u) == 0u) {
-                if (lane == 0 && *reinterpret_cast<const volatile int *>(P.host_abort)) st_vol(&S->abort, 1);
-                if (clock64() - idle_t0 > FZ_WATCHDOG_CYCLES) {
-                    if (lane == 0) { dg.ctr->engine_error = 1; st_vol(&S->abort, 1); }
-                    break;
+            bool dead = false;
+            while (ld_vol(&S->wake) == seen) {
+                __nanosleep(idle_it < 16u ? 100 : 400);
+                if ((++idle_it & 1023u) == 0u) {
+                    if (lane == 0 && *reinterpret_cast<const volatile int *>(P.host_abort)) { st_vol(&S->abort, 1); atomicAdd(&S->wake, 1); }
+                    if (clock64() - idle_t0 > FZ_WATCHDOG_CYCLES) {
+                        if (lane == 0) { dg.ctr->engine_error = 1; st_vol(&S->abort, 1); atomicAdd(&S->wake, 1); }
+                        dead = true;
+                        break;
+                    }
                 }
             }
-            __nanosleep(idle_it < 8u ? 250 : (idle_it < 64u ? 1000 : 2000));  // back off: idle warps must not clog the MIO queue
+            if (dead) break;
         }
         __syncwarp();
         FZ_DBG(0x4ff000);

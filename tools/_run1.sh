@@ -1,4 +1,5 @@
-export C4_FZ_TIMEOUT_S=120
-timeout 300 python -m pytest tests/test_gpu_fused.py tests/test_gpu_selfplay.py tests/test_gpu_edges.py -x -q 2>&1 | tail -3
-timeout 400 python bench.py --no-cpu --no-extras > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_default.err
-python tools/show_bench.py gpurun_out/bench_default.json
+export C4_FZ_TIMEOUT_S=60
+timeout 200 python tools/fused_check.py --quick 2>&1 | tail -3
+for n in 256 1024 2048 4096; do C4_ENGINE=fused timeout 100 python tools/fused_prof.py $n $n 2>&1 | tail -1 | cut -c1-120; done
+C4_ENGINE=fused timeout 100 python tools/fused_prof.py 4096 4096 --warm 2>&1 | tail -3
+timeout 300 python -m pytest tests/test_gpu_fused.py tests/test_gpu_selfplay.py -x -q 2>&1 | tail -3

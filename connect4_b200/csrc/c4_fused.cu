@@ -54,8 +54,7 @@
 #include <chrono>
 #include <thread>
 
-#include "c4_tree.cuh"
-#include "c4_tc.cuh"
+#include "c4_fz.cuh"
 
 // Strip geometry of the tower inside the fused engine (c4_tc.cuh: TcC<32> is the batch kernel's).  The engine is bound by
 // the tree warps, not by the tower (profiles/README.md), so the tower is kept small: strips of FZ_NB boards, FZ_GROUPS
@@ -95,8 +94,6 @@ template <class K> struct FzW {
 #define FZ_EPI_BAR() asm volatile("bar.sync 1, %0;\n" :: "n"(32 * W::EPI_WARPS) : "memory")
 #define FZ_GC_MAX 128                                     // game slots per CTA
 #define FZ_QCAP 128                                       // leaf ring entries (>= FZ_GC_MAX: one pending leaf per game)
-#define FZ_WATCHDOG_CYCLES 6000000000LL                   // ~3 s without a runnable game while games wait = protocol bug
-enum { FZ_ANSWERED = 5, FZ_RUNNING = 6 };
 
 struct FzParams {
     int n_slots;                        // game slots of the pool
@@ -131,133 +128,14 @@ template <class K> __host__ __device__ constexpr int fz_ctl_off(int R) { return 
 template <class K> __host__ __device__ constexpr int fz_tab_off(int R) { return (fz_ctl_off<K>(R) + (int)sizeof(FzCtl) + 15) & ~15; }
 template <class K> __host__ __device__ constexpr int fz_total(int R, int table_entries) { return fz_tab_off<K>(R) + 3 * 8 * table_entries; }
 
-__device__ __forceinline__ unsigned long long fz_globaltimer()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
-__device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
-
-// mbarrier wait that gives up when the CTA aborts (watchdog); false = aborted
-__device__ __forceinline__ bool fz_wait(uint32_t bar, uint32_t parity, const int *abort)
-{
-    if (mbar_try(bar, parity)) return true;
-    for (uint32_t it = 1;; it++) {
-        if (mbar_try(bar, parity)) return true;
-        if (it > 16u) __nanosleep(it > 256u ? 200 : 20);                  // an idle tower must not clog the SM's MIO queue
-        if ((it & 63u) == 0u && ld_vol(abort)) return false;
-    }
-}
-
-// Run game `gl` of this CTA (global slot g) until it needs the network, finishes, or the engine is stopping.
-// Same state machine as k_advance (c4_search.cu), minus the pass structure.
-template <bool SELFPLAY>
-__device__ __forceinline__ void fz_run_game(const C4Dev &d, FzCtl *S, int g, int gl, int st, int lane)
-{
-    Game G;
-    G.g = g; G.lane = lane;
-    G.gp = d.pool + (size_t)g * d.blocks_per_game * C4_SLOTS;
-    G.n_blocks = d.n_blocks[g];
-    G.sims_done = d.sims_done[g];
-    G.c0 = d.root_c0[g]; G.c1 = d.root_c1[g];
-    G.age = c4_age(G.c0, G.c1);
-
-    C4_DEV_ASSERT(gl >= 0 && gl < FZ_GC_MAX && G.n_blocks >= 1 && G.n_blocks <= d.blocks_per_game && G.sims_done <= d.sims);
-    if (st == FZ_ANSWERED) {
-        // consume the evaluator's answer for the pending leaf (oinkoink/mcts.py:129-135), then backpropagate
-        const uint32_t node = (uint32_t)d.pending_node[g];
-        const int plen = d.path_len[g];
-        C4_DEV_ASSERT(plen >= 0 && plen <= PATH_CAP && node < (uint32_t)G.n_blocks * C4_SLOTS);
-        const u64 lc0 = d.pend_c0[g], lc1 = d.pend_c1[g];
-        const bool is_root = (plen == 0);
-        const float ov = (lane < 8) ? S->ans[gl][lane] : 0.f;
-        if (d.memo) memo_insert(d, lc0, lc1, ov, lane);
-        const double value = (double)__shfl_sync(FULL, ov, 7);
-        apply_eval<true>(d, G, node, lc0, lc1, c4_age(lc0, lc1), value, 0.0, (lane < 7) ? ov : 0.f, is_root,
-                         SELFPLAY ? d.ply[g] : 0);
-        if (!is_root) {
-            const uint32_t plo = (lane < plen) ? d.path[(size_t)g * PATH_CAP + lane] : 0u;
-            const uint32_t phi = (lane + 32 < plen) ? d.path[(size_t)g * PATH_CAP + lane + 32] : 0u;
-            backup(G, plo, phi, plen - 1, value);
-            G.sims_done++;
-        }
-        st = ST_READY;
-    }
-
-    bool request = false;
-    u64 rc0 = 0, rc1 = 0;
-    uint32_t rnode = 0u, rlo = 0u, rhi = 0u;
-    int rlen = 0;
-    for (;;) {
-        if (ld_vol(&S->stop)) break;                                     // the engine is draining: park the game as it is
-        if (st == ST_NEWROOT) {
-            // Tree(board) + evaluate root (oinkoink/mcts.py:98-105): fresh pool, root = node 0 of block 0
-            G.n_blocks = 1;
-            G.sims_done = 0;
-            if (lane == 0) { st_a(G.gp, 0.0, 0u, C4_META_EXISTS); st_b(G.gp, 0.0, 0.0); }
-            __syncwarp();
-            float ov;
-            if (d.memo && memo_lookup(d, G.c0, G.c1, ov, lane)) {
-                apply_eval<true>(d, G, 0u, G.c0, G.c1, G.age, (double)__shfl_sync(FULL, ov, 7), 0.0, (lane < 7) ? ov : 0.f,
-                                 true, SELFPLAY ? d.ply[g] : 0);
-                if (lane == 0) d.stat_hits[g] += 1ULL;
-                st = ST_READY;
-            } else {
-                request = true; rc0 = G.c0; rc1 = G.c1; rnode = 0u; rlen = 0;
-                break;
-            }
-        }
-        if (G.sims_done >= d.sims) {
-            if (!SELFPLAY) {
-                st = ST_DONE;
-                if (lane == 0) atomicAdd(&d.ctr->n_done, 1ULL);
-                break;
-            }
-            st = finalize_move(d, G);
-            if (st == ST_IDLE) break;
-            continue;
-        }
-        const Leaf L = descend(d, G);
-        if (L.meta & C4_META_TERMINAL) {
-            // terminal branch of evaluate_node (mcts.py:125-128) + backpropagate
-            backup(G, L.path_lo, L.path_hi, L.depth + 1, c4_meta_value(L.meta));
-            G.sims_done++;
-            continue;
-        }
-        if (d.memo) {
-            float ov;
-            if (memo_lookup(d, L.c0, L.c1, ov, lane)) {
-                const double value = (double)__shfl_sync(FULL, ov, 7);
-                apply_eval<true>(d, G, L.node, L.c0, L.c1, L.age, value, 0.0, (lane < 7) ? ov : 0.f, false, 0);
-                backup(G, L.path_lo, L.path_hi, L.depth, value);
-                if (lane == 0) d.stat_hits[g] += 1ULL;
-                G.sims_done++;
-                continue;
-            }
-        }
-        request = true; rc0 = L.c0; rc1 = L.c1; rnode = L.node; rlen = L.depth + 1; rlo = L.path_lo; rhi = L.path_hi;
-        break;
-    }
-    if (request) st = ST_WAIT;
-    if (lane == 0) {
-        d.status[g] = st;
-        d.n_blocks[g] = G.n_blocks;
-        d.sims_done[g] = G.sims_done;
-        d.root_c0[g] = G.c0; d.root_c1[g] = G.c1;
-        if (request) {
-            d.pend_c0[g] = rc0; d.pend_c1[g] = rc1;
-            d.pending_node[g] = (int)rnode; d.path_len[g] = rlen;
-            d.stat_evals[g] += 1ULL;
-        }
-    }
-    if (request) {
-        if (lane < rlen) d.path[(size_t)g * PATH_CAP + lane] = rlo;
-        if (lane + 32 < rlen) d.path[(size_t)g * PATH_CAP + lane + 32] = rhi;
-    }
-    __syncwarp();
-    if (lane == 0) {
+// the fused engine's port: answers and the leaf ring live in the CTA's shared memory
+struct FzPort {
+    static constexpr int GC_MAX = FZ_GC_MAX;
+    FzCtl *S;
+    __device__ __forceinline__ int stopping() const { return ld_vol(&S->stop); }
+    __device__ __forceinline__ float answer(int, int gl, int lane) const { return (lane < 8) ? S->ans[gl][lane] : 0.f; }
+    __device__ __forceinline__ void publish(int, int gl, int st, bool request, u64 rc0, u64 rc1) const
+    {
         __threadfence_block();
         st_vol(&S->status[gl], st);                                       // WAIT must be visible before the request is
         if (st == ST_IDLE || st == ST_DONE) atomicAdd(&S->wake, 1);       // idle warps re-check whether anything is left
@@ -271,8 +149,7 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, FzCtl *S, int g, int
             *reinterpret_cast<volatile unsigned *>(&S->q_seq[idx]) = slot + 1u;
         }
     }
-    __syncwarp();
-}
+};
 
 template <typename OP, class K, bool SELFPLAY>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
@@ -633,7 +510,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
                     FZ_DBG(0x410000 | (s << 8) | cand);
                     const long long t_r0 = clock64();
                     if (s == FZ_ANSWERED) { FZ_PROF(8, 1); FZ_PROF(9, S->t_ans[cand] - S->t_push[cand]); FZ_PROF(10, t_r0 - S->t_ans[cand]); }
-                    fz_run_game<SELFPLAY>(d, S, g0 + cand, cand, s, lane);
+                    fz_run_game<SELFPLAY>(d, FzPort{S}, g0 + cand, cand, s, lane);
                     FZ_PROF(6, 1); FZ_PROF(7, clock64() - t_r0);
                     FZ_DBG(0x420000 | cand);
                     idle = false;

@@ -39,6 +39,10 @@
 bool c4_fused_eligible(const c4_net *net, int max_games, long long live_games);
 int c4_fused_run(const C4Dev &d, const c4_net *net, int max_games, int simulations, bool selfplay,
                  unsigned long long stop_games, double stop_ms, cudaStream_t stream);
+// c4_split.cu: the persistent engine with tree CTAs and tower CTAs on separate SMs (same contract)
+bool c4_split_eligible(const c4_net *net, int max_games, long long live_games);
+int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulations, bool selfplay,
+                 unsigned long long stop_games, double stop_ms, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ the pass kernel
 // A game needs an evaluation that is not in the memo: park the leaf, then either append it to the pool's batch (ST_WAIT) or,
@@ -848,9 +852,21 @@ static int check_device_errors(const C4Counters &c)
     return 0;
 }
 
+// a persistent engine (split or fused) instead of lock-step passes for `live_games` games in flight?
 static bool use_fused(const c4_ctx *ctx, int eval_kind, long long live_games)
 {
-    return eval_kind == C4_EVAL_NET && c4_fused_eligible(ctx->net, ctx->max_games, live_games);
+    return eval_kind == C4_EVAL_NET &&
+           (c4_split_eligible(ctx->net, ctx->max_games, live_games) || c4_fused_eligible(ctx->net, ctx->max_games, live_games));
+}
+
+// one persistent launch (pair) over the pool; *engine = 3 (split) or 2 (fused)
+static int persistent_run(c4_ctx *ctx, long long live_games, bool selfplay, unsigned long long stop_games, double stop_ms,
+                          cudaStream_t s, int *engine = nullptr)
+{
+    const bool split = c4_split_eligible(ctx->net, ctx->max_games, live_games);
+    if (engine) *engine = split ? 3 : 2;
+    return split ? c4_split_run(ctx->d, ctx->net, ctx->max_games, ctx->cfg.simulations, selfplay, stop_games, stop_ms, s)
+                 : c4_fused_run(ctx->d, ctx->net, ctx->max_games, ctx->cfg.simulations, selfplay, stop_games, stop_ms, s);
 }
 
 extern "C" int c4_search_run(c4_ctx *ctx, int eval_kind, void *stream)
@@ -870,7 +886,7 @@ extern "C" int c4_search_run(c4_ctx *ctx, int eval_kind, void *stream)
     C4Counters c;
     if (use_fused(ctx, eval_kind, ctx->n_search)) {
         // every search of the batch in ONE persistent launch (c4_fused.cu)
-        if ((rc = c4_fused_run(ctx->d, ctx->net, ctx->max_games, ctx->cfg.simulations, false, 0ULL, 0.0, s))) return rc;
+        if ((rc = persistent_run(ctx, ctx->n_search, false, 0ULL, 0.0, s))) return rc;
         if ((rc = read_counters(ctx, &c, s))) return rc;
         if ((rc = check_device_errors(c))) return rc;
         C4_REQUIRE((long long)c.n_done >= ctx->n_search, "c4_search_run: the fused engine left searches unfinished");
@@ -1053,7 +1069,7 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
     if (use_fused(ctx, eval_kind, std::min<long long>(n_games, ctx->max_games))) {
         // the whole generation in ONE persistent launch: slots go idle when no game is left to seed, CTAs leave when
         // all their slots are idle (c4_fused.cu)
-        if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, 0ULL, 0.0, s))) return rc;
+        if ((rc = persistent_run(ctx, std::min<long long>(n_games, ctx->max_games), true, 0ULL, 0.0, s))) return rc;
         if ((rc = read_counters(ctx, &c, s))) return rc;
         if ((rc = check_device_errors(c))) return rc;
         C4_REQUIRE((long long)c.games_finished >= n_games, "c4_selfplay_run: the fused engine left games unfinished");
@@ -1077,7 +1093,7 @@ extern "C" int c4_selfplay_run(c4_ctx *ctx, int eval_kind, int64_t n_games, int6
                         if ((rc = launch_advance_pool<true>(ctx, eval_kind, g0, n, p, ctx->pool_parity[p], -1, s))) return rc;
                     }
                 } else if ((rc = launch_advance<true>(ctx, eval_kind, ctx->max_games, -1, s))) return rc;
-                if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, 0ULL, 0.0, s))) return rc;
+                if ((rc = persistent_run(ctx, ctx->live_games, true, 0ULL, 0.0, s))) return rc;
                 if ((rc = read_counters(ctx, &c, s))) return rc;
                 if ((rc = check_device_errors(c))) return rc;
                 C4_REQUIRE((long long)c.games_finished >= n_games, "c4_selfplay_run: the fused engine left games unfinished");
@@ -1182,7 +1198,7 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     C4_CUDA(cudaSetDevice(ctx->device));
     C4Dev &d = ctx->d;
     const bool fused = use_fused(ctx, eval_kind, ctx->max_games);
-    const int eng = fused ? 2 : 1;
+    const int eng = fused ? (c4_split_eligible(ctx->net, ctx->max_games, ctx->max_games) ? 3 : 2) : 1;
     int rc;
     if (reset || !ctx->pool_fresh || ctx->pool_engine != eng) {
         d.n_games_target = (long long)1 << 60;
@@ -1212,8 +1228,8 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     int n_sampled = 0;
     float tree_sum = 0.f, net_sum = 0.f;
     if (fused) {
-        if ((rc = c4_fused_run(d, ctx->net, ctx->max_games, ctx->cfg.simulations, true, games_goal, max_ms, s))) return rc;
-        ctx->last_launches += 1;
+        if ((rc = persistent_run(ctx, ctx->max_games, true, games_goal, max_ms, s))) return rc;
+        ctx->last_launches += eng == 3 ? 2 : 1;
     } else {
         // lock-step engine: chunks of passes with a host look at the counters in between
         for (long long it = 0;; it++) {

@@ -1,0 +1,651 @@
+// c4_split.cu -- the split persistent self-play engine: tree CTAs and tower CTAs on SEPARATE SMs, one leaf ring in HBM.
+//
+// What it replaces: the same free-running runtime of the reference as the fused engine (game threads that never wait for
+// an unrelated game, oinkoink/neural/game_pool.py:15-49; an inference server that batches whatever requests are there,
+// oinkoink/neural/inference_server.py:37-63).  The fused engine (c4_fused.cu) puts tree warps AND a tower on every SM; its
+// ncu profile shows the price: the two roles share the SM's issue slots, registers (64 per thread for both) and L1, the
+// tower runs 1,850 cycles per tile-layer instead of 950, strips are 9 boards.  Here every SM has ONE role:
+//   * k_sp_tree: n_tree CTAs x 1,024 threads.  31 tree warps run the CTA's own games exactly as in the fused engine
+//     (fz_run_game, c4_fz.cuh -- the same device functions as the lock-step pass, hence identical records); a leaf that
+//     misses the evaluation memo goes into ONE global leaf ring (32-byte entries in HBM / L2).  Warp 31 is the CTA's mail
+//     warp: it polls the answer tags of the CTA's waiting games (contiguous words, a few sectors per sweep), flips their
+//     status words in shared memory and keeps the stop / abort flags.  No tower here: ~3 KB of shared memory, the rest of
+//     the 228 KB is L1 for the node records.
+//   * k_sp_net: n_net CTAs x 576 threads = the batch kernel's tower (c4_net.cu: 16-board strips, two epilogue groups, 90
+//     registers, 200 KB of shared memory) as a server: the dispatcher (epilogue warp 0) claims the leading entries of the
+//     ring with one atomicCAS on the head -- whatever is there, up to a strip; no batching delay -- and the strip's answers
+//     go to net_out[game] followed by the game's answer tag.
+// The two kernels are launched on two streams and are co-resident by construction: every CTA of either kernel needs a
+// whole SM (64 K registers / 200 KB of shared memory) and n_tree + n_net <= number of SMs.  All cross-SM hand-offs are
+// polls of L2-resident words with a back-off; every wait is bounded (tree-warp watchdog -> abort flag -> both kernels
+// leave; host deadline through a mapped word), so a protocol bug ends in an error code, not in a hung device.
+//
+// Lock-free hand-offs (what a race checker would flag, and why each is safe):
+//   * ring entry: slot reserved with atomicAdd(q_tail); {c0, c1, game, tag} written; __threadfence(); seq = slot + 1.
+//     A consumer owns entries [head, head + k) after its CAS on q_head and spins on each entry's seq before it reads the
+//     rest.  Capacity (16,384) >= game slots and a game has at most one leaf pending, so a slot is not reused before its
+//     entry was read.
+//   * answer: 8 lanes store net_out[game][0..7], each fences, __syncwarp, then lane 0 stores ans_tag[game] = tag.  The
+//     mail warp sees the tag, fences, flips WAIT -> ANSWERED in shared memory; the tree warp that claims the game reads
+//     net_out with ld.global.cg (L2).  tag = the game's request number in this launch (never 0), so a stale tag of an
+//     earlier request never matches.
+//   * status words, stop / abort flags: as in the fused engine (c4_fused.cu).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <thread>
+
+#include "c4_fz.cuh"
+
+#define SP_QCAP 16384                                     // leaf ring entries (>= game slots of the pool)
+#define SP_GMAX 16384                                     // game slots the engine accepts
+#define SP_GC_MAX 256                                     // game slots per tree CTA
+#define SP_TREE_THREADS 1024
+#define SP_TREE_WARPS 31                                  // warps 0..30 run games, warp 31 is the mail warp
+#define SP_NB 16                                          // boards per strip (TcC<32>::NB)
+
+struct __align__(32) SpEntry {
+    u64 c0, c1;
+    int game;
+    unsigned tag;
+    unsigned seq;                       // slot number + 1 once the entry is complete
+    unsigned pad;
+};
+
+struct SpGlobal {
+    unsigned q_tail; unsigned pad0[31];
+    unsigned q_head; unsigned pad1[31];
+    int quit, abort, trees_exited; int pad2[29];
+    unsigned long long prof[32];
+    unsigned ans_tag[SP_GMAX];
+    SpEntry q[SP_QCAP];
+};
+
+struct SpParams {
+    int n_slots;                        // game slots of the pool
+    unsigned long long stop_games;      // leave once ctr->games_finished reaches this (0 = never)
+    unsigned long long stop_ns;         // leave after this much run time (0 = never)
+    const int *host_abort;              // mapped host word: non-zero = the host gave up waiting, leave at once
+    int prof;                           // accumulate cycle / event sums in SpGlobal::prof (C4_FZ_DEBUG)
+    int batch_ns;                       // a dispatcher that finds less than a strip waits up to this long for more
+};
+
+// tree CTA control block (shared memory)
+struct SpCtl {
+    int abort, stop, tree_exited, wake;
+    int status[SP_GC_MAX];              // ST_* / FZ_*: authoritative while the kernel runs
+    unsigned req[SP_GC_MAX];            // request number of the game's last leaf (= its answer tag)
+};
+
+__device__ __forceinline__ unsigned ld_volu(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
+__device__ __forceinline__ void st_volu(unsigned *p, unsigned v) { *reinterpret_cast<volatile unsigned *>(p) = v; }
+
+#define SP_PROF(i, v) do { if (P.prof) atomicAdd(&G->prof[i], (unsigned long long)(v)); } while (0)
+
+// the split engine's port: the answer comes from net_out in HBM (written by a tower CTA), the request goes to the global ring
+struct SpPort {
+    static constexpr int GC_MAX = SP_GC_MAX;
+    SpCtl *S;
+    SpGlobal *G;
+    const float *net_out;
+    __device__ __forceinline__ int stopping() const { return ld_vol(&S->stop); }
+    __device__ __forceinline__ float answer(int g, int, int lane) const
+    {
+        return (lane < 8) ? __ldcg(net_out + (size_t)g * 8 + lane) : 0.f;
+    }
+    __device__ __forceinline__ void publish(int g, int gl, int st, bool request, u64 rc0, u64 rc1) const
+    {
+        unsigned tag = 0u;
+        if (request) { tag = S->req[gl] + 1u; *reinterpret_cast<volatile unsigned *>(&S->req[gl]) = tag; }
+        __threadfence_block();
+        st_vol(&S->status[gl], st);                                       // WAIT (and its tag) visible before the request is
+        if (st == ST_IDLE || st == ST_DONE) atomicAdd(&S->wake, 1);       // idle warps re-check whether anything is left
+        if (request) {
+            const unsigned slot = atomicAdd(&G->q_tail, 1u);
+            SpEntry *e = &G->q[slot % SP_QCAP];
+            C4_DEV_ASSERT(slot - ld_volu(&G->q_head) < SP_QCAP);            // one pending leaf per game
+            e->c0 = rc0; e->c1 = rc1; e->game = g; e->tag = tag;
+            __threadfence();
+            st_volu(&e->seq, slot + 1u);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ tree CTAs
+template <bool SELFPLAY>
+__global__ void __launch_bounds__(SP_TREE_THREADS, 1)
+k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
+{
+    __shared__ SpCtl Sm;
+    SpCtl *S = &Sm;
+    const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    // this CTA's game slots
+    const int per = P.n_slots / (int)gridDim.x, extra = P.n_slots % (int)gridDim.x;
+    const int Gc = per + ((int)blockIdx.x < extra ? 1 : 0);
+    const int g0 = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
+
+    for (int i = threadIdx.x; i < (int)(sizeof(SpCtl) / 4); i += blockDim.x) reinterpret_cast<uint32_t *>(S)[i] = 0u;
+    __syncthreads();
+    // (a game the lock-step engine parked on another game's evaluation, ST_WAITMEMO, has applied nothing yet: it simply
+    //  descends to that leaf again)
+    for (int i = threadIdx.x; i < SP_GC_MAX; i += blockDim.x) {
+        const int st0 = (i < Gc) ? dg.status[g0 + i] : ST_IDLE;
+        S->status[i] = st0 == ST_WAITMEMO ? (int)ST_READY : st0;
+    }
+    __syncthreads();
+    const unsigned long long t_begin = fz_globaltimer();
+
+    if (warp == SP_TREE_WARPS) {
+        // ================= mail warp: answer tags of the waiting games -> status words; stop / abort flags
+        for (uint32_t it = 0;; it++) {
+            if (lane == 0 && (it & 7u) == 0u) {
+                if (!ld_vol(&S->stop)) {
+                    bool stop = false;
+                    if (P.stop_games && __ldcg(&dg.ctr->games_finished) >= P.stop_games) stop = true;
+                    if (P.stop_ns && fz_globaltimer() - t_begin > P.stop_ns) stop = true;
+                    if (stop) { st_vol(&S->stop, 1); atomicAdd(&S->wake, 1); }
+                }
+                if ((it & 8191u) == 0u && *reinterpret_cast<const volatile int *>(P.host_abort)) st_vol(&G->abort, 1);
+                if (!ld_vol(&S->abort) && ld_vol(&G->abort)) { st_vol(&S->abort, 1); atomicAdd(&S->wake, 1); }
+            }
+            int n_wait = 0;
+            for (int base = 0; base < Gc; base += 32) {
+                const int i = base + lane;
+                const bool w = i < Gc && ld_vol(&S->status[i]) == ST_WAIT;
+                bool hit = false;
+                if (w) {
+                    const unsigned tag = ld_volu(&S->req[i]);
+                    hit = ld_volu(&G->ans_tag[g0 + i]) == tag;
+                    if (hit) { __threadfence(); st_vol(&S->status[i], FZ_ANSWERED); }
+                }
+                n_wait += __popc(__ballot_sync(FULL, w));
+                if (__any_sync(FULL, hit) && lane == 0) { __threadfence_block(); atomicAdd(&S->wake, 1); }
+            }
+            if (ld_vol(&S->tree_exited) == SP_TREE_WARPS) break;
+            __nanosleep(n_wait ? 150 : 1000);
+        }
+        __syncwarp();
+        if (lane == 0 && atomicAdd(&G->trees_exited, 1) == (int)gridDim.x - 1) { __threadfence(); st_vol(&G->quit, 1); }
+    } else {
+        // ================= tree warps (the picker loop of the fused engine)
+        const SpPort port{S, G, dg.net_out};
+        int rot = (warp * 9) % Gc;
+        bool idle = false;
+        long long idle_t0 = 0;
+        uint32_t idle_it = 0;
+        long long t_run = 0, n_run = 0, t_idle = 0;
+        for (;;) {
+            const int seen = ld_vol(&S->wake);                             // read BEFORE the scan: no wake-up is lost
+            const int aborting = ld_vol(&S->abort);
+            const int stop = ld_vol(&S->stop) | aborting;
+            int cand = -1, n_wait = 0, n_ans = 0, n_ready = 0;
+            bool cand_ans = false;
+            for (int base = 0; base < Gc; base += 32) {
+                const int i = base + lane;
+                int idx = i + rot;
+                if (idx >= Gc) idx -= Gc;
+                const int s = (i < Gc) ? ld_vol(&S->status[idx]) : ST_IDLE;
+                const unsigned ma = __ballot_sync(FULL, s == FZ_ANSWERED);
+                const unsigned mr = __ballot_sync(FULL, s == ST_READY || s == ST_NEWROOT);
+                const unsigned mw = __ballot_sync(FULL, s == ST_WAIT);
+                n_wait += __popc(mw); n_ans += __popc(ma); n_ready += __popc(mr);
+                if (ma && !cand_ans) { cand = __shfl_sync(FULL, idx, __ffs((int)ma) - 1); cand_ans = true; }
+                else if (mr && cand < 0 && !stop) cand = __shfl_sync(FULL, idx, __ffs((int)mr) - 1);
+            }
+            if (aborting) break;
+            if (cand >= 0) {
+                int s = 0, ok = 0;
+                if (lane == 0) {
+                    s = ld_vol(&S->status[cand]);
+                    if (s == FZ_ANSWERED || (!stop && (s == ST_READY || s == ST_NEWROOT)))
+                        ok = atomicCAS(&S->status[cand], s, (int)FZ_RUNNING) == s;
+                }
+                ok = __shfl_sync(FULL, ok, 0);
+                s = __shfl_sync(FULL, s, 0);
+                if (ok) {
+                    __threadfence_block();
+                    const long long t_r0 = clock64();
+                    if (idle) { t_idle += t_r0 - idle_t0; idle = false; }
+                    fz_run_game<SELFPLAY>(dg, port, g0 + cand, cand, s, lane);
+                    t_run += clock64() - t_r0; n_run++;
+                    rot = cand + 1 < Gc ? cand + 1 : 0;
+                }
+                continue;
+            }
+            if (n_wait == 0 && n_ans == 0 && (stop || n_ready == 0)) break;    // nothing left that needs this warp
+            // idle: wait until something is published (one shared-memory word is polled, see c4_fused.cu)
+            if (!idle) { idle = true; idle_t0 = clock64(); idle_it = 0; }
+            bool dead = false;
+            while (ld_vol(&S->wake) == seen) {
+                __nanosleep(idle_it < 16u ? 100 : 400);
+                if ((++idle_it & 1023u) == 0u && clock64() - idle_t0 > FZ_WATCHDOG_CYCLES) {
+                    if (lane == 0) { dg.ctr->engine_error = 1; st_vol(&G->abort, 1); st_vol(&S->abort, 1); atomicAdd(&S->wake, 1); }
+                    dead = true;
+                    break;
+                }
+            }
+            if (dead) break;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (P.prof) { SP_PROF(8, n_run); SP_PROF(9, t_run); SP_PROF(10, t_idle); }
+            __threadfence_block();
+            atomicAdd(&S->tree_exited, 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tower CTAs
+struct SpNetCtl {
+    int strip_nb, quit, abort, pad;
+    int strip_game[SP_NB];
+    unsigned strip_tag[SP_NB];
+    u64 strip_c0[SP_NB], strip_c1[SP_NB];
+    float ans[SP_NB][8];
+};
+__host__ __device__ constexpr int sp_ctl_off(int R) { return (TcK<32>::total(R) + 15) & ~15; }
+__host__ __device__ constexpr int sp_net_smem(int R) { return sp_ctl_off(R) + (int)sizeof(SpNetCtl); }
+
+template <typename OP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, float *__restrict__ net_out, C4Counters *ctr, SpParams P)
+{
+    using K = TcK<32>;
+    constexpr int F = 32;
+    static_assert(K::NB == SP_NB && K::EPI_WARPS == TC_EPI_WARPS && !K::SLICED, "geometry of the batch kernel for 32 filters");
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int L = 1 + 2 * R;
+    const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+    unsigned char *sX = smem + K::X, *sH = smem + K::H, *sW = smem + K::W;
+    float *small = reinterpret_cast<float *>(smem + K::SMALL);
+    const float *bias = small, *hp = small + L * F;
+    float *scratch = reinterpret_cast<float *>(smem + K::scratch(R));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + K::bars(R));
+    const uint32_t b_wfull = smem_u32(bars), b_wempty = b_wfull + 8 * K::WBARS;
+    const uint32_t b_accfull = b_wempty + 8 * K::WBARS, b_accempty = b_accfull + 8 * K::ACC_SLOTS;
+    const uint32_t b_epi = b_accempty + 8 * K::ACC_SLOTS;                   // T barriers
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * K::WBARS + 2 * K::ACC_SLOTS + K::T);
+    SpNetCtl *S = reinterpret_cast<SpNetCtl *>(smem + sp_ctl_off(R));
+
+    // ---- one-time setup (k_net_tc): zero the strips, small params, barriers, TMEM
+    for (int i = threadIdx.x; i < 2 * K::ACT_BYTES / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(sX)[i] = make_uint4(0u, 0u, 0u, 0u);
+    {
+        const unsigned char *src = image + (size_t)L * K::WSTAGE_BYTES;
+        const int nb16 = (L * F + HEAD_FLOATS) * 4 / 16;
+        for (int i = threadIdx.x; i < nb16; i += blockDim.x)
+            reinterpret_cast<uint4 *>(small)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    }
+    for (int i = threadIdx.x; i < (int)(sizeof(SpNetCtl) / 4); i += blockDim.x) reinterpret_cast<uint32_t *>(S)[i] = 0u;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < K::WBARS; i++) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, 1); }
+        for (int i = 0; i < K::ACC_SLOTS; i++) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, K::GROUP_WARPS); }
+        for (int i = 0; i < K::T; i++) mbar_init(b_epi + 8 * i, K::GROUP_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    TC_PROXY_FENCE();
+    TC_FENCE_BEFORE();
+    __syncthreads();
+    TC_FENCE_AFTER();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= weight producer: layer g of the endless (strip, layer) sequence -> ring stage g % WSTAGES; it
+        // runs up to WSTAGES layers ahead of the issuer, so the first layers of the NEXT strip are on chip while the tower idles
+        if (lane == 0) {
+            int g = 0;
+            bool live = true;
+            for (; live; g++) {
+                const int st = g % K::WSTAGES, use = g / K::WSTAGES;
+                if (use > 0) {
+                    const uint32_t bar = b_wempty + 8 * st, par = (uint32_t)(use - 1) & 1u;
+                    for (uint32_t it = 0; !mbar_try(bar, par); it++) {
+                        if (it > 4u) __nanosleep(it > 64u ? 500 : 100);
+                        if ((it & 15u) == 15u && ld_vol(&S->quit)) { live = false; break; }
+                    }
+                    if (!live) break;
+                }
+                mbar_expect_tx(b_wfull + 8 * st, K::WSTAGE_BYTES);
+                bulk_g2s(smem_u32(sW + st * K::WSTAGE_BYTES), image + (size_t)(g % L) * K::WSTAGE_BYTES, K::WSTAGE_BYTES,
+                         b_wfull + 8 * st);
+            }
+            // no bulk copy may be in flight when the CTA exits: wait for the stages requested last
+            for (int i = max(0, g - K::WSTAGES); i < g; i++) mbar_wait(b_wfull + 8 * (i % K::WSTAGES), (uint32_t)(i / K::WSTAGES) & 1u);
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread): the strip loop of k_net_tc with strips that arrive at run time
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)OP::FMT << 7) | ((uint32_t)OP::FMT << 10) |
+                                   ((uint32_t)(K::NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int g = 0, c = 0;                                   // (strip, layer) counter, (strip, layer, tile) counter
+            bool live = true;
+            for (int s = 0; live; s++) {
+                // every strip completes L + 1 phases on EVERY tile barrier (input planes + L epilogues)
+                if (!fz_wait(b_epi, (uint32_t)(s * (L + 1)) & 1u, &S->abort)) break;
+                const int nb = ld_vol(&S->strip_nb);
+                if (nb == 0) break;                                             // the dispatcher said quit
+                const int T = (7 * nb + 15) / 16;
+                for (int l = 0; l < L && live; l++, g++) {
+                    const int st = g % K::WSTAGES;
+                    if (!fz_wait(b_wfull + 8 * st, (uint32_t)(g / K::WSTAGES) & 1u, &S->abort)) { live = false; break; }
+                    const uint32_t wbase = smem_u32(sW + st * K::WSTAGE_BYTES);
+                    const uint32_t abase = smem_u32((l == 0 || (l & 1) == 0) ? sH : sX);   // stem and conv2 read H
+                    const uint64_t a_l = umma_desc(abase, K::ROWS * 16, 128);
+                    const uint64_t b_l = umma_desc(wbase, K::NN * 16, 128);
+                    const uint32_t ep_par = (uint32_t)(s * (L + 1) + l) & 1u;
+#pragma unroll
+                    for (int t = 0; t < K::T; t++, c++) {
+                        if (t >= T) break;
+                        if (t == 0 && !fz_wait(b_epi, ep_par, &S->abort)) { live = false; break; }
+                        if (t + 1 < T && !fz_wait(b_epi + 8 * (t + 1), ep_par, &S->abort)) { live = false; break; }
+                        const int slot = c % K::ACC_SLOTS, use = c / K::ACC_SLOTS;
+                        if (use > 0 && !fz_wait(b_accempty + 8 * slot, (uint32_t)(use - 1) & 1u, &S->abort)) { live = false; break; }
+                        TC_FENCE_AFTER();
+                        const uint32_t dcol = tmem + K::ACC_COL0 + slot * K::NN;
+                        const uint64_t a = a_l + (uint64_t)(128 * t);
+                        if (l != 0) {
+#pragma unroll
+                            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+                                for (int ks = 0; ks < K::KC / 2; ks++) {
+                                    const uint64_t aa = a + 8 * dy + 2 * K::ROWS * ks, bb = b_l + (dy * K::KC + 2 * ks) * K::NN;
+                                    if (dy == 0 && ks == 0) umma_f16c<0>(dcol, aa, bb, idesc); else umma_f16c<1>(dcol, aa, bb, idesc);
+                                }
+                        } else {                                              // stem: 16 (padded) input channels = one k-step
+#pragma unroll
+                            for (int dy = 0; dy < 3; dy++) {
+                                const uint64_t aa = a + 8 * dy, bb = b_l + dy * K::STEM_KC * K::NN;
+                                if (dy == 0) umma_f16c<0>(dcol, aa, bb, idesc); else umma_f16c<1>(dcol, aa, bb, idesc);
+                            }
+                        }
+                        umma_commit(b_accfull + 8 * slot);
+                    }
+                    if (live) umma_commit(b_wempty + 8 * st);
+                }
+                // observe the LAST epilogue phase of tile 0 too (c4_fused.cu: with a one-tile strip the wait for the next
+                // strip's input phase would otherwise alias this strip's phase L - 1)
+                if (live && !fz_wait(b_epi, (uint32_t)(s * (L + 1) + L) & 1u, &S->abort)) break;
+            }
+        }
+    } else {
+        // ================= epilogue warps (+ the dispatcher in the first of them)
+        const int e = warp - 2, quad = warp & 3, half = (e >> 2) % K::SLICES, group = e / K::GROUP_WARPS;
+        const int et = threadIdx.x - 64;                                     // 0..511
+        EpiCtx E;
+        E.b_accfull = b_accfull; E.b_accempty = b_accempty; E.b_epi = b_epi;
+        E.tmem_acc = tmem + ((uint32_t)(quad * 32) << 16) + K::ACC_COL0 + TC_CH * half;
+        E.tmem_res = tmem + ((uint32_t)(quad * 32) << 16) + TC_CH * half;
+        E.dst_x = sX + (size_t)(2 * half * K::ROWS + 8 + 32 * quad + lane) * 16;
+        E.dst_h = sH + (size_t)(2 * half * K::ROWS + 8 + 32 * quad + lane) * 16;
+        E.bias = bias; E.hp = hp;
+        E.scratch = scratch + half * K::NB * 128;
+        E.lane = lane; E.lm = (lane + 31) & 31; E.lp = (lane + 1) & 31; E.half = half; E.group = group;
+        E.rb0 = 4 * quad + (lane >> 3); E.col8 = lane & 7;
+        E.calib = nullptr;
+        int c = 0;                                                           // global (strip, layer, tile) counter
+        for (;;) {
+            const long long t_d0 = clock64();
+            // ---- dispatch: claim what the global ring holds (up to one strip)
+            if (e == 0) {
+                int k = 0;
+                long long t_first = 0;
+                for (uint32_t it = 1;; it++) {
+                    unsigned head = 0, tail = 0;
+                    int q = 0;
+                    if (lane == 0) {
+                        head = ld_volu(&G->q_head); tail = ld_volu(&G->q_tail);
+                        q = ld_vol(&G->quit) | (ld_vol(&G->abort) << 1);
+                    }
+                    head = __shfl_sync(FULL, head, 0); tail = __shfl_sync(FULL, tail, 0); q = __shfl_sync(FULL, q, 0);
+                    const int avail = (int)(tail - head);
+                    if (q & 2) break;                                        // abort: leave at once
+                    if (avail <= 0) {
+                        if (q) break;                                        // every tree CTA has left: nothing can be pending
+                        if ((it & 4095u) == 0u && lane == 0 && *reinterpret_cast<const volatile int *>(P.host_abort)) st_vol(&G->abort, 1);
+                        t_first = 0;
+                        __nanosleep(it > 64u ? 400 : 100);
+                        continue;
+                    }
+                    if (avail < K::NB && P.batch_ns > 0) {                   // optional batching window
+                        const long long now = (long long)fz_globaltimer();
+                        if (t_first == 0) t_first = now;
+                        if (now - t_first < P.batch_ns) { __nanosleep(100); continue; }
+                    }
+                    const int want = min(avail, K::NB);
+                    int ok = 0;
+                    if (lane == 0) ok = atomicCAS(&G->q_head, head, head + (unsigned)want) == head;
+                    ok = __shfl_sync(FULL, ok, 0);
+                    if (!ok) continue;
+                    if (lane < want) {
+                        SpEntry *en = &G->q[(head + (unsigned)lane) % SP_QCAP];
+                        for (uint32_t w = 0; ld_volu(&en->seq) != head + (unsigned)lane + 1u; w++) {   // reserved, not complete yet
+                            __nanosleep(40);
+                            if ((w & 255u) == 255u && ld_vol(&G->abort)) break;
+                        }
+                        __threadfence();
+                        S->strip_c0[lane] = *reinterpret_cast<volatile u64 *>(&en->c0);
+                        S->strip_c1[lane] = *reinterpret_cast<volatile u64 *>(&en->c1);
+                        S->strip_game[lane] = *reinterpret_cast<volatile int *>(&en->game);
+                        S->strip_tag[lane] = ld_volu(&en->tag);
+                    }
+                    k = want;
+                    break;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (k == 0) st_vol(&S->quit, 1);
+                    __threadfence_block();
+                    st_vol(&S->strip_nb, k);
+                }
+            }
+            EPI_BAR();
+            const int nb = ld_vol(&S->strip_nb);
+            // (the dispatcher overwrites strip_game for the next strip while other warps are still in their head tails, so
+            //  the game of THIS warp's board is read now)
+            const int my_game = S->strip_game[e];
+            const unsigned my_tag = S->strip_tag[e];
+            const long long t_d1 = clock64();
+            if (nb == 0) {                                                   // quit: wake the issuer so it reads strip_nb == 0
+                if (lane == 0 && e < K::GROUP_WARPS)
+                    for (int t = 0; t < K::T; t++) mbar_arrive(b_epi + 8 * t);
+                break;
+            }
+            const int T = (7 * nb + 15) / 16;
+            E.valid_mask = 0;
+            for (int t = 0; t < T; t++) {
+                const int rb = 16 * t + E.rb0, b = rb / 7;
+                if (E.col8 != 0 && rb - 7 * b != 0 && b < nb) E.valid_mask |= 1u << t;
+            }
+            // ---- input planes (Board.to_array) -> channels 0..15 of H
+            for (int i = et; i < nb * 42; i += 32 * TC_EPI_WARPS) {
+                const int b = i / 42, px = i - b * 42, r = px / 7, col = px - r * 7;
+                const u64 a0 = S->strip_c0[b], a1 = S->strip_c1[b];
+                const int bit = 7 * col + (5 - r);
+                const uint32_t tomove = ((__popcll(a0 | a1) & 1) == 0) ? OP::ONE : 0u;
+                const uint32_t o = (uint32_t)((a0 >> bit) & 1ULL) * OP::ONE, x = (uint32_t)((a1 >> bit) & 1ULL) * OP::ONE;
+                const int row = 8 + (7 * b + 1 + r) * 8 + (col + 1);
+                *reinterpret_cast<uint4 *>(sH + (size_t)row * 16) = make_uint4(tomove | (o << 16), x, 0u, 0u);
+                *reinterpret_cast<uint4 *>(sH + (size_t)(K::ROWS + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            TC_PROXY_FENCE();
+            EPI_BAR();
+            // every phase completes on ALL tile barriers (also those of tiles this strip does not have), so that the
+            // phase parity of a tile barrier is a function of (strip, layer) only
+            if (lane == 0 && e < K::GROUP_WARPS)
+                for (int t = 0; t < K::T; t++) mbar_arrive(b_epi + 8 * t);
+#define SP_SKIPPED_TILES() if (lane == 0 && e < K::GROUP_WARPS) for (int t = T; t < K::T; t++) mbar_arrive(b_epi + 8 * t)
+            tc_epilogue_layer<OP, F, 0>(E, 0, T, c); c += T; SP_SKIPPED_TILES();
+            for (int l = 1; l < L - 1; l += 2) {
+                tc_epilogue_layer<OP, F, 1>(E, l, T, c); c += T; SP_SKIPPED_TILES();
+                if (l + 1 < L - 1) { tc_epilogue_layer<OP, F, 2>(E, l + 1, T, c); c += T; SP_SKIPPED_TILES(); }
+            }
+            tc_epilogue_layer<OP, F, 3>(E, L - 1, T, c); c += T; SP_SKIPPED_TILES();
+#undef SP_SKIPPED_TILES
+
+            // ---- head tails: one warp per board; the answer goes to net_out[game], then the game's answer tag
+            EPI_BAR();
+            if (e < nb) {
+                float *sc = scratch + e * 128;
+                for (int i = lane; i < 126; i += 32) {
+                    float bb = i < 42 ? hp[HO_VB] : (i < 84 ? hp[HO_PB] : hp[HO_PB + 1]);
+                    float acc = sc[i];                                       // channel slices summed in a fixed order
+#pragma unroll
+                    for (int q = 1; q < K::SLICES; q++) acc += sc[q * K::NB * 128 + i];
+                    sc[i] = leaky(acc + bb);
+                }
+                __syncwarp();
+                float *ans = S->ans[e];
+                head_tail(sc, hp, ans, lane);
+                float o = (lane < 8) ? ans[lane] : 0.f;
+                if (__any_sync(FULL, !isfinite(o))) {
+                    // operand overflow (fp16) or NaN weights: never into the tree -- neutral answer + a flag that makes the
+                    // host call fail (the reference asserts, oinkoink/neural/pytorch/model.py:258-263,275-280)
+                    o = (lane < 7) ? (1.f / 7.f) : 0.5f;
+                    if (lane == 0) ctr->net_nonfinite = 1;
+                }
+                C4_DEV_ASSERT(my_game >= 0 && my_game < P.n_slots && my_tag != 0u);
+                if (lane < 8) { __stcg(net_out + (size_t)my_game * 8 + lane, o); __threadfence(); }
+                __syncwarp();
+                if (lane == 0) st_volu(&G->ans_tag[my_game], my_tag);
+            }
+            if (P.prof && e == 0 && lane == 0) { SP_PROF(0, 1); SP_PROF(1, nb); SP_PROF(2, t_d1 - t_d0); SP_PROF(3, clock64() - t_d1); }
+        }
+    }
+    TC_FENCE_BEFORE();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// internal interface used by c4_search.cu
+static int sp_sms()
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return sms;
+}
+
+// tower CTAs for a pool of `max_games` slots (env C4_SP_NET_CTAS overrides): the rest of the SMs run trees
+static int sp_net_ctas(int sms, int max_games)
+{
+    int n = getenv("C4_SP_NET_CTAS") ? atoi(getenv("C4_SP_NET_CTAS")) : (sms * 3) / 8;
+    n = std::max(1, std::min(n, sms - 1));
+    // small pools: one tree CTA per 8 games is plenty, the towers can have the rest
+    (void)max_games;
+    return n;
+}
+
+static bool c4_split_supported(const c4_net *net, int max_games)
+{
+    if (!net || net->F != 32 || !net->use_tc || !net->image_tc) return false;
+    const int sms = sp_sms();
+    if (sms < 8 || max_games > SP_GMAX || max_games < 1) return false;
+    const int n_tree = std::min(sms - sp_net_ctas(sms, max_games), max_games);
+    if ((max_games + n_tree - 1) / n_tree > SP_GC_MAX) return false;
+    return sp_net_smem(net->R) <= 227 * 1024;
+}
+
+// ... and is it the engine to use for `live_games` games in flight?  env C4_ENGINE=split forces it.
+bool c4_split_eligible(const c4_net *net, int max_games, long long live_games)
+{
+    (void)live_games;
+    const char *want = getenv("C4_ENGINE");
+    if (!want || strcmp(want, "split")) return false;
+    return c4_split_supported(net, max_games);
+}
+
+// Run the pool until every game slot is idle / done, `stop_games` games have finished (counter in d.ctr) or `stop_ms` have
+// passed, and wait for it (same contract as c4_fused_run).  d.net_out must be writable device memory of 8 floats per slot.
+int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulations, bool selfplay,
+                 unsigned long long stop_games, double stop_ms, cudaStream_t stream)
+{
+    (void)simulations;
+    int dev = 0;
+    C4_CUDA(cudaGetDevice(&dev));
+    const int sms = sp_sms();
+    C4_REQUIRE(c4_split_supported(net, max_games), "split engine: network or pool size not supported");
+    struct PerDevice { int *h_abort = nullptr, *d_abort = nullptr; SpGlobal *G = nullptr; cudaStream_t side = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr; };
+    static PerDevice per_device[64];
+    C4_REQUIRE(dev >= 0 && dev < 64, "split engine: device index");
+    PerDevice &pd = per_device[dev];
+    static const bool debug = getenv("C4_FZ_DEBUG") != nullptr;
+    if (!pd.h_abort) {
+        C4_CUDA(cudaHostAlloc((void **)&pd.h_abort, 64, cudaHostAllocMapped));
+        C4_CUDA(cudaHostGetDevicePointer((void **)&pd.d_abort, pd.h_abort, 0));
+        C4_CUDA(cudaMalloc((void **)&pd.G, sizeof(SpGlobal)));
+        C4_CUDA(cudaStreamCreateWithFlags(&pd.side, cudaStreamNonBlocking));
+        C4_CUDA(cudaEventCreateWithFlags(&pd.ev_a, cudaEventDisableTiming));
+        C4_CUDA(cudaEventCreateWithFlags(&pd.ev_b, cudaEventDisableTiming));
+    }
+    *reinterpret_cast<volatile int *>(pd.h_abort) = 0;
+    SpParams P;
+    P.n_slots = max_games;
+    P.stop_games = stop_games;
+    P.stop_ns = stop_ms > 0.0 ? (unsigned long long)(stop_ms * 1e6) : 0ULL;
+    P.host_abort = pd.d_abort;
+    P.prof = debug ? 1 : 0;
+    P.batch_ns = getenv("C4_SP_BATCH_NS") ? atoi(getenv("C4_SP_BATCH_NS")) : 0;
+    const int n_net = sp_net_ctas(sms, max_games);
+    const int n_tree = std::min(sms - n_net, max_games);
+    const int smem = sp_net_smem(net->R);
+    auto kn = net->fp16 ? k_sp_net<OpFP16> : k_sp_net<OpBF16>;
+    auto kt = selfplay ? k_sp_tree<true> : k_sp_tree<false>;
+    C4_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // Both kernels must be LOADED before the first of them starts: with lazy module loading (the CUDA 12 default) the first
+    // launch of a function loads it, and that load can wait for running kernels -- here for a tower kernel that itself
+    // waits for the tree kernel: a deadlock, and it was the first thing the bring-up hit.
+    {
+        cudaFuncAttributes fa;
+        C4_CUDA(cudaFuncGetAttributes(&fa, kn));
+        C4_CUDA(cudaFuncGetAttributes(&fa, kt));
+    }
+    // ring head / tail, flags, answer tags and the entries' seq words all start from zero
+    C4_CUDA(cudaMemsetAsync(pd.G, 0, sizeof(SpGlobal), stream));
+    C4_CUDA(cudaEventRecord(pd.ev_a, stream));
+    C4_CUDA(cudaStreamWaitEvent(pd.side, pd.ev_a, 0));
+    kn<<<n_net, TC_THREADS, smem, pd.side>>>((const unsigned char *)net->image_tc, net->R, pd.G, const_cast<float *>(d.net_out), d.ctr, P);
+    C4_CUDA(cudaGetLastError());
+    kt<<<n_tree, SP_TREE_THREADS, 0, stream>>>(d, pd.G, P);
+    C4_CUDA(cudaGetLastError());
+    C4_CUDA(cudaEventRecord(pd.ev_b, pd.side));
+    C4_CUDA(cudaStreamWaitEvent(stream, pd.ev_b, 0));
+    const double limit_s = getenv("C4_FZ_TIMEOUT_S") ? atof(getenv("C4_FZ_TIMEOUT_S")) : 900.0;
+    const auto t0 = std::chrono::steady_clock::now();
+    bool asked = false;
+    for (long long it = 0;; it++) {
+        cudaError_t q = cudaStreamQuery(stream);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) { C4_CUDA(q); }
+        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (!asked && el > limit_s) { *reinterpret_cast<volatile int *>(pd.h_abort) = 1; asked = true; }
+        if (asked && el > limit_s + 5.0) {
+            fprintf(stderr, "[split] the launches did not end %.0f s after the abort request; giving up\n", 5.0);
+            fflush(stderr);
+            _exit(86);
+        }
+        if (it > 2000) std::this_thread::sleep_for(std::chrono::microseconds(el > 1.0 ? 2000 : 50));
+    }
+    if (debug) {
+        unsigned long long h[32];
+        C4_CUDA(cudaMemcpy(h, pd.G->prof, sizeof(h), cudaMemcpyDeviceToHost));
+        const double ns = (double)std::max(1ULL, h[0]), nr = (double)std::max(1ULL, h[8]);
+        fprintf(stderr, "[split prof] %d tree CTAs + %d tower CTAs | strips %llu boards/strip %.2f | tower cycles per strip: idle %.0f busy %.0f "
+                        "(busy share %.2f) | tree runs %llu cycles/run %.0f tree-warp idle share %.2f\n",
+                n_tree, n_net, h[0], h[1] / ns, h[2] / ns, h[3] / ns, h[3] / (double)std::max(1ULL, h[2] + h[3]),
+                h[8], h[9] / nr, h[10] / (double)std::max(1ULL, h[9] + h[10]));
+    }
+    if (asked) { c4_set_error("split engine: host deadline passed (C4_FZ_TIMEOUT_S); the launches were aborted"); return -4; }
+    return 0;
+}

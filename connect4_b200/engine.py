@@ -244,7 +244,7 @@ class Engine():
                                                C.byref(ev), C.byref(hits), C.byref(games), C.byref(ms), C.byref(eng),
                                                _lib.stream_ptr()))
         return dict(positions=pos.value, evals=ev.value, memo_hits=hits.value, games=games.value, device_ms=ms.value,
-                    engine={1: "lockstep", 2: "fused"}.get(eng.value, "?"), memo_log2=self.lib.c4_ctx_get(self.h, 4),
+                    engine={1: "lockstep", 2: "fused", 3: "split"}.get(eng.value, "?"), memo_log2=self.lib.c4_ctx_get(self.h, 4),
                     launches=self.lib.c4_ctx_get(self.h, 6), tree_ms=self.lib.c4_ctx_get(self.h, 8) / 1e6,
                     net_ms=self.lib.c4_ctx_get(self.h, 9) / 1e6, passes=self.lib.c4_ctx_get(self.h, 10))
 

@@ -5,7 +5,7 @@ set -e
 name=$1; shift
 out=connect4_b200/lib/variants
 mkdir -p $out/$name
-for f in c4_board c4_search c4_net c4_fused; do
+for f in c4_board c4_search c4_net c4_fused c4_split; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -O2 "$@" \
      -c connect4_b200/csrc/$f.cu -o $out/$name/$f.o &
 done

@@ -131,7 +131,9 @@ template <class K> __host__ __device__ constexpr int fz_total(int R, int table_e
 // the fused engine's port: answers and the leaf ring live in the CTA's shared memory
 struct FzPort {
     static constexpr int GC_MAX = FZ_GC_MAX;
+    static constexpr bool DEDUP = false;                                  // measured slower in this engine (header comment)
     FzCtl *S;
+    __device__ __forceinline__ bool impatient(int) const { return true; }
     __device__ __forceinline__ int stopping() const { return ld_vol(&S->stop); }
     __device__ __forceinline__ float answer(int, int gl, int lane) const { return (lane < 8) ? S->ans[gl][lane] : 0.f; }
     __device__ __forceinline__ void publish(int, int gl, int st, bool request, u64 rc0, u64 rc1) const
@@ -201,12 +203,7 @@ k_fused(const C4Dev dg, const unsigned char *__restrict__ image, int R, FzParams
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     __syncthreads();                                                      // FzCtl zeroed before the statuses go in
-    // (a game the lock-step engine parked on another game's evaluation, ST_WAITMEMO, has applied nothing yet: it simply
-    //  descends to that leaf again)
-    for (int i = threadIdx.x; i < FZ_GC_MAX; i += blockDim.x) {
-        const int st0 = (i < Gc) ? dg.status[g0 + i] : ST_IDLE;
-        S->status[i] = st0 == ST_WAITMEMO ? (int)ST_READY : st0;
-    }
+    for (int i = threadIdx.x; i < FZ_GC_MAX; i += blockDim.x) S->status[i] = (i < Gc) ? fz_entry_status(dg, g0 + i) : (int)ST_IDLE;
     TC_PROXY_FENCE();
     TC_FENCE_BEFORE();
     __syncthreads();

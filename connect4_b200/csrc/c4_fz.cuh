@@ -4,13 +4,15 @@
 //   PORT::GC_MAX                                   game slots per CTA
 //   int   stopping()                               the engine is draining: park the game as it is
 //   float answer(g, gl, lane)                      lane < 8: {prior[7], value} of the game's answered leaf
-//   void  publish(g, gl, st, request, c0, c1)      lane 0: make the game's new status visible, then (request) queue the leaf
+//   void  publish(g, gl, st, request, c0, c1)      lane 0: make the game's new status visible, then (request) queue the leaf;
+//                                                  st == ST_WAITMEMO: the game waits for the memo entry of (c0, c1)
+//   PORT::DEDUP, bool impatient(gl)                de-duplication of evaluations in flight; a parked game asks for itself
 #pragma once
 #include "c4_tree.cuh"
 #include "c4_tc.cuh"
 
 #define FZ_WATCHDOG_CYCLES 6000000000LL                   // ~3 s without a runnable game while games wait = protocol bug
-enum { FZ_ANSWERED = 5, FZ_RUNNING = 6 };
+enum { FZ_ANSWERED = 5, FZ_RUNNING = 6, FZ_MEMOREADY = 8 };      // (7 = ST_WAITMEMO)
 
 __device__ __forceinline__ unsigned long long fz_globaltimer()
 {
@@ -20,6 +22,16 @@ __device__ __forceinline__ unsigned long long fz_globaltimer()
 }
 __device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+
+// Status of a game slot at the start of a persistent launch.  A game the previous engine parked on another game's evaluation
+// (ST_WAITMEMO) has applied nothing yet: it descends to that leaf again -- or, if the parked position was its root, sets the
+// root up again.
+__device__ __forceinline__ int fz_entry_status(const C4Dev &d, int g)
+{
+    const int st = d.status[g];
+    if (st != ST_WAITMEMO) return st;
+    return d.path_len[g] == 0 ? (int)ST_NEWROOT : (int)ST_READY;
+}
 
 // mbarrier wait that gives up when the CTA aborts (watchdog); false = aborted
 __device__ __forceinline__ bool fz_wait(uint32_t bar, uint32_t parity, const int *abort)
@@ -34,6 +46,10 @@ __device__ __forceinline__ bool fz_wait(uint32_t bar, uint32_t parity, const int
 
 // Run game `gl` of this CTA (global slot g) until it needs the network, finishes, or the engine is stopping.
 // Same state machine as k_advance (c4_search.cu), minus the pass structure.
+// PORT::DEDUP (split engine): de-duplication of evaluations in flight with the PENDING tags of c4_tree.cuh -- a game whose
+// leaf is being evaluated for another game parks it (ST_WAITMEMO, leaf saved like a request) and is handed back as
+// FZ_MEMOREADY once the tag in the memo entry has changed; it then probes again: a hit is consumed in place of a network
+// answer (bit-identical numbers), a miss (the entry was overwritten by a colliding key) claims and asks for itself.
 template <bool SELFPLAY, class PORT>
 __device__ __forceinline__ void fz_run_game(const C4Dev &d, const PORT &port, int g, int gl, int st, int lane)
 {
@@ -45,33 +61,50 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, const PORT &port, in
     G.c0 = d.root_c0[g]; G.c1 = d.root_c1[g];
     G.age = c4_age(G.c0, G.c1);
 
+    bool request = false, park = false, saved = false;
+    u64 rc0 = 0, rc1 = 0;
+    uint32_t rnode = 0u, rlo = 0u, rhi = 0u;
+    int rlen = 0;
     C4_DEV_ASSERT(gl >= 0 && gl < PORT::GC_MAX && G.n_blocks >= 1 && G.n_blocks <= d.blocks_per_game && G.sims_done <= d.sims);
-    if (st == FZ_ANSWERED) {
+    if (st == FZ_ANSWERED || (PORT::DEDUP && st == FZ_MEMOREADY)) {
         // consume the evaluator's answer for the pending leaf (oinkoink/mcts.py:129-135), then backpropagate
         const uint32_t node = (uint32_t)d.pending_node[g];
         const int plen = d.path_len[g];
         C4_DEV_ASSERT(plen >= 0 && plen <= PATH_CAP && node < (uint32_t)G.n_blocks * C4_SLOTS);
         const u64 lc0 = d.pend_c0[g], lc1 = d.pend_c1[g];
         const bool is_root = (plen == 0);
-        const float ov = port.answer(g, gl, lane);
-        if (d.memo) memo_insert(d, lc0, lc1, ov, lane);
-        const double value = (double)__shfl_sync(FULL, ov, 7);
-        apply_eval<true>(d, G, node, lc0, lc1, c4_age(lc0, lc1), value, 0.0, (lane < 7) ? ov : 0.f, is_root,
-                         SELFPLAY ? d.ply[g] : 0);
-        if (!is_root) {
-            const uint32_t plo = (lane < plen) ? d.path[(size_t)g * PATH_CAP + lane] : 0u;
-            const uint32_t phi = (lane + 32 < plen) ? d.path[(size_t)g * PATH_CAP + lane + 32] : 0u;
-            backup(G, plo, phi, plen - 1, value);
-            G.sims_done++;
+        float ov;
+        bool have = true;
+        if (!PORT::DEDUP || st == FZ_ANSWERED) {
+            ov = port.answer(g, gl, lane);
+            if (d.memo) memo_insert(d, lc0, lc1, ov, lane);
+        } else {
+            u64 seen = 0;
+            const int pr = memo_probe(d, lc0, lc1, ov, lane, seen);
+            if (pr == MEMO_HIT) {
+                if (lane == 0) d.stat_hits[g] += 1ULL;
+            } else {
+                // still pending (the watch timed out) or overwritten by a colliding key: wait on, or ask for itself
+                have = false; saved = true; rc0 = lc0; rc1 = lc1;
+                if ((pr == MEMO_PENDING && !port.impatient(gl)) || (pr == MEMO_MISS && !memo_claim(d, lc0, lc1, seen, lane))) park = true;
+                else request = true;
+            }
         }
-        st = ST_READY;
+        if (have) {
+            const double value = (double)__shfl_sync(FULL, ov, 7);
+            apply_eval<true>(d, G, node, lc0, lc1, c4_age(lc0, lc1), value, 0.0, (lane < 7) ? ov : 0.f, is_root,
+                             SELFPLAY ? d.ply[g] : 0);
+            if (!is_root) {
+                const uint32_t plo = (lane < plen) ? d.path[(size_t)g * PATH_CAP + lane] : 0u;
+                const uint32_t phi = (lane + 32 < plen) ? d.path[(size_t)g * PATH_CAP + lane + 32] : 0u;
+                backup(G, plo, phi, plen - 1, value);
+                G.sims_done++;
+            }
+            st = ST_READY;
+        }
     }
 
-    bool request = false;
-    u64 rc0 = 0, rc1 = 0;
-    uint32_t rnode = 0u, rlo = 0u, rhi = 0u;
-    int rlen = 0;
-    for (;;) {
+    while (!request && !park) {
         if (port.stopping()) break;                                    // the engine is draining: park the game as it is
         if (st == ST_NEWROOT) {
             // Tree(board) + evaluate root (oinkoink/mcts.py:98-105): fresh pool, root = node 0 of block 0
@@ -80,13 +113,18 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, const PORT &port, in
             if (lane == 0) { st_a(G.gp, 0.0, 0u, C4_META_EXISTS); st_b(G.gp, 0.0, 0.0); }
             __syncwarp();
             float ov;
-            if (d.memo && memo_lookup(d, G.c0, G.c1, ov, lane)) {
+            u64 seen = 0;
+            int pr = MEMO_MISS;
+            if (d.memo) pr = PORT::DEDUP ? memo_probe(d, G.c0, G.c1, ov, lane, seen) : (memo_lookup(d, G.c0, G.c1, ov, lane) ? MEMO_HIT : MEMO_MISS);
+            if (pr == MEMO_HIT) {
                 apply_eval<true>(d, G, 0u, G.c0, G.c1, G.age, (double)__shfl_sync(FULL, ov, 7), 0.0, (lane < 7) ? ov : 0.f,
                                  true, SELFPLAY ? d.ply[g] : 0);
                 if (lane == 0) d.stat_hits[g] += 1ULL;
                 st = ST_READY;
             } else {
-                request = true; rc0 = G.c0; rc1 = G.c1; rnode = 0u; rlen = 0;
+                rc0 = G.c0; rc1 = G.c1; rnode = 0u; rlen = 0;
+                if (PORT::DEDUP && d.memo && d.memo_dedup && (pr == MEMO_PENDING || !memo_claim(d, rc0, rc1, seen, lane))) park = true;
+                else request = true;
                 break;
             }
         }
@@ -107,9 +145,12 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, const PORT &port, in
             G.sims_done++;
             continue;
         }
+        u64 seen = 0;
+        int pr = MEMO_MISS;
         if (d.memo) {
             float ov;
-            if (memo_lookup(d, L.c0, L.c1, ov, lane)) {
+            pr = PORT::DEDUP ? memo_probe(d, L.c0, L.c1, ov, lane, seen) : (memo_lookup(d, L.c0, L.c1, ov, lane) ? MEMO_HIT : MEMO_MISS);
+            if (pr == MEMO_HIT) {
                 const double value = (double)__shfl_sync(FULL, ov, 7);
                 apply_eval<true>(d, G, L.node, L.c0, L.c1, L.age, value, 0.0, (lane < 7) ? ov : 0.f, false, 0);
                 backup(G, L.path_lo, L.path_hi, L.depth, value);
@@ -118,22 +159,25 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, const PORT &port, in
                 continue;
             }
         }
-        request = true; rc0 = L.c0; rc1 = L.c1; rnode = L.node; rlen = L.depth + 1; rlo = L.path_lo; rhi = L.path_hi;
+        rc0 = L.c0; rc1 = L.c1; rnode = L.node; rlen = L.depth + 1; rlo = L.path_lo; rhi = L.path_hi;
+        if (PORT::DEDUP && d.memo && d.memo_dedup && (pr == MEMO_PENDING || !memo_claim(d, rc0, rc1, seen, lane))) park = true;
+        else request = true;
         break;
     }
     if (request) st = ST_WAIT;
+    if (park) st = ST_WAITMEMO;
     if (lane == 0) {
         d.status[g] = st;
         d.n_blocks[g] = G.n_blocks;
         d.sims_done[g] = G.sims_done;
         d.root_c0[g] = G.c0; d.root_c1[g] = G.c1;
-        if (request) {
+        if ((request || park) && !saved) {
             d.pend_c0[g] = rc0; d.pend_c1[g] = rc1;
             d.pending_node[g] = (int)rnode; d.path_len[g] = rlen;
-            d.stat_evals[g] += 1ULL;
         }
+        if (request) d.stat_evals[g] += 1ULL;
     }
-    if (request) {
+    if ((request || park) && !saved) {
         if (lane < rlen) d.path[(size_t)g * PATH_CAP + lane] = rlo;
         if (lane + 32 < rlen) d.path[(size_t)g * PATH_CAP + lane + 32] = rhi;
     }

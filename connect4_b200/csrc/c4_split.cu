@@ -11,24 +11,28 @@
 //     warp: it polls the answer tags of the CTA's waiting games (contiguous words, a few sectors per sweep), flips their
 //     status words in shared memory and keeps the stop / abort flags.  No tower here: ~3 KB of shared memory, the rest of
 //     the 228 KB is L1 for the node records.
-//   * k_sp_net: n_net CTAs x 576 threads = the batch kernel's tower (c4_net.cu: 16-board strips, two epilogue groups, 90
-//     registers, 200 KB of shared memory) as a server: the dispatcher (epilogue warp 0) claims the leading entries of the
-//     ring with one atomicCAS on the head -- whatever is there, up to a strip; no batching delay -- and the strip's answers
-//     go to net_out[game] followed by the game's answer tag.
+//   * k_sp_net: n_net CTAs x 576 threads = the batch kernel's tower (c4_net.cu: 16-board strips, two epilogue groups, 94
+//     registers, 200 KB of shared memory) as a server with its OWN leaf ring: the dispatcher (epilogue warp 0) takes what
+//     its ring holds -- up to a strip; no batching delay -- and the strip's answers go to the games' answer slots.
+//   * requests are dealt round-robin: ONE atomicAdd on a global ticket counter gives a request both its tower (ticket %
+//     n_net) and its slot in that tower's ring (ticket / n_net); a tower learns how many entries it owns from the same
+//     counter.  Single consumer per ring: no CAS, no contention between the towers (the first version had one shared ring
+//     claimed with a CAS on its head: 16k cycles per strip went into the claim).
 // The two kernels are launched on two streams and are co-resident by construction: every CTA of either kernel needs a
 // whole SM (64 K registers / 200 KB of shared memory) and n_tree + n_net <= number of SMs.  All cross-SM hand-offs are
 // polls of L2-resident words with a back-off; every wait is bounded (tree-warp watchdog -> abort flag -> both kernels
 // leave; host deadline through a mapped word), so a protocol bug ends in an error code, not in a hung device.
 //
-// Lock-free hand-offs (what a race checker would flag, and why each is safe):
-//   * ring entry: slot reserved with atomicAdd(q_tail); {c0, c1, game, tag} written; __threadfence(); seq = slot + 1.
-//     A consumer owns entries [head, head + k) after its CAS on q_head and spins on each entry's seq before it reads the
-//     rest.  Capacity (16,384) >= game slots and a game has at most one leaf pending, so a slot is not reused before its
-//     entry was read.
-//   * answer: 8 lanes store net_out[game][0..7], each fences, __syncwarp, then lane 0 stores ans_tag[game] = tag.  The
-//     mail warp sees the tag, fences, flips WAIT -> ANSWERED in shared memory; the tree warp that claims the game reads
-//     net_out with ld.global.cg (L2).  tag = the game's request number in this launch (never 0), so a stale tag of an
-//     earlier request never matches.
+// NO gpu-scope fence on the data path: __threadfence() invalidates the SM's whole L1 (CCTL.IVALL) -- in a tree CTA that
+// is the cache of the node records, and the first version paid it on every request and every answer.  Instead every
+// cross-SM message is made of self-validating 8-byte words (aligned 8-byte stores and loads are single transactions):
+//   * ring entry = two words {c0 (48 bits) | game << 48 | stamp << 62} {c1 (48 bits) | tag << 48 | stamp << 62}; stamp = 1 +
+//     lap parity of the slot (0 = never written; rings are zeroed per launch).  The consumer spins until both stamps are
+//     those of the lap it expects.  Ring capacity >= game slots and a game has at most one leaf pending, so a slot is never
+//     overwritten before it was read.
+//   * answer = eight words {float bits | tag << 32} in the game's answer slot, stored by eight lanes of the tower's head
+//     warp.  tag = the game's request number (14 bits, never 0).  The mail warp looks at the LAST word only (a hint); the
+//     tree warp that claims the game reads all eight with ld.global.cg and spins until every tag matches.
 //   * status words, stop / abort flags: as in the fused engine (c4_fused.cu).
 #include <stdio.h>
 #include <stdlib.h>
@@ -41,29 +45,22 @@
 
 #include "c4_fz.cuh"
 
-#define SP_QCAP 16384                                     // leaf ring entries (>= game slots of the pool)
 #define SP_GMAX 16384                                     // game slots the engine accepts
 #define SP_GC_MAX 256                                     // game slots per tree CTA
 #define SP_TREE_THREADS 1024
 #define SP_TREE_WARPS 31                                  // warps 0..30 run games, warp 31 is the mail warp
 #define SP_NB 16                                          // boards per strip (TcC<32>::NB)
-
-struct __align__(32) SpEntry {
-    u64 c0, c1;
-    int game;
-    unsigned tag;
-    unsigned seq;                       // slot number + 1 once the entry is complete
-    unsigned pad;
-};
+#define SP_PATIENCE 4                                     // watch time-outs after which a parked game asks for itself
+#define SP_WATCH_SWEEPS 2048                              // mail-warp sweeps (~150 ns each) until a watch times out
 
 struct SpGlobal {
-    unsigned q_tail; unsigned pad0[31];
-    unsigned q_head; unsigned pad1[31];
+    unsigned ticket; unsigned pad0[31];                   // requests issued so far (dealt round-robin to the towers)
     int quit, abort, trees_exited; int pad2[29];
     unsigned long long prof[32];
-    unsigned ans_tag[SP_GMAX];
-    SpEntry q[SP_QCAP];
+    unsigned long long ans[SP_GMAX][8];                   // per game slot: {float bits | tag << 32} x {prior[7], value}
+    // followed by the rings: [n_net][ring_cap][2] words
 };
+__host__ __device__ constexpr size_t sp_rings_off() { return (sizeof(SpGlobal) + 255) & ~(size_t)255; }
 
 struct SpParams {
     int n_slots;                        // game slots of the pool
@@ -72,6 +69,8 @@ struct SpParams {
     const int *host_abort;              // mapped host word: non-zero = the host gave up waiting, leave at once
     int prof;                           // accumulate cycle / event sums in SpGlobal::prof (C4_FZ_DEBUG)
     int batch_ns;                       // a dispatcher that finds less than a strip waits up to this long for more
+    int n_net;                          // tower CTAs = rings
+    unsigned ring_cap;                  // entries per ring (power of two >= game slots)
 };
 
 // tree CTA control block (shared memory)
@@ -79,38 +78,73 @@ struct SpCtl {
     int abort, stop, tree_exited, wake;
     int status[SP_GC_MAX];              // ST_* / FZ_*: authoritative while the kernel runs
     unsigned req[SP_GC_MAX];            // request number of the game's last leaf (= its answer tag)
+    // ST_WAITMEMO games: the memo entry's check word the mail warp watches, the PENDING tag it holds while the owner's
+    // evaluation is in flight, the mail-warp sweep at which the game was parked, and how often the watch timed out
+    const unsigned long long *watch[SP_GC_MAX];
+    unsigned long long watch_tag[SP_GC_MAX];
+    unsigned watch_t0[SP_GC_MAX];
+    int watch_timeouts[SP_GC_MAX];
+    unsigned sweep;                     // the mail warp's sweep counter
 };
 
 __device__ __forceinline__ unsigned ld_volu(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
+__device__ __forceinline__ unsigned long long ld_vol64(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
+__device__ __forceinline__ unsigned sp_tag(unsigned request_no) { return request_no % 16383u + 1u; }   // 14 bits, never 0
+__device__ __forceinline__ unsigned long long *sp_ring(SpGlobal *G, unsigned cap, int r)
+{
+    return reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(G) + sp_rings_off()) + (size_t)r * cap * 2;
+}
 __device__ __forceinline__ void st_volu(unsigned *p, unsigned v) { *reinterpret_cast<volatile unsigned *>(p) = v; }
 
 #define SP_PROF(i, v) do { if (P.prof) atomicAdd(&G->prof[i], (unsigned long long)(v)); } while (0)
 
-// the split engine's port: the answer comes from net_out in HBM (written by a tower CTA), the request goes to the global ring
+// the split engine's port: the answer comes from the game's answer slot in HBM / L2 (written by a tower CTA), the request goes
+// to the ring of the tower its ticket names
 struct SpPort {
     static constexpr int GC_MAX = SP_GC_MAX;
+    static constexpr bool DEDUP = true;
     SpCtl *S;
     SpGlobal *G;
-    const float *net_out;
+    const uint32_t *memo;
+    uint32_t memo_mask, memo_epoch;
+    unsigned n_net, ring_cap;
     __device__ __forceinline__ int stopping() const { return ld_vol(&S->stop); }
-    __device__ __forceinline__ float answer(int g, int, int lane) const
+    // all eight words of the answer must carry the tag of the game's request (the mail warp only saw the last one)
+    __device__ __forceinline__ float answer(int g, int gl, int lane) const
     {
-        return (lane < 8) ? __ldcg(net_out + (size_t)g * 8 + lane) : 0.f;
+        const unsigned tag = sp_tag(S->req[gl]);
+        const unsigned long long *a = &G->ans[g][lane & 7];
+        unsigned long long v = __ldcg(a);
+        while (!__all_sync(FULL, (unsigned)(v >> 32) == tag)) v = ld_vol64(a);
+        return (lane < 8) ? __uint_as_float((unsigned)v) : 0.f;
     }
+    // a parked game whose watch timed out SP_PATIENCE times (the owner of the tag never answered) asks for itself
+    __device__ __forceinline__ bool impatient(int gl) const { return S->watch_timeouts[gl] >= SP_PATIENCE; }
     __device__ __forceinline__ void publish(int g, int gl, int st, bool request, u64 rc0, u64 rc1) const
     {
         unsigned tag = 0u;
-        if (request) { tag = S->req[gl] + 1u; *reinterpret_cast<volatile unsigned *>(&S->req[gl]) = tag; }
+        if (request) {
+            const unsigned no = S->req[gl] + 1u;
+            *reinterpret_cast<volatile unsigned *>(&S->req[gl]) = no;
+            tag = sp_tag(no);
+            S->watch_timeouts[gl] = 0;
+        }
+        if (st == ST_WAITMEMO) {
+            S->watch[gl] = reinterpret_cast<const unsigned long long *>(memo + (size_t)memo_index(rc0, rc1, memo_mask) * 16 + 12);
+            S->watch_tag[gl] = memo_pending_tag(memo_epoch, rc0, rc1);
+            S->watch_t0[gl] = ld_volu(&S->sweep);
+        }
         __threadfence_block();
-        st_vol(&S->status[gl], st);                                       // WAIT (and its tag) visible before the request is
+        st_vol(&S->status[gl], st);                                       // WAIT (and its request number) visible before the request is
         if (st == ST_IDLE || st == ST_DONE) atomicAdd(&S->wake, 1);       // idle warps re-check whether anything is left
         if (request) {
-            const unsigned slot = atomicAdd(&G->q_tail, 1u);
-            SpEntry *e = &G->q[slot % SP_QCAP];
-            C4_DEV_ASSERT(slot - ld_volu(&G->q_head) < SP_QCAP);            // one pending leaf per game
-            e->c0 = rc0; e->c1 = rc1; e->game = g; e->tag = tag;
-            __threadfence();
-            st_volu(&e->seq, slot + 1u);
+            const unsigned n = atomicAdd(&G->ticket, 1u);
+            const unsigned r = n % n_net, k = n / n_net;
+            const unsigned long long stamp = 1ULL + ((k / ring_cap) & 1u);
+            unsigned long long *e = sp_ring(G, ring_cap, (int)r) + (size_t)(k & (ring_cap - 1u)) * 2;
+            C4_DEV_ASSERT((rc0 >> 48) == 0 && (rc1 >> 48) == 0 && g < (1 << 14));
+            __stcg(reinterpret_cast<ulonglong2 *>(e), make_ulonglong2(rc0 | ((unsigned long long)g << 48) | (stamp << 62),
+                                                                       rc1 | ((unsigned long long)tag << 48) | (stamp << 62)));
         }
     }
 };
@@ -130,12 +164,7 @@ k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
 
     for (int i = threadIdx.x; i < (int)(sizeof(SpCtl) / 4); i += blockDim.x) reinterpret_cast<uint32_t *>(S)[i] = 0u;
     __syncthreads();
-    // (a game the lock-step engine parked on another game's evaluation, ST_WAITMEMO, has applied nothing yet: it simply
-    //  descends to that leaf again)
-    for (int i = threadIdx.x; i < SP_GC_MAX; i += blockDim.x) {
-        const int st0 = (i < Gc) ? dg.status[g0 + i] : ST_IDLE;
-        S->status[i] = st0 == ST_WAITMEMO ? (int)ST_READY : st0;
-    }
+    for (int i = threadIdx.x; i < SP_GC_MAX; i += blockDim.x) S->status[i] = (i < Gc) ? fz_entry_status(dg, g0 + i) : (int)ST_IDLE;
     __syncthreads();
     const unsigned long long t_begin = fz_globaltimer();
 
@@ -153,18 +182,26 @@ k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
                 if (!ld_vol(&S->abort) && ld_vol(&G->abort)) { st_vol(&S->abort, 1); atomicAdd(&S->wake, 1); }
             }
             int n_wait = 0;
+            const bool look = (it & 7u) == 0u;                                // the memo watches are looked at every 8th sweep
             for (int base = 0; base < Gc; base += 32) {
                 const int i = base + lane;
-                const bool w = i < Gc && ld_vol(&S->status[i]) == ST_WAIT;
+                const int st = i < Gc ? ld_vol(&S->status[i]) : (int)ST_IDLE;
+                const bool w = st == ST_WAIT, wm = st == ST_WAITMEMO;
                 bool hit = false;
                 if (w) {
-                    const unsigned tag = ld_volu(&S->req[i]);
-                    hit = ld_volu(&G->ans_tag[g0 + i]) == tag;
-                    if (hit) { __threadfence(); st_vol(&S->status[i], FZ_ANSWERED); }
+                    const unsigned tag = sp_tag(ld_volu(&S->req[i]));
+                    hit = (unsigned)(ld_vol64(&G->ans[g0 + i][7]) >> 32) == tag;
+                    if (hit) { __threadfence_block(); st_vol(&S->status[i], FZ_ANSWERED); }
+                } else if (wm && look) {
+                    // the PENDING tag is gone: the owner's answer is in (or a colliding key took the entry) -- probe again
+                    const bool timeout = it - S->watch_t0[i] > SP_WATCH_SWEEPS;
+                    hit = *reinterpret_cast<const volatile unsigned long long *>(S->watch[i]) != S->watch_tag[i] || timeout;
+                    if (hit) { if (timeout) S->watch_timeouts[i]++; __threadfence_block(); st_vol(&S->status[i], FZ_MEMOREADY); }
                 }
-                n_wait += __popc(__ballot_sync(FULL, w));
+                n_wait += __popc(__ballot_sync(FULL, w || wm));
                 if (__any_sync(FULL, hit) && lane == 0) { __threadfence_block(); atomicAdd(&S->wake, 1); }
             }
+            if (lane == 0) st_volu(&S->sweep, it + 1u);
             if (ld_vol(&S->tree_exited) == SP_TREE_WARPS) break;
             __nanosleep(n_wait ? 150 : 1000);
         }
@@ -172,7 +209,7 @@ k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
         if (lane == 0 && atomicAdd(&G->trees_exited, 1) == (int)gridDim.x - 1) { __threadfence(); st_vol(&G->quit, 1); }
     } else {
         // ================= tree warps (the picker loop of the fused engine)
-        const SpPort port{S, G, dg.net_out};
+        const SpPort port{S, G, dg.memo, dg.memo_mask, dg.memo_epoch, (unsigned)P.n_net, P.ring_cap};
         int rot = (warp * 9) % Gc;
         bool idle = false;
         long long idle_t0 = 0;
@@ -190,9 +227,10 @@ k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
                 if (idx >= Gc) idx -= Gc;
                 const int s = (i < Gc) ? ld_vol(&S->status[idx]) : ST_IDLE;
                 const unsigned ma = __ballot_sync(FULL, s == FZ_ANSWERED);
-                const unsigned mr = __ballot_sync(FULL, s == ST_READY || s == ST_NEWROOT);
+                const unsigned mr = __ballot_sync(FULL, s == ST_READY || s == ST_NEWROOT || s == FZ_MEMOREADY);
                 const unsigned mw = __ballot_sync(FULL, s == ST_WAIT);
                 n_wait += __popc(mw); n_ans += __popc(ma); n_ready += __popc(mr);
+                n_ready += __popc(__ballot_sync(FULL, s == ST_WAITMEMO));   // parked on another game's evaluation: will be handed back
                 if (ma && !cand_ans) { cand = __shfl_sync(FULL, idx, __ffs((int)ma) - 1); cand_ans = true; }
                 else if (mr && cand < 0 && !stop) cand = __shfl_sync(FULL, idx, __ffs((int)mr) - 1);
             }
@@ -201,7 +239,7 @@ k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
                 int s = 0, ok = 0;
                 if (lane == 0) {
                     s = ld_vol(&S->status[cand]);
-                    if (s == FZ_ANSWERED || (!stop && (s == ST_READY || s == ST_NEWROOT)))
+                    if (s == FZ_ANSWERED || (!stop && (s == ST_READY || s == ST_NEWROOT || s == FZ_MEMOREADY)))
                         ok = atomicCAS(&S->status[cand], s, (int)FZ_RUNNING) == s;
                 }
                 ok = __shfl_sync(FULL, ok, 0);
@@ -252,7 +290,7 @@ __host__ __device__ constexpr int sp_net_smem(int R) { return sp_ctl_off(R) + (i
 
 template <typename OP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, float *__restrict__ net_out, C4Counters *ctr, SpParams P)
+k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters *ctr, SpParams P)
 {
     using K = TcK<32>;
     constexpr int F = 32;
@@ -392,27 +430,32 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, float *__r
         E.rb0 = 4 * quad + (lane >> 3); E.col8 = lane & 7;
         E.calib = nullptr;
         int c = 0;                                                           // global (strip, layer, tile) counter
+        unsigned ring_head = 0u;                                             // dispatcher: entries of this tower's ring consumed
+        const unsigned long long *ring = sp_ring(G, P.ring_cap, (int)blockIdx.x);
         for (;;) {
             const long long t_d0 = clock64();
-            // ---- dispatch: claim what the global ring holds (up to one strip)
+            long long t_work = t_d0;                                         // dispatcher: first look that found leaves
             if (e == 0) {
+                // ---- dispatch: take what this tower's ring holds (up to one strip).  The ring's entries are the tickets
+                // n = k * n_net + blockIdx.x; `ticket` tickets have been issued so far.
                 int k = 0;
                 long long t_first = 0;
                 for (uint32_t it = 1;; it++) {
-                    unsigned head = 0, tail = 0;
+                    unsigned issued = 0;
                     int q = 0;
                     if (lane == 0) {
-                        head = ld_volu(&G->q_head); tail = ld_volu(&G->q_tail);
+                        const unsigned t = ld_volu(&G->ticket);
+                        issued = (t + (unsigned)P.n_net - 1u - blockIdx.x) / (unsigned)P.n_net;
                         q = ld_vol(&G->quit) | (ld_vol(&G->abort) << 1);
                     }
-                    head = __shfl_sync(FULL, head, 0); tail = __shfl_sync(FULL, tail, 0); q = __shfl_sync(FULL, q, 0);
-                    const int avail = (int)(tail - head);
+                    issued = __shfl_sync(FULL, issued, 0); q = __shfl_sync(FULL, q, 0);
+                    const int avail = (int)(issued - ring_head);
                     if (q & 2) break;                                        // abort: leave at once
                     if (avail <= 0) {
                         if (q) break;                                        // every tree CTA has left: nothing can be pending
                         if ((it & 4095u) == 0u && lane == 0 && *reinterpret_cast<const volatile int *>(P.host_abort)) st_vol(&G->abort, 1);
                         t_first = 0;
-                        __nanosleep(it > 64u ? 400 : 100);
+                        __nanosleep(it > 64u ? 300 : 60);
                         continue;
                     }
                     if (avail < K::NB && P.batch_ns > 0) {                   // optional batching window
@@ -420,24 +463,25 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, float *__r
                         if (t_first == 0) t_first = now;
                         if (now - t_first < P.batch_ns) { __nanosleep(100); continue; }
                     }
-                    const int want = min(avail, K::NB);
-                    int ok = 0;
-                    if (lane == 0) ok = atomicCAS(&G->q_head, head, head + (unsigned)want) == head;
-                    ok = __shfl_sync(FULL, ok, 0);
-                    if (!ok) continue;
-                    if (lane < want) {
-                        SpEntry *en = &G->q[(head + (unsigned)lane) % SP_QCAP];
-                        for (uint32_t w = 0; ld_volu(&en->seq) != head + (unsigned)lane + 1u; w++) {   // reserved, not complete yet
+                    if (P.prof) t_work = clock64();
+                    k = min(avail, K::NB);
+                    if (lane < k) {
+                        const unsigned idx = ring_head + (unsigned)lane;
+                        const unsigned long long stamp = 1ULL + ((idx / P.ring_cap) & 1u);
+                        const unsigned long long *en = ring + (size_t)(idx & (P.ring_cap - 1u)) * 2;
+                        unsigned long long a = 0, b = 0;
+                        for (uint32_t w = 0;; w++) {                         // ticket taken, words not written yet
+                            a = ld_vol64(en); b = ld_vol64(en + 1);
+                            if ((a >> 62) == stamp && (b >> 62) == stamp) break;
                             __nanosleep(40);
                             if ((w & 255u) == 255u && ld_vol(&G->abort)) break;
                         }
-                        __threadfence();
-                        S->strip_c0[lane] = *reinterpret_cast<volatile u64 *>(&en->c0);
-                        S->strip_c1[lane] = *reinterpret_cast<volatile u64 *>(&en->c1);
-                        S->strip_game[lane] = *reinterpret_cast<volatile int *>(&en->game);
-                        S->strip_tag[lane] = ld_volu(&en->tag);
+                        S->strip_c0[lane] = a & 0xFFFFFFFFFFFFULL;
+                        S->strip_c1[lane] = b & 0xFFFFFFFFFFFFULL;
+                        S->strip_game[lane] = (int)((a >> 48) & 0x3FFFu);
+                        S->strip_tag[lane] = (unsigned)((b >> 48) & 0x3FFFu);
                     }
-                    k = want;
+                    ring_head += (unsigned)k;
                     break;
                 }
                 __syncwarp();
@@ -478,6 +522,7 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, float *__r
             }
             TC_PROXY_FENCE();
             EPI_BAR();
+            const long long t_d2 = clock64();
             // every phase completes on ALL tile barriers (also those of tiles this strip does not have), so that the
             // phase parity of a tile barrier is a function of (strip, layer) only
             if (lane == 0 && e < K::GROUP_WARPS)
@@ -491,8 +536,9 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, float *__r
             tc_epilogue_layer<OP, F, 3>(E, L - 1, T, c); c += T; SP_SKIPPED_TILES();
 #undef SP_SKIPPED_TILES
 
-            // ---- head tails: one warp per board; the answer goes to net_out[game], then the game's answer tag
+            // ---- head tails: one warp per board; the answer goes to the game's answer slot, every word tagged
             EPI_BAR();
+            const long long t_d3 = clock64();
             if (e < nb) {
                 float *sc = scratch + e * 128;
                 for (int i = lane; i < 126; i += 32) {
@@ -513,11 +559,12 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, float *__r
                     if (lane == 0) ctr->net_nonfinite = 1;
                 }
                 C4_DEV_ASSERT(my_game >= 0 && my_game < P.n_slots && my_tag != 0u);
-                if (lane < 8) { __stcg(net_out + (size_t)my_game * 8 + lane, o); __threadfence(); }
-                __syncwarp();
-                if (lane == 0) st_volu(&G->ans_tag[my_game], my_tag);
+                if (lane < 8) __stcg(&G->ans[my_game][lane], (unsigned long long)__float_as_uint(o) | ((unsigned long long)my_tag << 32));
             }
-            if (P.prof && e == 0 && lane == 0) { SP_PROF(0, 1); SP_PROF(1, nb); SP_PROF(2, t_d1 - t_d0); SP_PROF(3, clock64() - t_d1); }
+            if (P.prof && e == 0 && lane == 0) {
+                SP_PROF(0, 1); SP_PROF(1, nb); SP_PROF(2, t_work - t_d0); SP_PROF(3, clock64() - t_work);
+                SP_PROF(4, t_d1 - t_work); SP_PROF(5, t_d2 - t_d1); SP_PROF(6, t_d3 - t_d2); SP_PROF(7, clock64() - t_d3);
+            }
         }
     }
     TC_FENCE_BEFORE();
@@ -567,7 +614,7 @@ bool c4_split_eligible(const c4_net *net, int max_games, long long live_games)
 }
 
 // Run the pool until every game slot is idle / done, `stop_games` games have finished (counter in d.ctr) or `stop_ms` have
-// passed, and wait for it (same contract as c4_fused_run).  d.net_out must be writable device memory of 8 floats per slot.
+// passed, and wait for it (same contract as c4_fused_run).
 int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulations, bool selfplay,
                  unsigned long long stop_games, double stop_ms, cudaStream_t stream)
 {
@@ -584,7 +631,7 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     if (!pd.h_abort) {
         C4_CUDA(cudaHostAlloc((void **)&pd.h_abort, 64, cudaHostAllocMapped));
         C4_CUDA(cudaHostGetDevicePointer((void **)&pd.d_abort, pd.h_abort, 0));
-        C4_CUDA(cudaMalloc((void **)&pd.G, sizeof(SpGlobal)));
+        C4_CUDA(cudaMalloc((void **)&pd.G, sp_rings_off() + (size_t)sms * SP_GMAX * 16));   // rings for any tower count / pool size
         C4_CUDA(cudaStreamCreateWithFlags(&pd.side, cudaStreamNonBlocking));
         C4_CUDA(cudaEventCreateWithFlags(&pd.ev_a, cudaEventDisableTiming));
         C4_CUDA(cudaEventCreateWithFlags(&pd.ev_b, cudaEventDisableTiming));
@@ -599,6 +646,10 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     P.batch_ns = getenv("C4_SP_BATCH_NS") ? atoi(getenv("C4_SP_BATCH_NS")) : 0;
     const int n_net = sp_net_ctas(sms, max_games);
     const int n_tree = std::min(sms - n_net, max_games);
+    unsigned cap = 64;
+    while ((int)cap < max_games) cap <<= 1;
+    P.n_net = n_net;
+    P.ring_cap = cap;
     const int smem = sp_net_smem(net->R);
     auto kn = net->fp16 ? k_sp_net<OpFP16> : k_sp_net<OpBF16>;
     auto kt = selfplay ? k_sp_tree<true> : k_sp_tree<false>;
@@ -611,11 +662,11 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
         C4_CUDA(cudaFuncGetAttributes(&fa, kn));
         C4_CUDA(cudaFuncGetAttributes(&fa, kt));
     }
-    // ring head / tail, flags, answer tags and the entries' seq words all start from zero
-    C4_CUDA(cudaMemsetAsync(pd.G, 0, sizeof(SpGlobal), stream));
+    // ticket counter, flags, answer slots and the rings' stamps all start from zero
+    C4_CUDA(cudaMemsetAsync(pd.G, 0, sp_rings_off() + (size_t)n_net * cap * 16, stream));
     C4_CUDA(cudaEventRecord(pd.ev_a, stream));
     C4_CUDA(cudaStreamWaitEvent(pd.side, pd.ev_a, 0));
-    kn<<<n_net, TC_THREADS, smem, pd.side>>>((const unsigned char *)net->image_tc, net->R, pd.G, const_cast<float *>(d.net_out), d.ctr, P);
+    kn<<<n_net, TC_THREADS, smem, pd.side>>>((const unsigned char *)net->image_tc, net->R, pd.G, d.ctr, P);
     C4_CUDA(cudaGetLastError());
     kt<<<n_tree, SP_TREE_THREADS, 0, stream>>>(d, pd.G, P);
     C4_CUDA(cudaGetLastError());
@@ -642,9 +693,9 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
         C4_CUDA(cudaMemcpy(h, pd.G->prof, sizeof(h), cudaMemcpyDeviceToHost));
         const double ns = (double)std::max(1ULL, h[0]), nr = (double)std::max(1ULL, h[8]);
         fprintf(stderr, "[split prof] %d tree CTAs + %d tower CTAs | strips %llu boards/strip %.2f | tower cycles per strip: idle %.0f busy %.0f "
-                        "(busy share %.2f) | tree runs %llu cycles/run %.0f tree-warp idle share %.2f\n",
+                        "(busy share %.2f) = claim %.0f + input %.0f + layers %.0f + heads %.0f | tree runs %llu cycles/run %.0f tree-warp idle share %.2f\n",
                 n_tree, n_net, h[0], h[1] / ns, h[2] / ns, h[3] / ns, h[3] / (double)std::max(1ULL, h[2] + h[3]),
-                h[8], h[9] / nr, h[10] / (double)std::max(1ULL, h[9] + h[10]));
+                h[4] / ns, h[5] / ns, h[6] / ns, h[7] / ns, h[8], h[9] / nr, h[10] / (double)std::max(1ULL, h[9] + h[10]));
     }
     if (asked) { c4_set_error("split engine: host deadline passed (C4_FZ_TIMEOUT_S); the launches were aborted"); return -4; }
     return 0;

@@ -231,10 +231,11 @@ __device__ __forceinline__ bool memo_lookup(const C4Dev &d, u64 c0, u64 c1, floa
 // will never answer) read as plain misses; and a waiter that has looked WAITMEMO_PATIENCE times asks for itself.
 #define WAITMEMO_PATIENCE 64
 enum { MEMO_MISS = 0, MEMO_HIT = 1, MEMO_PENDING = 2 };
-__device__ __forceinline__ u64 memo_pending_tag(const C4Dev &d, u64 c0, u64 c1)
+__device__ __forceinline__ u64 memo_pending_tag(uint32_t epoch, u64 c0, u64 c1)
 {
-    return (memo_mix(c1 * 0x9E3779B97F4A7C15ULL ^ memo_mix(c0 + 0xD6E8FEB86659FD93ULL + ((u64)d.memo_epoch << 50))) & ~3ULL) | 2ULL;
+    return (memo_mix(c1 * 0x9E3779B97F4A7C15ULL ^ memo_mix(c0 + 0xD6E8FEB86659FD93ULL + ((u64)epoch << 50))) & ~3ULL) | 2ULL;
 }
+__device__ __forceinline__ u64 memo_pending_tag(const C4Dev &d, u64 c0, u64 c1) { return memo_pending_tag(d.memo_epoch, c0, c1); }
 // like memo_lookup, three-valued; `seen` = the check word that was read (the CAS of memo_claim expects it)
 __device__ __forceinline__ int memo_probe(const C4Dev &d, u64 c0, u64 c1, float &out_lane, int lane, u64 &seen)
 {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- self-play positions/sec at 800 sims/move (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine auto|fused|lockstep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine auto|split|fused|lockstep]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 Workload (ours): BASELINE.json configs[2] as SURVEY.md 8(d) defines it -- 4096 concurrent self-play games per GPU from
@@ -21,10 +21,12 @@ A "step" = one such generation: fresh pool, empty memo, until `--games` games ha
           (identical for every N).
   steady_state = the warm regime (memo filled by several seconds of play) -- context only, a real generation never
           gets there.
-  roofline = the engine's dominant kernel.  Fused engine: ONE kernel (k_fused) holds the tree warps and the tcgen05
-          tower; its tensor-side figure (network FLOPs / kernel time vs the measured sustained bf16 peak) is `roofline`,
-          its HBM-side figure (1.28 KB per simulation + 64 B per memo probe) `roofline_other`.  Lock-step
-          engine: the tree pass / the network kernel from launch durations sampled with CUDA events.
+  roofline = the engine's dominant kernel.  Split engine (default for 32-filter networks): two persistent kernels on
+          disjoint SMs for the whole step -- k_sp_tree (HBM class: 1.28 KB per simulation + 64 B per memo probe, SURVEY.md
+          8d; it bounds the step and is `roofline`) and k_sp_net (tensor: network FLOPs / step time vs the measured
+          sustained bf16 peak; `roofline_other`).  Fused engine: ONE kernel (k_fused) holds both roles; its tensor-side
+          figure is `roofline`, its HBM-side figure `roofline_other`.  Lock-step engine: the tree pass / the network
+          kernel from launch durations sampled with CUDA events.
           `traffic` is null: no DRAM counter is read inside this run (ncu captures are under profiles/).
   cpu_baseline = the oracle port (oracle/selfplay_port.py) on the box's host cores, bounded sample (rank 0, N=1 only).
 --impl reference: the CPU port alone, all host cores, same metric / config.
@@ -164,7 +166,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "fused", "lockstep"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "split", "fused", "lockstep"])
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU = games a step runs to completion")
     ap.add_argument("--e2e-games", type=int, default=16384, help="games per GPU of the end-to-end generation (4 pool-fulls)")
     ap.add_argument("--gen-games", type=int, default=1200, help="games of the example_config generation (configs[3])")
@@ -311,15 +313,19 @@ def main():
                                   "after_device_seconds_of_play": t_warm / 1e3,
                                   "note": "memo warmed by seconds of play with one network: not reachable in a real generation"}
         if world == 1 and args.engine == "auto":
-            other = "lockstep" if engine == "fused" else "fused"
-            os.environ["C4_ENGINE"] = other
-            p4 = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=1000)
-            rr = [p4.stream(stop_games=args.games, reset=True, cold_memo=True) for _ in range(3)][1:]
-            if rr[0]["engine"] == other:
-                extras["engine_ab"] = {"engine": other, "value": sum(x["positions"] for x in rr) / sum(x["device_ms"] for x in rr) * 1e3,
-                                       "unit": UNIT, "what": "the same cold generation on this package's other engine"}
-            p4.engine.close()
+            ab = []
+            for other in ("split", "fused", "lockstep"):
+                if other == engine:
+                    continue
+                os.environ["C4_ENGINE"] = other
+                p4 = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=1000)
+                rr = [p4.stream(stop_games=args.games, reset=True, cold_memo=True) for _ in range(3)][1:]
+                if rr[0]["engine"] == other:
+                    ab.append({"engine": other, "value": sum(x["positions"] for x in rr) / sum(x["device_ms"] for x in rr) * 1e3,
+                               "unit": UNIT, "memo_hit_rate": sum(x["memo_hits"] for x in rr) / max(1, sum(x["memo_hits"] + x["evals"] for x in rr))})
+                p4.engine.close()
             os.environ.pop("C4_ENGINE")
+            extras["engine_ab"] = {"what": "the same cold generation on this package's other engines", "runs": ab}
 
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
@@ -329,17 +335,30 @@ def main():
         tf = evals * flops / secs / 1e12 / world                              # per GPU
         tree_bytes = positions * SIMS * 1280.0 + (evals + hits) * 64.0
         gbs = tree_bytes / secs / 1e9 / world
-        if engine == "fused":
-            kname = "k_fused<OpFP16,selfplay> (persistent: tree warps + tcgen05 tower per SM, one launch per step)"
-            roof_t = {"kernel": kname, "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+        if engine in ("fused", "split"):
+            # persistent engines: the kernel(s) run for the whole step, so launch duration = step time
+            if engine == "fused":
+                kname_t = kname_h = "k_fused<OpFP16,selfplay> (persistent: tree warps + tcgen05 tower per SM, one launch per step)"
+                where_t = where_h = ""
+            else:
+                sms = torch.cuda.get_device_properties(local).multi_processor_count
+                n_net = int(os.environ.get("C4_SP_NET_CTAS", (sms * 72 + 74) // 148))
+                kname_h = "k_sp_tree<selfplay> (persistent tree CTAs: %d of %d SMs, 31 game warps + 1 mail warp each)" % (sms - n_net, sms)
+                kname_t = "k_sp_net<OpFP16> (persistent tcgen05/TMEM tower CTAs: %d of %d SMs, one leaf ring each)" % (n_net, sms)
+                where_h = "; runs on %d of %d SMs for the whole step, peak = whole device" % (sms - n_net, sms)
+                where_t = "; runs on %d of %d SMs for the whole step, peak = whole device" % (n_net, sms)
+            roof_t = {"kernel": kname_t, "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                       "traffic": None, "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals / n_launch,
                       "ms_per_launch": step_ms, "share_of_step": 1.0,
-                      "note": "network FLOPs of the step / step time; the step is bound by instruction issue and dependent-chain "
-                              "latency (tree simulations + the tower's epilogue), not by the tensor pipe"}
-            roof_h = {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                      "note": "network FLOPs of the step / step time; the towers run short strips (latency over fill), bound by the "
+                              "per-tile issue / epilogue chain, not by the tensor pipe" + where_t}
+            roof_h = {"kernel": kname_h, "bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
                       "traffic": None, "peak_source": peak_src.replace("sustained bf16", "copy bandwidth"),
                       "algorithmic_bytes_per_launch": tree_bytes / n_launch, "sims_per_launch": positions * SIMS / n_launch,
-                      "note": "1.28 KB per simulation (SURVEY.md 8d) + 64 B per memo probe; dependent-load latency bound"}
+                      "ms_per_launch": step_ms, "share_of_step": 1.0,
+                      "note": "1.28 KB per simulation (SURVEY.md 8d) + 64 B per memo probe; dependent-load latency bound" + where_h}
+            if engine == "split":
+                roof_t, roof_h = roof_h, roof_t                       # `roofline` = the tree kernel: it bounds the step (tower CTAs have slack)
         else:
             # lock-step engine: per-launch figures of rank 0 from the launches sampled with CUDA events inside the timed steps
             passes = max(1, tot["passes"])

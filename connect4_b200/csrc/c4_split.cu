@@ -41,6 +41,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <thread>
 
 #include "c4_fz.cuh"
@@ -584,32 +585,98 @@ static int sp_sms()
     return sms;
 }
 
-// tower CTAs for a pool of `max_games` slots (env C4_SP_NET_CTAS overrides): the rest of the SMs run trees
-static int sp_net_ctas(int sms, int max_games)
+// tower CTAs (env C4_SP_NET_CTAS overrides); the rest of the SMs run trees.  Measured on a B200 (148 SMs), cold generation,
+// positions/s by tower count (profiles/README.md): 4,096 games 64: 417k, 72: 431k, 80: 421k, 88: 384k; 2,048 games 56: 291k,
+// 72: 308k, 88: 294k; 1,024 games 56: 181k, 72 / 88: 185k; 256 games 72: 56k, 104: 59k; 8,192 games 56: 486k, 72: 484k --
+// just under half of the SMs at every pool size.
+static int sp_net_ctas(int sms)
 {
-    int n = getenv("C4_SP_NET_CTAS") ? atoi(getenv("C4_SP_NET_CTAS")) : (sms * 3) / 8;
-    n = std::max(1, std::min(n, sms - 1));
-    // small pools: one tree CTA per 8 games is plenty, the towers can have the rest
-    (void)max_games;
-    return n;
+    int n = getenv("C4_SP_NET_CTAS") ? atoi(getenv("C4_SP_NET_CTAS")) : (sms * 72 + 74) / 148;
+    return std::max(1, std::min(n, sms - 1));
+}
+
+struct SpDevice {
+    int *h_abort = nullptr, *d_abort = nullptr;
+    SpGlobal *G = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    int coresident = 0;                 // 0 = not probed yet, 1 = two kernels on two streams run side by side, -1 = they do not
+    std::mutex run;                     // one run per device at a time: the rings and answer slots are per device
+};
+static SpDevice g_sp_device[64];
+static std::mutex g_sp_init;
+
+__global__ void k_sp_probe_wait(int *flag, int *result)
+{
+    const unsigned long long t0 = fz_globaltimer();
+    while (ld_vol(flag) == 0) {
+        if (fz_globaltimer() - t0 > 200000000ULL) { *result = -1; return; }      // 0.2 s: the other kernel is not running
+        __nanosleep(1000);
+    }
+    *result = 1;
+}
+__global__ void k_sp_probe_set(int *flag) { st_vol(flag, 1); }
+
+// Per-device buffers, and the one-time co-residency probe.  The engine needs two kernels that wait for each other to run
+// at the same time.  Nothing in CUDA guarantees that for two launches; it holds here because both are launched by one
+// process into two streams of one context and together need no more SMs than the device has -- but a tool that serialises
+// launches (ncu kernel replay, compute-sanitizer, CUDA_LAUNCH_BLOCKING=1) breaks it.  So the first use runs a 1-thread
+// kernel that waits (at most 0.2 s) for a flag set by a second 1-thread kernel on another stream; if the flag never
+// arrives the engine reports itself unsupported and the caller uses the fused / lock-step engines.
+static SpDevice *sp_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SpDevice &pd = g_sp_device[dev];
+    std::lock_guard<std::mutex> lock(g_sp_init);
+    if (pd.coresident != 0) return &pd;
+    const int sms = sp_sms();
+    pd.coresident = -1;
+    if (sms < 8) return &pd;
+    if (cudaHostAlloc((void **)&pd.h_abort, 64, cudaHostAllocMapped) != cudaSuccess) return &pd;
+    if (cudaHostGetDevicePointer((void **)&pd.d_abort, pd.h_abort, 0) != cudaSuccess) return &pd;
+    if (cudaMalloc((void **)&pd.G, sp_rings_off() + (size_t)sms * SP_GMAX * 16) != cudaSuccess) return &pd;   // rings for any tower count / pool size
+    if (cudaStreamCreateWithFlags(&pd.side, cudaStreamNonBlocking) != cudaSuccess) return &pd;
+    if (cudaStreamCreateWithFlags(&pd.side2, cudaStreamNonBlocking) != cudaSuccess) return &pd;
+    if (cudaEventCreateWithFlags(&pd.ev_a, cudaEventDisableTiming) != cudaSuccess) return &pd;
+    if (cudaEventCreateWithFlags(&pd.ev_b, cudaEventDisableTiming) != cudaSuccess) return &pd;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_sp_probe_wait) != cudaSuccess || cudaFuncGetAttributes(&fa, k_sp_probe_set) != cudaSuccess) return &pd;
+    int *w = reinterpret_cast<int *>(pd.G);                               // two scratch words of the (not yet used) control block
+    if (cudaMemsetAsync(w, 0, 8, pd.side) != cudaSuccess) return &pd;
+    if (cudaStreamSynchronize(pd.side) != cudaSuccess) return &pd;
+    k_sp_probe_wait<<<1, 1, 0, pd.side>>>(w, w + 1);
+    k_sp_probe_set<<<1, 1, 0, pd.side2>>>(w);
+    int result = 0;
+    if (cudaStreamSynchronize(pd.side) != cudaSuccess || cudaStreamSynchronize(pd.side2) != cudaSuccess) return &pd;
+    if (cudaMemcpy(&result, w + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return &pd;
+    pd.coresident = result == 1 ? 1 : -1;
+    if (pd.coresident < 0 && getenv("C4_FZ_DEBUG"))
+        fprintf(stderr, "[split] two kernels on two streams do not run side by side here (serialising tool?): engine disabled\n");
+    return &pd;
 }
 
 static bool c4_split_supported(const c4_net *net, int max_games)
 {
     if (!net || net->F != 32 || !net->use_tc || !net->image_tc) return false;
+    if (getenv("C4_SP_DISABLE")) return false;                            // (tests of the other engines' auto policy)
     const int sms = sp_sms();
     if (sms < 8 || max_games > SP_GMAX || max_games < 1) return false;
-    const int n_tree = std::min(sms - sp_net_ctas(sms, max_games), max_games);
+    const int n_tree = std::min(sms - sp_net_ctas(sms), max_games);
     if ((max_games + n_tree - 1) / n_tree > SP_GC_MAX) return false;
-    return sp_net_smem(net->R) <= 227 * 1024;
+    if (sp_net_smem(net->R) > 227 * 1024) return false;
+    const SpDevice *pd = sp_device();
+    return pd && pd->coresident == 1;
 }
 
-// ... and is it the engine to use for `live_games` games in flight?  env C4_ENGINE=split forces it.
+// ... and is it the engine to use?  env C4_ENGINE = "split" / "fused" / "lockstep" forces one.  Auto: whenever it is supported --
+// measured cold generations, positions/s (profiles/README.md), split / fused / lock-step: 256 games 59k / 52k / 23k; 1,024 games
+// 185k / 123k / 96k; 2,048 games 308k / 201k / 181k; 4,096 games 431k / 310k / 336k; 8,192 games 486k / 315k / 427k.
 bool c4_split_eligible(const c4_net *net, int max_games, long long live_games)
 {
     (void)live_games;
     const char *want = getenv("C4_ENGINE");
-    if (!want || strcmp(want, "split")) return false;
+    if (want && (!strcmp(want, "fused") || !strcmp(want, "lockstep"))) return false;
     return c4_split_supported(net, max_games);
 }
 
@@ -619,23 +686,11 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
                  unsigned long long stop_games, double stop_ms, cudaStream_t stream)
 {
     (void)simulations;
-    int dev = 0;
-    C4_CUDA(cudaGetDevice(&dev));
     const int sms = sp_sms();
-    C4_REQUIRE(c4_split_supported(net, max_games), "split engine: network or pool size not supported");
-    struct PerDevice { int *h_abort = nullptr, *d_abort = nullptr; SpGlobal *G = nullptr; cudaStream_t side = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr; };
-    static PerDevice per_device[64];
-    C4_REQUIRE(dev >= 0 && dev < 64, "split engine: device index");
-    PerDevice &pd = per_device[dev];
+    C4_REQUIRE(c4_split_supported(net, max_games), "split engine: network, pool size or device not supported");
+    SpDevice &pd = *sp_device();
+    std::lock_guard<std::mutex> run_lock(pd.run);
     static const bool debug = getenv("C4_FZ_DEBUG") != nullptr;
-    if (!pd.h_abort) {
-        C4_CUDA(cudaHostAlloc((void **)&pd.h_abort, 64, cudaHostAllocMapped));
-        C4_CUDA(cudaHostGetDevicePointer((void **)&pd.d_abort, pd.h_abort, 0));
-        C4_CUDA(cudaMalloc((void **)&pd.G, sp_rings_off() + (size_t)sms * SP_GMAX * 16));   // rings for any tower count / pool size
-        C4_CUDA(cudaStreamCreateWithFlags(&pd.side, cudaStreamNonBlocking));
-        C4_CUDA(cudaEventCreateWithFlags(&pd.ev_a, cudaEventDisableTiming));
-        C4_CUDA(cudaEventCreateWithFlags(&pd.ev_b, cudaEventDisableTiming));
-    }
     *reinterpret_cast<volatile int *>(pd.h_abort) = 0;
     SpParams P;
     P.n_slots = max_games;
@@ -644,7 +699,7 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     P.host_abort = pd.d_abort;
     P.prof = debug ? 1 : 0;
     P.batch_ns = getenv("C4_SP_BATCH_NS") ? atoi(getenv("C4_SP_BATCH_NS")) : 0;
-    const int n_net = sp_net_ctas(sms, max_games);
+    const int n_net = sp_net_ctas(sms);
     const int n_tree = std::min(sms - n_net, max_games);
     unsigned cap = 64;
     while ((int)cap < max_games) cap <<= 1;

@@ -164,13 +164,14 @@ def test_fused_engine_with_the_64_filter_network(monkeypatch, slots, sims, n):
 
 
 def test_generation_handed_over_from_lockstep_to_fused_for_the_drain(monkeypatch):
-    """auto engine policy on a pool with more than 16 games per SM: the lock-step engine (with de-duplication of the
-    evaluations in flight) plays the bulk, the drain -- few games left -- is handed to the fused engine; the records are
-    those of either engine alone"""
+    """auto engine policy without the split engine (what a 64-filter network gets) on a pool with more than 16 games per
+    SM: the lock-step engine (with de-duplication of the evaluations in flight) plays the bulk, the drain -- few games
+    left -- is handed to the fused engine; the records are those of either engine alone"""
     import torch
     model = _model()
     slots = 16 * torch.cuda.get_device_properties(0).multi_processor_count + 300
     monkeypatch.delenv("C4_ENGINE", raising=False)
+    monkeypatch.setenv("C4_SP_DISABLE", "1")
     from connect4_b200.neural.game_pool import SelfPlayPool
     pool = SelfPlayPool(model, _cfg(12), concurrent_games=slots, seed=3)
     auto = _sorted(pool.generate_records(slots + 500))

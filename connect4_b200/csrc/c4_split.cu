@@ -286,16 +286,15 @@ struct SpNetCtl {
     u64 strip_c0[SP_NB], strip_c1[SP_NB];
     float ans[SP_NB][8];
 };
-__host__ __device__ constexpr int sp_ctl_off(int R) { return (TcK<32>::total(R) + 15) & ~15; }
-__host__ __device__ constexpr int sp_net_smem(int R) { return sp_ctl_off(R) + (int)sizeof(SpNetCtl); }
+template <int F> __host__ __device__ constexpr int sp_ctl_off(int R) { return (TcK<F>::total(R) + 15) & ~15; }
+template <int F> __host__ __device__ constexpr int sp_net_smem(int R) { return sp_ctl_off<F>(R) + (int)sizeof(SpNetCtl); }
 
-template <typename OP>
+template <typename OP, int F>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters *ctr, SpParams P)
 {
-    using K = TcK<32>;
-    constexpr int F = 32;
-    static_assert(K::NB == SP_NB && K::EPI_WARPS == TC_EPI_WARPS && !K::SLICED, "geometry of the batch kernel for 32 filters");
+    using K = TcK<F>;                                                      // the batch kernel's geometry (c4_tc.cuh)
+    static_assert(K::NB <= SP_NB && K::EPI_WARPS == TC_EPI_WARPS, "strip control block / epilogue warps");
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = 1 + 2 * R;
     const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -309,7 +308,7 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
     const uint32_t b_accfull = b_wempty + 8 * K::WBARS, b_accempty = b_accfull + 8 * K::ACC_SLOTS;
     const uint32_t b_epi = b_accempty + 8 * K::ACC_SLOTS;                   // T barriers
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * K::WBARS + 2 * K::ACC_SLOTS + K::T);
-    SpNetCtl *S = reinterpret_cast<SpNetCtl *>(smem + sp_ctl_off(R));
+    SpNetCtl *S = reinterpret_cast<SpNetCtl *>(smem + sp_ctl_off<F>(R));
 
     // ---- one-time setup (k_net_tc): zero the strips, small params, barriers, TMEM
     for (int i = threadIdx.x; i < 2 * K::ACT_BYTES / 16; i += blockDim.x)
@@ -340,7 +339,29 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
     if (warp == 0) {
         // ================= weight producer: layer g of the endless (strip, layer) sequence -> ring stage g % WSTAGES; it
         // runs up to WSTAGES layers ahead of the issuer, so the first layers of the NEXT strip are on chip while the tower idles
-        if (lane == 0) {
+        if (lane == 0 && K::SLICED) {
+            // one weight stage, refilled one dy slice at a time: slice dy of layer g is requested as soon as the issuer has
+            // released slice dy of layer g - 1 (c4_net.cu)
+            int g = 0, last[3] = {-1, -1, -1};
+            bool live = true;
+            for (; live; g++)
+                for (int dy = 0; dy < 3 && live; dy++) {
+                    if (g > 0) {
+                        const uint32_t bar = b_wempty + 8 * dy, par = (uint32_t)(g - 1) & 1u;
+                        for (uint32_t it = 0; !mbar_try(bar, par); it++) {
+                            if (it > 4u) __nanosleep(it > 64u ? 500 : 100);
+                            if ((it & 15u) == 15u && ld_vol(&S->quit)) { live = false; break; }
+                        }
+                        if (!live) break;
+                    }
+                    mbar_expect_tx(b_wfull + 8 * dy, K::WSLICE_BYTES);
+                    bulk_g2s(smem_u32(sW + dy * K::WSLICE_BYTES), image + (size_t)(g % L) * K::WSTAGE_BYTES + dy * K::WSLICE_BYTES,
+                             K::WSLICE_BYTES, b_wfull + 8 * dy);
+                    last[dy] = g;
+                }
+            for (int dy = 0; dy < 3; dy++)                                        // no bulk copy in flight at exit
+                if (last[dy] >= 0) mbar_wait(b_wfull + 8 * dy, (uint32_t)last[dy] & 1u);
+        } else if (lane == 0) {
             int g = 0;
             bool live = true;
             for (; live; g++) {
@@ -375,7 +396,7 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
                 const int T = (7 * nb + 15) / 16;
                 for (int l = 0; l < L && live; l++, g++) {
                     const int st = g % K::WSTAGES;
-                    if (!fz_wait(b_wfull + 8 * st, (uint32_t)(g / K::WSTAGES) & 1u, &S->abort)) { live = false; break; }
+                    if (!K::SLICED && !fz_wait(b_wfull + 8 * st, (uint32_t)(g / K::WSTAGES) & 1u, &S->abort)) { live = false; break; }
                     const uint32_t wbase = smem_u32(sW + st * K::WSTAGE_BYTES);
                     const uint32_t abase = smem_u32((l == 0 || (l & 1) == 0) ? sH : sX);   // stem and conv2 read H
                     const uint64_t a_l = umma_desc(abase, K::ROWS * 16, 128);
@@ -393,22 +414,28 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
                         const uint64_t a = a_l + (uint64_t)(128 * t);
                         if (l != 0) {
 #pragma unroll
-                            for (int dy = 0; dy < 3; dy++)
+                            for (int dy = 0; dy < 3; dy++) {
+                                if (K::SLICED && t == 0 && !fz_wait(b_wfull + 8 * dy, (uint32_t)g & 1u, &S->abort)) { live = false; break; }
 #pragma unroll
                                 for (int ks = 0; ks < K::KC / 2; ks++) {
                                     const uint64_t aa = a + 8 * dy + 2 * K::ROWS * ks, bb = b_l + (dy * K::KC + 2 * ks) * K::NN;
                                     if (dy == 0 && ks == 0) umma_f16c<0>(dcol, aa, bb, idesc); else umma_f16c<1>(dcol, aa, bb, idesc);
                                 }
+                                if (K::SLICED && t == T - 1) umma_commit(b_wempty + 8 * dy);  // slice free for the next layer
+                            }
                         } else {                                              // stem: 16 (padded) input channels = one k-step
 #pragma unroll
                             for (int dy = 0; dy < 3; dy++) {
+                                if (K::SLICED && t == 0 && !fz_wait(b_wfull + 8 * dy, (uint32_t)g & 1u, &S->abort)) { live = false; break; }
                                 const uint64_t aa = a + 8 * dy, bb = b_l + dy * K::STEM_KC * K::NN;
                                 if (dy == 0) umma_f16c<0>(dcol, aa, bb, idesc); else umma_f16c<1>(dcol, aa, bb, idesc);
+                                if (K::SLICED && t == T - 1) umma_commit(b_wempty + 8 * dy);
                             }
                         }
+                        if (!live) break;
                         umma_commit(b_accfull + 8 * slot);
                     }
-                    if (live) umma_commit(b_wempty + 8 * st);
+                    if (live && !K::SLICED) umma_commit(b_wempty + 8 * st);
                 }
                 // observe the LAST epilogue phase of tile 0 too (c4_fused.cu: with a one-tile strip the wait for the next
                 // strip's input phase would otherwise alias this strip's phase L - 1)
@@ -589,9 +616,10 @@ static int sp_sms()
 // positions/s by tower count (profiles/README.md): 4,096 games 64: 417k, 72: 431k, 80: 421k, 88: 384k; 2,048 games 56: 291k,
 // 72: 308k, 88: 294k; 1,024 games 56: 181k, 72 / 88: 185k; 256 games 72: 56k, 104: 59k; 8,192 games 56: 486k, 72: 484k --
 // just under half of the SMs at every pool size.
-static int sp_net_ctas(int sms)
+static int sp_net_ctas(int sms, int filters)
 {
-    int n = getenv("C4_SP_NET_CTAS") ? atoi(getenv("C4_SP_NET_CTAS")) : (sms * 72 + 74) / 148;
+    // (a 64-filter evaluation is 8x the tensor work of a 32-filter one: most SMs run towers)
+    int n = getenv("C4_SP_NET_CTAS") ? atoi(getenv("C4_SP_NET_CTAS")) : (filters == 64 ? (sms * 112 + 74) / 148 : (sms * 72 + 74) / 148);
     return std::max(1, std::min(n, sms - 1));
 }
 
@@ -658,13 +686,13 @@ static SpDevice *sp_device()
 
 static bool c4_split_supported(const c4_net *net, int max_games)
 {
-    if (!net || net->F != 32 || !net->use_tc || !net->image_tc) return false;
+    if (!net || (net->F != 32 && net->F != 64) || !net->use_tc || !net->image_tc) return false;
     if (getenv("C4_SP_DISABLE")) return false;                            // (tests of the other engines' auto policy)
     const int sms = sp_sms();
     if (sms < 8 || max_games > SP_GMAX || max_games < 1) return false;
-    const int n_tree = std::min(sms - sp_net_ctas(sms), max_games);
+    const int n_tree = std::min(sms - sp_net_ctas(sms, net->F), max_games);
     if ((max_games + n_tree - 1) / n_tree > SP_GC_MAX) return false;
-    if (sp_net_smem(net->R) > 227 * 1024) return false;
+    if ((net->F == 32 ? sp_net_smem<32>(net->R) : sp_net_smem<64>(net->R)) > 227 * 1024) return false;
     const SpDevice *pd = sp_device();
     return pd && pd->coresident == 1;
 }
@@ -699,14 +727,14 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     P.host_abort = pd.d_abort;
     P.prof = debug ? 1 : 0;
     P.batch_ns = getenv("C4_SP_BATCH_NS") ? atoi(getenv("C4_SP_BATCH_NS")) : 0;
-    const int n_net = sp_net_ctas(sms);
+    const int n_net = sp_net_ctas(sms, net->F);
     const int n_tree = std::min(sms - n_net, max_games);
     unsigned cap = 64;
     while ((int)cap < max_games) cap <<= 1;
     P.n_net = n_net;
     P.ring_cap = cap;
-    const int smem = sp_net_smem(net->R);
-    auto kn = net->fp16 ? k_sp_net<OpFP16> : k_sp_net<OpBF16>;
+    const int smem = net->F == 32 ? sp_net_smem<32>(net->R) : sp_net_smem<64>(net->R);
+    auto kn = net->F == 32 ? (net->fp16 ? k_sp_net<OpFP16, 32> : k_sp_net<OpBF16, 32>) : (net->fp16 ? k_sp_net<OpFP16, 64> : k_sp_net<OpBF16, 64>);
     auto kt = selfplay ? k_sp_tree<true> : k_sp_tree<false>;
     C4_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // Both kernels must be LOADED before the first of them starts: with lazy module loading (the CUDA 12 default) the first

@@ -153,3 +153,18 @@ def test_deduplication_in_the_split_engine_changes_work_not_results(monkeypatch)
     monkeypatch.delenv("C4_MEMO_NO_DEDUP", raising=False)
     assert out[True][0] < out[False][0]
     _same(out[True][1], out[False][1])
+
+
+@pytest.mark.parametrize("slots,sims,n", [(6, 16, 10), (150, 32, 300)])
+def test_split_engine_with_the_64_filter_network(monkeypatch, slots, sims, n):
+    """the reference's example_config network (64 filters / 6 residual blocks / 6 fc layers, oinkoink/data/example_config.py):
+    the tower CTAs run the batch kernel's 64-filter geometry (6-board strips, weight stage refilled slice by slice)"""
+    import torch
+    from connect4_b200.neural.config import ModelConfig, NetConfig
+    from connect4_b200.neural.model import ModelWrapper
+    torch.manual_seed(0)
+    model = ModelWrapper(ModelConfig(net_config=NetConfig(filters=64, n_fc_layers=6, n_residuals=6)))
+    a = _generate(monkeypatch, "split", model, _cfg(sims), slots, n)
+    b = _generate(monkeypatch, "lockstep", model, _cfg(sims), slots, n)
+    assert sorted(set(a["game_id"].tolist())) == list(range(n))
+    _same(a, b)

@@ -1,27 +1,34 @@
-// c4_split.cu -- the split persistent self-play engine: tree CTAs and tower CTAs on SEPARATE SMs, one leaf ring in HBM.
+// c4_split.cu -- the split persistent self-play engine: tree CTAs and tower CTAs on SEPARATE SMs, one leaf ring per tower in HBM.
 //
 // What it replaces: the same free-running runtime of the reference as the fused engine (game threads that never wait for
 // an unrelated game, oinkoink/neural/game_pool.py:15-49; an inference server that batches whatever requests are there,
 // oinkoink/neural/inference_server.py:37-63).  The fused engine (c4_fused.cu) puts tree warps AND a tower on every SM; its
 // ncu profile shows the price: the two roles share the SM's issue slots, registers (64 per thread for both) and L1, the
 // tower runs 1,850 cycles per tile-layer instead of 950, strips are 9 boards.  Here every SM has ONE role:
-//   * k_sp_tree: n_tree CTAs x 1,024 threads.  31 tree warps run the CTA's own games exactly as in the fused engine
-//     (fz_run_game, c4_fz.cuh -- the same device functions as the lock-step pass, hence identical records); a leaf that
-//     misses the evaluation memo goes into ONE global leaf ring (32-byte entries in HBM / L2).  Warp 31 is the CTA's mail
-//     warp: it polls the answer tags of the CTA's waiting games (contiguous words, a few sectors per sweep), flips their
-//     status words in shared memory and keeps the stop / abort flags.  No tower here: ~3 KB of shared memory, the rest of
-//     the 228 KB is L1 for the node records.
-//   * k_sp_net: n_net CTAs x 576 threads = the batch kernel's tower (c4_net.cu: 16-board strips, two epilogue groups, 94
-//     registers, 200 KB of shared memory) as a server with its OWN leaf ring: the dispatcher (epilogue warp 0) takes what
-//     its ring holds -- up to a strip; no batching delay -- and the strip's answers go to the games' answer slots.
+//   * tree CTAs (1,024 threads): 31 tree warps run the CTA's own games exactly as in the fused engine (fz_run_game,
+//     c4_fz.cuh -- the same device functions as the lock-step pass, hence identical records); a leaf that misses the
+//     evaluation memo goes into a tower's leaf ring (16-byte entries in HBM / L2).  Warp 31 is the CTA's mail warp: it polls
+//     the answer slots of the CTA's waiting games and the memo entries other games wait for, flips their status words in
+//     shared memory and keeps the stop / abort flags.
+//   * tower CTAs = the batch kernel's tower (c4_net.cu: 16-board strips, two epilogue groups of 8 warps at 96 registers,
+//     200 KB of shared memory; 6-board strips for 64 filters) as a server with its OWN leaf ring: the dispatcher (epilogue
+//     warp 0) takes what its ring holds -- up to a strip; no batching delay -- and the strip's answers go to the games'
+//     answer slots.
 //   * requests are dealt round-robin: ONE atomicAdd on a global ticket counter gives a request both its tower (ticket %
 //     n_net) and its slot in that tower's ring (ticket / n_net); a tower learns how many entries it owns from the same
 //     counter.  Single consumer per ring: no CAS, no contention between the towers (the first version had one shared ring
 //     claimed with a CAS on its head: 16k cycles per strip went into the claim).
-// The two kernels are launched on two streams and are co-resident by construction: every CTA of either kernel needs a
-// whole SM (64 K registers / 200 KB of shared memory) and n_tree + n_net <= number of SMs.  All cross-SM hand-offs are
-// polls of L2-resident words with a back-off; every wait is bounded (tree-warp watchdog -> abort flag -> both kernels
-// leave; host deadline through a mapped word), so a protocol bug ends in an error code, not in a hung device.
+// ONE launch (k_sp_one): CTAs 0 .. n_tree - 1 are tree CTAs, the rest tower CTAs; one CTA of 1,024 threads per SM and
+// n_tree + n_net <= number of SMs, so all of them are resident at once -- the form a kernel that waits must have.  A launch
+// has one block size and one register count (64 at 1,024 threads): a tower CTA reshapes its register file with setmaxnreg --
+// the 12 warps without a role drop to 24 registers and leave, the producer / issuer warpgroup drops to 40, the 16 epilogue warps
+// rise to the 96 the batch kernel's epilogue needs.  A launch also has one shared-memory size, so the tree CTAs carry the
+// tower's 200 KB and keep ~28 KB of L1 (cost: 420k instead of 428k positions/s).  The two-launch form (k_sp_tree + k_sp_net on two
+// streams, env C4_SP_LAUNCH=two) keeps the tree CTAs' L1 whole, but CUDA does not promise that two launches run side by
+// side -- a tool that serialises launches (ncu, CUDA_LAUNCH_BLOCKING=1) deadlocks it until the watchdog -- so it is opt-in
+// and gated by a co-residency probe.  All cross-SM hand-offs are polls of L2-resident words with a back-off; every wait is
+// bounded (tree-warp watchdog -> abort flag -> all CTAs leave; host deadline through a mapped word), so a protocol bug ends
+// in an error code, not in a hung device.
 //
 // NO gpu-scope fence on the data path: __threadfence() invalidates the SM's whole L1 (CCTL.IVALL) -- in a tree CTA that
 // is the cache of the node records, and the first version paid it on every request and every answer.  Instead every
@@ -70,6 +77,7 @@ struct SpParams {
     const int *host_abort;              // mapped host word: non-zero = the host gave up waiting, leave at once
     int prof;                           // accumulate cycle / event sums in SpGlobal::prof (C4_FZ_DEBUG)
     int batch_ns;                       // a dispatcher that finds less than a strip waits up to this long for more
+    int n_tree;                         // tree CTAs (the first n_tree CTAs of a single launch)
     int n_net;                          // tower CTAs = rings
     unsigned ring_cap;                  // entries per ring (power of two >= game slots)
 };
@@ -151,15 +159,13 @@ struct SpPort {
 };
 
 // ------------------------------------------------------------------------------------------------ tree CTAs
+// (body of a tree CTA: CTAs 0 .. n_tree - 1 of the launch)
 template <bool SELFPLAY>
-__global__ void __launch_bounds__(SP_TREE_THREADS, 1)
-k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
+__device__ __forceinline__ void sp_tree_body(const C4Dev &dg, SpGlobal *G, const SpParams &P, SpCtl *S)
 {
-    __shared__ SpCtl Sm;
-    SpCtl *S = &Sm;
     const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // this CTA's game slots
-    const int per = P.n_slots / (int)gridDim.x, extra = P.n_slots % (int)gridDim.x;
+    const int per = P.n_slots / P.n_tree, extra = P.n_slots % P.n_tree;
     const int Gc = per + ((int)blockIdx.x < extra ? 1 : 0);
     const int g0 = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
 
@@ -207,7 +213,7 @@ k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
             __nanosleep(n_wait ? 150 : 1000);
         }
         __syncwarp();
-        if (lane == 0 && atomicAdd(&G->trees_exited, 1) == (int)gridDim.x - 1) { __threadfence(); st_vol(&G->quit, 1); }
+        if (lane == 0 && atomicAdd(&G->trees_exited, 1) == P.n_tree - 1) { __threadfence(); st_vol(&G->quit, 1); }
     } else {
         // ================= tree warps (the picker loop of the fused engine)
         const SpPort port{S, G, dg.memo, dg.memo_mask, dg.memo_epoch, (unsigned)P.n_net, P.ring_cap};
@@ -289,13 +295,17 @@ struct SpNetCtl {
 template <int F> __host__ __device__ constexpr int sp_ctl_off(int R) { return (TcK<F>::total(R) + 15) & ~15; }
 template <int F> __host__ __device__ constexpr int sp_net_smem(int R) { return sp_ctl_off<F>(R) + (int)sizeof(SpNetCtl); }
 
-template <typename OP, int F>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters *ctr, SpParams P)
+// (body of tower CTA `tower`.  Warp roles: EPI0 .. EPI0 + 15 epilogue, PRODUCER, ISSUER.  ONE_LAUNCH: the CTA has 1,024
+//  threads at 64 registers like the tree CTAs of the same launch; the 16 epilogue warps raise their register limit to 96 with
+//  setmaxnreg from what the 12 warps without a role and the producer / issuer warpgroup give back:
+//  16 x 32 x 96 + 4 x 32 x 40 + 12 x 32 x 24 = 63,488 <= 65,536.)
+template <typename OP, int F, int EPI0, int PRODUCER, int ISSUER, bool ONE_LAUNCH>
+__device__ __forceinline__ void sp_net_body(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters *ctr,
+                                            const SpParams &P, unsigned char *smem, const unsigned tower)
 {
     using K = TcK<F>;                                                      // the batch kernel's geometry (c4_tc.cuh)
     static_assert(K::NB <= SP_NB && K::EPI_WARPS == TC_EPI_WARPS, "strip control block / epilogue warps");
-    extern __shared__ __align__(16) unsigned char smem[];
+    static_assert(EPI0 % 4 == 0 || !ONE_LAUNCH, "setmaxnreg works on warpgroups");
     const int L = 1 + 2 * R;
     const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -326,7 +336,7 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
         for (int i = 0; i < K::T; i++) mbar_init(b_epi + 8 * i, K::GROUP_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == PRODUCER) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" :: "r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -335,8 +345,20 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
     __syncthreads();
     TC_FENCE_AFTER();
     const uint32_t tmem = *tmem_slot;
+    if (ONE_LAUNCH) {
+        if (warp >= EPI0 + 16 && (warp < (PRODUCER & ~3) || warp >= (PRODUCER & ~3) + 4)) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n");          // no role in a tower CTA
+            return;
+        }
+        if (warp >= (PRODUCER & ~3) && warp < (PRODUCER & ~3) + 4) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");          // producer / issuer warpgroup (single threads at work)
+            if (warp != PRODUCER && warp != ISSUER) return;
+        } else {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 96;\n");          // epilogue warps
+        }
+    }
 
-    if (warp == 0) {
+    if (warp == PRODUCER) {
         // ================= weight producer: layer g of the endless (strip, layer) sequence -> ring stage g % WSTAGES; it
         // runs up to WSTAGES layers ahead of the issuer, so the first layers of the NEXT strip are on chip while the tower idles
         if (lane == 0 && K::SLICED) {
@@ -381,7 +403,7 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
             // no bulk copy may be in flight when the CTA exits: wait for the stages requested last
             for (int i = max(0, g - K::WSTAGES); i < g; i++) mbar_wait(b_wfull + 8 * (i % K::WSTAGES), (uint32_t)(i / K::WSTAGES) & 1u);
         }
-    } else if (warp == 1) {
+    } else if (warp == ISSUER) {
         // ================= MMA issuer (one thread): the strip loop of k_net_tc with strips that arrive at run time
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)OP::FMT << 7) | ((uint32_t)OP::FMT << 10) |
@@ -444,8 +466,8 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
         }
     } else {
         // ================= epilogue warps (+ the dispatcher in the first of them)
-        const int e = warp - 2, quad = warp & 3, half = (e >> 2) % K::SLICES, group = e / K::GROUP_WARPS;
-        const int et = threadIdx.x - 64;                                     // 0..511
+        const int e = warp - EPI0, quad = warp & 3, half = (e >> 2) % K::SLICES, group = e / K::GROUP_WARPS;
+        const int et = threadIdx.x - 32 * EPI0;                              // 0..511
         EpiCtx E;
         E.b_accfull = b_accfull; E.b_accempty = b_accempty; E.b_epi = b_epi;
         E.tmem_acc = tmem + ((uint32_t)(quad * 32) << 16) + K::ACC_COL0 + TC_CH * half;
@@ -459,13 +481,13 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
         E.calib = nullptr;
         int c = 0;                                                           // global (strip, layer, tile) counter
         unsigned ring_head = 0u;                                             // dispatcher: entries of this tower's ring consumed
-        const unsigned long long *ring = sp_ring(G, P.ring_cap, (int)blockIdx.x);
+        const unsigned long long *ring = sp_ring(G, P.ring_cap, (int)tower);
         for (;;) {
             const long long t_d0 = clock64();
             long long t_work = t_d0;                                         // dispatcher: first look that found leaves
             if (e == 0) {
                 // ---- dispatch: take what this tower's ring holds (up to one strip).  The ring's entries are the tickets
-                // n = k * n_net + blockIdx.x; `ticket` tickets have been issued so far.
+                // n = k * n_net + tower; `ticket` tickets have been issued so far.
                 int k = 0;
                 long long t_first = 0;
                 for (uint32_t it = 1;; it++) {
@@ -473,7 +495,7 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
                     int q = 0;
                     if (lane == 0) {
                         const unsigned t = ld_volu(&G->ticket);
-                        issued = (t + (unsigned)P.n_net - 1u - blockIdx.x) / (unsigned)P.n_net;
+                        issued = (t + (unsigned)P.n_net - 1u - tower) / (unsigned)P.n_net;
                         q = ld_vol(&G->quit) | (ld_vol(&G->abort) << 1);
                     }
                     issued = __shfl_sync(FULL, issued, 0); q = __shfl_sync(FULL, q, 0);
@@ -596,11 +618,38 @@ k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters
         }
     }
     TC_FENCE_BEFORE();
-    __syncthreads();
-    if (warp == 0) {
+    asm volatile("bar.sync 2, 576;\n" ::: "memory");                       // the 18 warps with a role
+    if (warp == PRODUCER) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem) : "memory");
     }
+}
+
+// ---- the kernels.  Two launches on two streams (tree CTAs: 2 KB of shared memory, the rest of the SM's 256 KB is L1 for the
+// node records) ...
+template <bool SELFPLAY>
+__global__ void __launch_bounds__(SP_TREE_THREADS, 1)
+k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
+{
+    __shared__ SpCtl Sm;
+    sp_tree_body<SELFPLAY>(dg, G, P, &Sm);
+}
+template <typename OP, int F>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_sp_net(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters *ctr, SpParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    sp_net_body<OP, F, 2, 0, 1, false>(image, R, G, ctr, P, smem, blockIdx.x);
+}
+// ... or ONE launch whose CTAs take a role by index (co-resident by construction: one CTA per SM, grid <= SMs; this is the
+// form ncu can profile).  Every CTA then has the tower's shared memory, so the tree CTAs keep only ~28 KB (32 filters) of L1.
+template <typename OP, int F, bool SELFPLAY>
+__global__ void __launch_bounds__(SP_TREE_THREADS, 1)
+k_sp_one(const C4Dev dg, const unsigned char *__restrict__ image, int R, SpGlobal *G, SpParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    if ((int)blockIdx.x < P.n_tree) sp_tree_body<SELFPLAY>(dg, G, P, reinterpret_cast<SpCtl *>(smem));
+    else sp_net_body<OP, F, 0, 16, 17, true>(image, R, G, dg.ctr, P, smem, blockIdx.x - (unsigned)P.n_tree);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -694,7 +743,16 @@ static bool c4_split_supported(const c4_net *net, int max_games)
     if ((max_games + n_tree - 1) / n_tree > SP_GC_MAX) return false;
     if ((net->F == 32 ? sp_net_smem<32>(net->R) : sp_net_smem<64>(net->R)) > 227 * 1024) return false;
     const SpDevice *pd = sp_device();
-    return pd && pd->coresident == 1;
+    return pd && pd->G;                                                   // (two launches need pd->coresident == 1, one launch does not)
+}
+
+// ONE launch by default.  env C4_SP_LAUNCH=two: two launches on two streams, if the device runs them side by side (probe) --
+// the tree CTAs then keep the SM's whole L1 (428k instead of 420k positions/s on the benchmark generation), at the price of
+// relying on co-residency that CUDA does not promise.
+static bool sp_two_launches(const SpDevice &pd)
+{
+    const char *want = getenv("C4_SP_LAUNCH");
+    return want && !strcmp(want, "two") && pd.coresident == 1;
 }
 
 // ... and is it the engine to use?  env C4_ENGINE = "split" / "fused" / "lockstep" forces one.  Auto: whenever it is supported --
@@ -733,28 +791,41 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     while ((int)cap < max_games) cap <<= 1;
     P.n_net = n_net;
     P.ring_cap = cap;
+    P.n_tree = n_tree;
     const int smem = net->F == 32 ? sp_net_smem<32>(net->R) : sp_net_smem<64>(net->R);
-    auto kn = net->F == 32 ? (net->fp16 ? k_sp_net<OpFP16, 32> : k_sp_net<OpBF16, 32>) : (net->fp16 ? k_sp_net<OpFP16, 64> : k_sp_net<OpBF16, 64>);
-    auto kt = selfplay ? k_sp_tree<true> : k_sp_tree<false>;
-    C4_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    // Both kernels must be LOADED before the first of them starts: with lazy module loading (the CUDA 12 default) the first
-    // launch of a function loads it, and that load can wait for running kernels -- here for a tower kernel that itself
-    // waits for the tree kernel: a deadlock, and it was the first thing the bring-up hit.
-    {
-        cudaFuncAttributes fa;
-        C4_CUDA(cudaFuncGetAttributes(&fa, kn));
-        C4_CUDA(cudaFuncGetAttributes(&fa, kt));
-    }
     // ticket counter, flags, answer slots and the rings' stamps all start from zero
     C4_CUDA(cudaMemsetAsync(pd.G, 0, sp_rings_off() + (size_t)n_net * cap * 16, stream));
-    C4_CUDA(cudaEventRecord(pd.ev_a, stream));
-    C4_CUDA(cudaStreamWaitEvent(pd.side, pd.ev_a, 0));
-    kn<<<n_net, TC_THREADS, smem, pd.side>>>((const unsigned char *)net->image_tc, net->R, pd.G, d.ctr, P);
-    C4_CUDA(cudaGetLastError());
-    kt<<<n_tree, SP_TREE_THREADS, 0, stream>>>(d, pd.G, P);
-    C4_CUDA(cudaGetLastError());
-    C4_CUDA(cudaEventRecord(pd.ev_b, pd.side));
-    C4_CUDA(cudaStreamWaitEvent(stream, pd.ev_b, 0));
+    const bool two = sp_two_launches(pd);
+    if (two) {
+        auto kn = net->F == 32 ? (net->fp16 ? k_sp_net<OpFP16, 32> : k_sp_net<OpBF16, 32>) : (net->fp16 ? k_sp_net<OpFP16, 64> : k_sp_net<OpBF16, 64>);
+        auto kt = selfplay ? k_sp_tree<true> : k_sp_tree<false>;
+        C4_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // Both kernels must be LOADED before the first of them starts: with lazy module loading (the CUDA 12 default) the
+        // first launch of a function loads it, and that load can wait for running kernels -- here for a tower kernel that
+        // itself waits for the tree kernel: a deadlock, and it was the first thing the bring-up hit.
+        {
+            cudaFuncAttributes fa;
+            C4_CUDA(cudaFuncGetAttributes(&fa, kn));
+            C4_CUDA(cudaFuncGetAttributes(&fa, kt));
+        }
+        C4_CUDA(cudaEventRecord(pd.ev_a, stream));
+        C4_CUDA(cudaStreamWaitEvent(pd.side, pd.ev_a, 0));
+        kn<<<n_net, TC_THREADS, smem, pd.side>>>((const unsigned char *)net->image_tc, net->R, pd.G, d.ctr, P);
+        C4_CUDA(cudaGetLastError());
+        kt<<<n_tree, SP_TREE_THREADS, 0, stream>>>(d, pd.G, P);
+        C4_CUDA(cudaGetLastError());
+        C4_CUDA(cudaEventRecord(pd.ev_b, pd.side));
+        C4_CUDA(cudaStreamWaitEvent(stream, pd.ev_b, 0));
+    } else {
+        void (*k1)(const C4Dev, const unsigned char *, int, SpGlobal *, SpParams);
+        if (net->F == 32) k1 = selfplay ? (net->fp16 ? k_sp_one<OpFP16, 32, true> : k_sp_one<OpBF16, 32, true>)
+                                        : (net->fp16 ? k_sp_one<OpFP16, 32, false> : k_sp_one<OpBF16, 32, false>);
+        else k1 = selfplay ? (net->fp16 ? k_sp_one<OpFP16, 64, true> : k_sp_one<OpBF16, 64, true>)
+                           : (net->fp16 ? k_sp_one<OpFP16, 64, false> : k_sp_one<OpBF16, 64, false>);
+        C4_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k1<<<n_tree + n_net, SP_TREE_THREADS, smem, stream>>>(d, (const unsigned char *)net->image_tc, net->R, pd.G, P);
+        C4_CUDA(cudaGetLastError());
+    }
     const double limit_s = getenv("C4_FZ_TIMEOUT_S") ? atof(getenv("C4_FZ_TIMEOUT_S")) : 900.0;
     const auto t0 = std::chrono::steady_clock::now();
     bool asked = false;
@@ -775,9 +846,9 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
         unsigned long long h[32];
         C4_CUDA(cudaMemcpy(h, pd.G->prof, sizeof(h), cudaMemcpyDeviceToHost));
         const double ns = (double)std::max(1ULL, h[0]), nr = (double)std::max(1ULL, h[8]);
-        fprintf(stderr, "[split prof] %d tree CTAs + %d tower CTAs | strips %llu boards/strip %.2f | tower cycles per strip: idle %.0f busy %.0f "
+        fprintf(stderr, "[split prof] %d tree CTAs + %d tower CTAs, %s | strips %llu boards/strip %.2f | tower cycles per strip: idle %.0f busy %.0f "
                         "(busy share %.2f) = claim %.0f + input %.0f + layers %.0f + heads %.0f | tree runs %llu cycles/run %.0f tree-warp idle share %.2f\n",
-                n_tree, n_net, h[0], h[1] / ns, h[2] / ns, h[3] / ns, h[3] / (double)std::max(1ULL, h[2] + h[3]),
+                n_tree, n_net, two ? "two launches" : "one launch", h[0], h[1] / ns, h[2] / ns, h[3] / ns, h[3] / (double)std::max(1ULL, h[2] + h[3]),
                 h[4] / ns, h[5] / ns, h[6] / ns, h[7] / ns, h[8], h[9] / nr, h[10] / (double)std::max(1ULL, h[9] + h[10]));
     }
     if (asked) { c4_set_error("split engine: host deadline passed (C4_FZ_TIMEOUT_S); the launches were aborted"); return -4; }

@@ -65,13 +65,14 @@ def test_split_generation_with_start_positions_and_bf16_operands(monkeypatch):
 
 
 def test_split_generation_does_not_depend_on_towers_memo_or_deduplication(monkeypatch):
-    """the number of tower CTAs (3 .. 120 of 148 SMs), the evaluation memo and the de-duplication of evaluations in flight
-    change who does which work when, never the records"""
+    """the number of tower CTAs (3 .. 120 of 148 SMs), the evaluation memo, the de-duplication of evaluations in flight and
+    the launch form (one launch with roles by CTA index / two launches) change who does which work when, never the records"""
     model = _model()
     recs = []
-    knobs = ("C4_SP_NET_CTAS", "C4_MEMO_LOG2", "C4_MEMO_NO_DEDUP")
+    knobs = ("C4_SP_NET_CTAS", "C4_MEMO_LOG2", "C4_MEMO_NO_DEDUP", "C4_SP_LAUNCH")
     for env in ({}, {"C4_SP_NET_CTAS": "3"}, {"C4_SP_NET_CTAS": "120"}, {"C4_MEMO_LOG2": "0"}, {"C4_MEMO_NO_DEDUP": "1"},
-                {"C4_MEMO_LOG2": "8"}):                       # 256 entries: colliding keys overwrite PENDING tags all the time
+                {"C4_MEMO_LOG2": "8"},                        # 256 entries: colliding keys overwrite PENDING tags all the time
+                {"C4_SP_LAUNCH": "two"}):                     # tree and tower kernels as two launches on two streams
         for k in knobs:
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():

@@ -21,10 +21,10 @@ A "step" = one such generation: fresh pool, empty memo, until `--games` games ha
           (identical for every N).
   steady_state = the warm regime (memo filled by several seconds of play) -- context only, a real generation never
           gets there.
-  roofline = the engine's dominant kernel.  Split engine (default for 32-filter networks): two persistent kernels on
-          disjoint SMs for the whole step -- k_sp_tree (HBM class: 1.28 KB per simulation + 64 B per memo probe, SURVEY.md
-          8d; it bounds the step and is `roofline`) and k_sp_net (tensor: network FLOPs / step time vs the measured
-          sustained bf16 peak; `roofline_other`).  Fused engine: ONE kernel (k_fused) holds both roles; its tensor-side
+  roofline = the engine's dominant kernel.  Split engine (default): ONE persistent launch per step (k_sp_one) whose CTAs
+          take a role by index -- tree CTAs (HBM class: 1.28 KB per simulation + 64 B per memo probe; they
+          bound the step and are `roofline`) and tower CTAs (tensor: network FLOPs / step time vs the measured sustained
+          bf16 peak; `roofline_other`).  Fused engine: ONE kernel (k_fused) holds both roles; its tensor-side
           figure is `roofline`, its HBM-side figure `roofline_other`.  Lock-step engine: the tree pass / the network
           kernel from launch durations sampled with CUDA events.
           `traffic` is null: no DRAM counter is read inside this run (ncu captures are under profiles/).
@@ -343,8 +343,8 @@ def main():
             else:
                 sms = torch.cuda.get_device_properties(local).multi_processor_count
                 n_net = int(os.environ.get("C4_SP_NET_CTAS", (sms * 72 + 74) // 148))
-                kname_h = "k_sp_tree<selfplay> (persistent tree CTAs: %d of %d SMs, 31 game warps + 1 mail warp each)" % (sms - n_net, sms)
-                kname_t = "k_sp_net<OpFP16> (persistent tcgen05/TMEM tower CTAs: %d of %d SMs, one leaf ring each)" % (n_net, sms)
+                kname_h = "k_sp_one<OpFP16,32,selfplay>, tree CTAs (%d of %d SMs: 31 game warps + 1 mail warp each)" % (sms - n_net, sms)
+                kname_t = "k_sp_one<OpFP16,32,selfplay>, tower CTAs (%d of %d SMs: tcgen05/TMEM tower, one leaf ring each)" % (n_net, sms)
                 where_h = "; runs on %d of %d SMs for the whole step, peak = whole device" % (sms - n_net, sms)
                 where_t = "; runs on %d of %d SMs for the whole step, peak = whole device" % (n_net, sms)
             roof_t = {"kernel": kname_t, "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,

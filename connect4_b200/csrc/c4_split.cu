@@ -21,7 +21,7 @@
 // ONE launch (k_sp_one): CTAs 0 .. n_tree - 1 are tree CTAs, the rest tower CTAs; one CTA of 1,024 threads per SM and
 // n_tree + n_net <= number of SMs, so all of them are resident at once -- the form a kernel that waits must have.  A launch
 // has one block size and one register count (64 at 1,024 threads): a tower CTA reshapes its register file with setmaxnreg --
-// the 12 warps without a role drop to 24 registers and leave, the producer / issuer warpgroup drops to 40, the 16 epilogue warps
+// the 12 warps without a role drop to 24 registers and leave, the producer / issuer warpgroup drops to 56, the 16 epilogue warps
 // rise to the 96 the batch kernel's epilogue needs.  A launch also has one shared-memory size, so the tree CTAs carry the
 // tower's 200 KB and keep ~28 KB of L1 (cost: 420k instead of 428k positions/s).  The two-launch form (k_sp_tree + k_sp_net on two
 // streams, env C4_SP_LAUNCH=two) keeps the tree CTAs' L1 whole, but CUDA does not promise that two launches run side by
@@ -298,7 +298,7 @@ template <int F> __host__ __device__ constexpr int sp_net_smem(int R) { return s
 // (body of tower CTA `tower`.  Warp roles: EPI0 .. EPI0 + 15 epilogue, PRODUCER, ISSUER.  ONE_LAUNCH: the CTA has 1,024
 //  threads at 64 registers like the tree CTAs of the same launch; the 16 epilogue warps raise their register limit to 96 with
 //  setmaxnreg from what the 12 warps without a role and the producer / issuer warpgroup give back:
-//  16 x 32 x 96 + 4 x 32 x 40 + 12 x 32 x 24 = 63,488 <= 65,536.)
+//  16 x 32 x 96 + 4 x 32 x 56 + 12 x 32 x 24 = 65,536.)
 template <typename OP, int F, int EPI0, int PRODUCER, int ISSUER, bool ONE_LAUNCH>
 __device__ __forceinline__ void sp_net_body(const unsigned char *__restrict__ image, int R, SpGlobal *G, C4Counters *ctr,
                                             const SpParams &P, unsigned char *smem, const unsigned tower)
@@ -351,7 +351,7 @@ __device__ __forceinline__ void sp_net_body(const unsigned char *__restrict__ im
             return;
         }
         if (warp >= (PRODUCER & ~3) && warp < (PRODUCER & ~3) + 4) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");          // producer / issuer warpgroup (single threads at work)
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");          // producer / issuer warpgroup (single threads at work)
             if (warp != PRODUCER && warp != ISSUER) return;
         } else {
             asm volatile("setmaxnreg.inc.sync.aligned.u32 96;\n");          // epilogue warps
@@ -694,43 +694,50 @@ __global__ void k_sp_probe_wait(int *flag, int *result)
 }
 __global__ void k_sp_probe_set(int *flag) { st_vol(flag, 1); }
 
-// Per-device buffers, and the one-time co-residency probe.  The engine needs two kernels that wait for each other to run
-// at the same time.  Nothing in CUDA guarantees that for two launches; it holds here because both are launched by one
-// process into two streams of one context and together need no more SMs than the device has -- but a tool that serialises
-// launches (ncu kernel replay, compute-sanitizer, CUDA_LAUNCH_BLOCKING=1) breaks it.  So the first use runs a 1-thread
-// kernel that waits (at most 0.2 s) for a flag set by a second 1-thread kernel on another stream; if the flag never
-// arrives the engine reports itself unsupported and the caller uses the fused / lock-step engines.
+// Per-device buffers of the engine (control block, answer slots, rings; mapped abort word; side streams)
 static SpDevice *sp_device()
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     SpDevice &pd = g_sp_device[dev];
     std::lock_guard<std::mutex> lock(g_sp_init);
-    if (pd.coresident != 0) return &pd;
+    if (pd.G) return &pd;
     const int sms = sp_sms();
+    if (sms < 8) return nullptr;
+    SpGlobal *G = nullptr;
+    if (cudaHostAlloc((void **)&pd.h_abort, 64, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    if (cudaHostGetDevicePointer((void **)&pd.d_abort, pd.h_abort, 0) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&pd.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&pd.side2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&pd.ev_a, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&pd.ev_b, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaMalloc((void **)&G, sp_rings_off() + (size_t)sms * SP_GMAX * 16) != cudaSuccess) return nullptr;   // rings for any tower count / pool size
+    pd.G = G;
+    return &pd;
+}
+
+// The two-launch form needs two kernels that wait for each other to run at the same time.  Nothing in CUDA guarantees that
+// for two launches; it holds when both are launched by one process into two streams of one context and together need no more
+// SMs than the device has -- but a tool that serialises launches (ncu kernel replay, compute-sanitizer,
+// CUDA_LAUNCH_BLOCKING=1) breaks it.  So before its first use a 1-thread kernel waits (at most 0.2 s) for a flag set by a
+// second 1-thread kernel on another stream; if the flag never arrives the engine stays with ONE launch.
+static bool sp_coresident(SpDevice &pd)
+{
+    std::lock_guard<std::mutex> lock(g_sp_init);
+    if (pd.coresident != 0) return pd.coresident == 1;
     pd.coresident = -1;
-    if (sms < 8) return &pd;
-    if (cudaHostAlloc((void **)&pd.h_abort, 64, cudaHostAllocMapped) != cudaSuccess) return &pd;
-    if (cudaHostGetDevicePointer((void **)&pd.d_abort, pd.h_abort, 0) != cudaSuccess) return &pd;
-    if (cudaMalloc((void **)&pd.G, sp_rings_off() + (size_t)sms * SP_GMAX * 16) != cudaSuccess) return &pd;   // rings for any tower count / pool size
-    if (cudaStreamCreateWithFlags(&pd.side, cudaStreamNonBlocking) != cudaSuccess) return &pd;
-    if (cudaStreamCreateWithFlags(&pd.side2, cudaStreamNonBlocking) != cudaSuccess) return &pd;
-    if (cudaEventCreateWithFlags(&pd.ev_a, cudaEventDisableTiming) != cudaSuccess) return &pd;
-    if (cudaEventCreateWithFlags(&pd.ev_b, cudaEventDisableTiming) != cudaSuccess) return &pd;
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, k_sp_probe_wait) != cudaSuccess || cudaFuncGetAttributes(&fa, k_sp_probe_set) != cudaSuccess) return &pd;
-    int *w = reinterpret_cast<int *>(pd.G);                               // two scratch words of the (not yet used) control block
-    if (cudaMemsetAsync(w, 0, 8, pd.side) != cudaSuccess) return &pd;
-    if (cudaStreamSynchronize(pd.side) != cudaSuccess) return &pd;
+    if (cudaFuncGetAttributes(&fa, k_sp_probe_wait) != cudaSuccess || cudaFuncGetAttributes(&fa, k_sp_probe_set) != cudaSuccess) return false;
+    int *w = reinterpret_cast<int *>(pd.G);                               // two scratch words of the control block (no run is active)
+    if (cudaMemsetAsync(w, 0, 8, pd.side) != cudaSuccess || cudaStreamSynchronize(pd.side) != cudaSuccess) return false;
     k_sp_probe_wait<<<1, 1, 0, pd.side>>>(w, w + 1);
     k_sp_probe_set<<<1, 1, 0, pd.side2>>>(w);
     int result = 0;
-    if (cudaStreamSynchronize(pd.side) != cudaSuccess || cudaStreamSynchronize(pd.side2) != cudaSuccess) return &pd;
-    if (cudaMemcpy(&result, w + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return &pd;
+    if (cudaStreamSynchronize(pd.side) != cudaSuccess || cudaStreamSynchronize(pd.side2) != cudaSuccess) return false;
+    if (cudaMemcpy(&result, w + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
     pd.coresident = result == 1 ? 1 : -1;
-    if (pd.coresident < 0 && getenv("C4_FZ_DEBUG"))
-        fprintf(stderr, "[split] two kernels on two streams do not run side by side here (serialising tool?): engine disabled\n");
-    return &pd;
+    if (pd.coresident < 0) fprintf(stderr, "[split] two kernels on two streams do not run side by side here (serialising tool?): one launch\n");
+    return pd.coresident == 1;
 }
 
 static bool c4_split_supported(const c4_net *net, int max_games)
@@ -743,16 +750,16 @@ static bool c4_split_supported(const c4_net *net, int max_games)
     if ((max_games + n_tree - 1) / n_tree > SP_GC_MAX) return false;
     if ((net->F == 32 ? sp_net_smem<32>(net->R) : sp_net_smem<64>(net->R)) > 227 * 1024) return false;
     const SpDevice *pd = sp_device();
-    return pd && pd->G;                                                   // (two launches need pd->coresident == 1, one launch does not)
+    return pd != nullptr;
 }
 
 // ONE launch by default.  env C4_SP_LAUNCH=two: two launches on two streams, if the device runs them side by side (probe) --
 // the tree CTAs then keep the SM's whole L1 (428k instead of 420k positions/s on the benchmark generation), at the price of
 // relying on co-residency that CUDA does not promise.
-static bool sp_two_launches(const SpDevice &pd)
+static bool sp_two_launches(SpDevice &pd)
 {
     const char *want = getenv("C4_SP_LAUNCH");
-    return want && !strcmp(want, "two") && pd.coresident == 1;
+    return want && !strcmp(want, "two") && sp_coresident(pd);
 }
 
 // ... and is it the engine to use?  env C4_ENGINE = "split" / "fused" / "lockstep" forces one.  Auto: whenever it is supported --
@@ -793,9 +800,9 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     P.ring_cap = cap;
     P.n_tree = n_tree;
     const int smem = net->F == 32 ? sp_net_smem<32>(net->R) : sp_net_smem<64>(net->R);
+    const bool two = sp_two_launches(pd);                                 // (may run the probe, which uses the control block: before the reset)
     // ticket counter, flags, answer slots and the rings' stamps all start from zero
     C4_CUDA(cudaMemsetAsync(pd.G, 0, sp_rings_off() + (size_t)n_net * cap * 16, stream));
-    const bool two = sp_two_launches(pd);
     if (two) {
         auto kn = net->F == 32 ? (net->fp16 ? k_sp_net<OpFP16, 32> : k_sp_net<OpBF16, 32>) : (net->fp16 ? k_sp_net<OpFP16, 64> : k_sp_net<OpBF16, 64>);
         auto kt = selfplay ? k_sp_tree<true> : k_sp_tree<false>;

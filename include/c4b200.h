@@ -201,9 +201,10 @@ int c4_selfplay_reset(c4_ctx *ctx, void *stream);
  * the last call left it.  Runs until `stop_games` more games have finished (0 = no game limit) or `max_ms` device
  * milliseconds have passed (0 = no time limit); at least one of the two must be given.  HOST outputs (any may be NULL):
  * positions = root moves played, evals = network evaluations, memo_hits = leaves answered by the evaluation memo, games =
- * games finished, device_ms = CUDA-event time, engine = 2 when the fused persistent engine ran (c4_fused.cu: one launch,
- * tree warps and the tcgen05 tower on the same SM, no pass barrier; 32-filter networks), 1 for the lock-step pass engine
- * (env C4_ENGINE=lockstep forces it).  Records are discarded.  Synchronises the stream. */
+ * games finished, device_ms = CUDA-event time, engine = 3 when the split persistent engine ran (c4_split.cu, the default for
+ * 32- and 64-filter networks: one launch, tree CTAs and tcgen05 tower CTAs on separate SMs, no pass barrier), 2 for the fused
+ * persistent engine (c4_fused.cu: tree warps and a tower on every SM), 1 for the lock-step pass engine (env
+ * C4_ENGINE=split|fused|lockstep forces one).  Records are discarded.  Synchronises the stream. */
 int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t stop_games, double max_ms, int64_t *positions,
                        int64_t *evals, int64_t *memo_hits, int64_t *games, float *device_ms, int32_t *engine,
                        void *stream);

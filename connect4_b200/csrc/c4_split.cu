@@ -608,7 +608,6 @@ __device__ __forceinline__ void sp_net_body(const unsigned char *__restrict__ im
                     o = (lane < 7) ? (1.f / 7.f) : 0.5f;
                     if (lane == 0) ctr->net_nonfinite = 1;
                 }
-                C4_DEV_ASSERT(my_game >= 0 && my_game < P.n_slots && my_tag != 0u);
                 if (lane < 8) __stcg(&G->ans[my_game][lane], (unsigned long long)__float_as_uint(o) | ((unsigned long long)my_tag << 32));
             }
             if (P.prof && e == 0 && lane == 0) {

@@ -1,5 +1,5 @@
 """the workload compute-sanitizer is run on (memcheck / racecheck, one tool per gpurun call): a small NET self-play
-generation on both engines, a batch of stand-alone NET searches and a 1,536-position c4_net_forward.
+generation on all three engines, a batch of stand-alone NET searches and a 1,536-position c4_net_forward.
 usage: compute-sanitizer --tool memcheck python tools/sanitize_case.py [games] [sims]"""
 import os, sys
 import numpy as np
@@ -17,7 +17,7 @@ model = ModelWrapper(state_dict={k: z[k] for k in z.files})
 v, p = model.evaluate_bitboards(g["c0"][:1536], g["c1"][:1536])
 print("c4_net_forward 1536 positions: max |dv| %.2e" % np.abs(v.cpu().numpy() - g["value"][:1536]).max(), flush=True)
 out = {}
-for engine in ("fused", "lockstep"):
+for engine in ("split", "fused", "lockstep"):
     os.environ["C4_ENGINE"] = engine
     pool = SelfPlayPool(model, MCTSConfig(sims, 19652, 1.25, 0.3, 0.25, 6), concurrent_games=games, seed=4)
     rec = pool.generate_records(games + games // 2)
@@ -30,5 +30,5 @@ for engine in ("fused", "lockstep"):
     eng.run("net")
     print(engine, "searches: root visits", eng.readout()["root_visits"][:4], flush=True)
     eng.close()
-assert all(out["fused"][f].tobytes() == out["lockstep"][f].tobytes() for f in out["fused"].dtype.names)
+assert all(out[e][f].tobytes() == out["lockstep"][f].tobytes() for e in ("split", "fused") for f in out[e].dtype.names)
 print("engines agree", flush=True)

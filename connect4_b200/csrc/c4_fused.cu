@@ -132,7 +132,9 @@ template <class K> __host__ __device__ constexpr int fz_total(int R, int table_e
 struct FzPort {
     static constexpr int GC_MAX = FZ_GC_MAX;
     static constexpr bool DEDUP = false;                                  // measured slower in this engine (header comment)
+    typedef Game GameType;
     FzCtl *S;
+    __device__ __forceinline__ void stage(Game &, int) const {}
     __device__ __forceinline__ bool impatient(int) const { return true; }
     __device__ __forceinline__ int stopping() const { return ld_vol(&S->stop); }
     __device__ __forceinline__ float answer(int, int gl, int lane) const { return (lane < 8) ? S->ans[gl][lane] : 0.f; }

@@ -7,6 +7,7 @@
 //   void  publish(g, gl, st, request, c0, c1)      lane 0: make the game's new status visible, then (request) queue the leaf;
 //                                                  st == ST_WAITMEMO: the game waits for the memo entry of (c0, c1)
 //   PORT::DEDUP, bool impatient(gl)                de-duplication of evaluations in flight; a parked game asks for itself
+//   PORT::GameType, void stage(G, gl)              Game, or GameS with the game's shared-memory node area filled in
 #pragma once
 #include "c4_tree.cuh"
 #include "c4_tc.cuh"
@@ -53,9 +54,10 @@ __device__ __forceinline__ bool fz_wait(uint32_t bar, uint32_t parity, const int
 template <bool SELFPLAY, class PORT>
 __device__ __forceinline__ void fz_run_game(const C4Dev &d, const PORT &port, int g, int gl, int st, int lane)
 {
-    Game G;
+    typename PORT::GameType G;
     G.g = g; G.lane = lane;
     G.gp = d.pool + (size_t)g * d.blocks_per_game * C4_SLOTS;
+    port.stage(G, gl);                                                   // (split engine: the top of the tree lives in shared memory)
     G.n_blocks = d.n_blocks[g];
     G.sims_done = d.sims_done[g];
     G.c0 = d.root_c0[g]; G.c1 = d.root_c1[g];
@@ -110,7 +112,7 @@ __device__ __forceinline__ void fz_run_game(const C4Dev &d, const PORT &port, in
             // Tree(board) + evaluate root (oinkoink/mcts.py:98-105): fresh pool, root = node 0 of block 0
             G.n_blocks = 1;
             G.sims_done = 0;
-            if (lane == 0) { st_a(G.gp, 0.0, 0u, C4_META_EXISTS); st_b(G.gp, 0.0, 0.0); }
+            if (lane == 0) { G.sta(0u, 0.0, 0u, C4_META_EXISTS); G.stb(0u, 0.0, 0.0); }
             __syncwarp();
             float ov;
             u64 seen = 0;

@@ -80,6 +80,7 @@ struct SpParams {
     int n_tree;                         // tree CTAs (the first n_tree CTAs of a single launch)
     int n_net;                          // tower CTAs = rings
     unsigned ring_cap;                  // entries per ring (power of two >= game slots)
+    int stage_nodes;                    // node records per game that a tree CTA keeps in shared memory (multiple of 8; 0 = none)
 };
 
 // tree CTA control block (shared memory)
@@ -114,6 +115,15 @@ struct SpPort {
     static constexpr bool DEDUP = true;
     SpCtl *S;
     SpGlobal *G;
+#ifdef C4_SP_STAGE_TOP
+    typedef GameS GameType;
+    uint32_t stage_base32;              // .shared address of [game of the CTA][stage_nodes] node records (or stage_nodes == 0)
+    uint32_t stage_nodes;
+    __device__ __forceinline__ void stage(GameS &g, int gl) const { g.sp32 = stage_base32 + (uint32_t)gl * stage_nodes * 32u; g.sp_nodes = stage_nodes; }
+#else
+    typedef Game GameType;
+    __device__ __forceinline__ void stage(Game &, int) const {}
+#endif
     const uint32_t *memo;
     uint32_t memo_mask, memo_epoch;
     unsigned n_net, ring_cap;
@@ -172,6 +182,20 @@ __device__ __forceinline__ void sp_tree_body(const C4Dev &dg, SpGlobal *G, const
     for (int i = threadIdx.x; i < (int)(sizeof(SpCtl) / 4); i += blockDim.x) reinterpret_cast<uint32_t *>(S)[i] = 0u;
     __syncthreads();
     for (int i = threadIdx.x; i < SP_GC_MAX; i += blockDim.x) S->status[i] = (i < Gc) ? fz_entry_status(dg, g0 + i) : (int)ST_IDLE;
+#ifdef C4_SP_STAGE_TOP
+    // shared-memory staging of the top of each tree: the first stage_nodes node records of every game of this CTA (the blocks
+    // created first: root, its children, the first expansions) are copied in here, live in shared memory while the launch
+    // runs (GameS in c4_tree.cuh) and are copied back at the end -- a game never leaves its CTA
+    C4Node *stage_base = reinterpret_cast<C4Node *>(reinterpret_cast<unsigned char *>(S) + ((sizeof(SpCtl) + 127) & ~(size_t)127));
+    {
+        const int per_game = P.stage_nodes * 2;                              // 16-byte units (a node record is 32 bytes)
+        for (int i = threadIdx.x; i < Gc * per_game; i += blockDim.x) {
+            const int gl = i / per_game, k = i - gl * per_game;
+            reinterpret_cast<uint4 *>(stage_base)[i] =
+                __ldcg(reinterpret_cast<const uint4 *>(dg.pool + (size_t)(g0 + gl) * dg.blocks_per_game * C4_SLOTS) + k);
+        }
+    }
+#endif
     __syncthreads();
     const unsigned long long t_begin = fz_globaltimer();
 
@@ -216,7 +240,13 @@ __device__ __forceinline__ void sp_tree_body(const C4Dev &dg, SpGlobal *G, const
         if (lane == 0 && atomicAdd(&G->trees_exited, 1) == P.n_tree - 1) { __threadfence(); st_vol(&G->quit, 1); }
     } else {
         // ================= tree warps (the picker loop of the fused engine)
+#ifdef C4_SP_STAGE_TOP
+        uint32_t stage_base32;                                                // (volatile: computed once, not re-derived from the window base at every access)
+        asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(stage_base32) : "l"(stage_base));
+        const SpPort port{S, G, stage_base32, (uint32_t)P.stage_nodes, dg.memo, dg.memo_mask, dg.memo_epoch, (unsigned)P.n_net, P.ring_cap};
+#else
         const SpPort port{S, G, dg.memo, dg.memo_mask, dg.memo_epoch, (unsigned)P.n_net, P.ring_cap};
+#endif
         int rot = (warp * 9) % Gc;
         bool idle = false;
         long long idle_t0 = 0;
@@ -282,6 +312,18 @@ __device__ __forceinline__ void sp_tree_body(const C4Dev &dg, SpGlobal *G, const
             atomicAdd(&S->tree_exited, 1);
         }
     }
+#ifdef C4_SP_STAGE_TOP
+    // every warp of the CTA is done with the games: the staged tree tops go back to the pool in HBM (read-outs, tree export,
+    // the next launch and the other engines read it there)
+    __syncthreads();
+    {
+        const int per_game = P.stage_nodes * 2;
+        for (int i = threadIdx.x; i < Gc * per_game; i += blockDim.x) {
+            const int gl = i / per_game, k = i - gl * per_game;
+            reinterpret_cast<uint4 *>(dg.pool + (size_t)(g0 + gl) * dg.blocks_per_game * C4_SLOTS)[k] = reinterpret_cast<const uint4 *>(stage_base)[i];
+        }
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ tower CTAs
@@ -799,7 +841,21 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     P.ring_cap = cap;
     P.n_tree = n_tree;
     const int smem = net->F == 32 ? sp_net_smem<32>(net->R) : sp_net_smem<64>(net->R);
+    P.stage_nodes = 0;
+#ifdef C4_SP_STAGE_TOP
+    // ONE launch: every CTA has the tower's shared memory; a tree CTA uses it for the top of its games' trees (env
+    // C4_SP_STAGE=0 turns that off; C4_SP_STAGE=n caps the node records per game).  Compiled in with -DC4_SP_STAGE_TOP only:
+    // measured slower than no staging (profiles/README.md, "shared-memory staging of the tree top")
+    {
+        const int gc_max = (max_games + n_tree - 1) / n_tree;
+        const int avail = smem - (int)((sizeof(SpCtl) + 127) & ~(size_t)127);
+        int nodes = std::min(avail / (gc_max * 32), std::min(512, d.blocks_per_game * C4_SLOTS)) & ~7;
+        if (getenv("C4_SP_STAGE")) nodes = std::min(nodes, atoi(getenv("C4_SP_STAGE")) & ~7);
+        P.stage_nodes = std::max(0, nodes);
+    }
+#endif
     const bool two = sp_two_launches(pd);                                 // (may run the probe, which uses the control block: before the reset)
+    if (two) P.stage_nodes = 0;                                           // (the tree kernel of the two-launch form has no dynamic shared memory)
     // ticket counter, flags, answer slots and the rings' stamps all start from zero
     C4_CUDA(cudaMemsetAsync(pd.G, 0, sp_rings_off() + (size_t)n_net * cap * 16, stream));
     if (two) {

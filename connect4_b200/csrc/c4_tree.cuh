@@ -280,14 +280,77 @@ struct Game {
     int sims_done;
     u64 c0, c1;          // root board
     int age;             // root age
+    // node accessors (node i of this game): every read / write of the tree goes through these
+    __device__ __forceinline__ C4NodeA lda(uint32_t i) const { return ld_a(gp + i); }
+    __device__ __forceinline__ C4NodeB ldb(uint32_t i) const { return ld_b(gp + i); }
+    __device__ __forceinline__ void sta(uint32_t i, double vsum, uint32_t visits, uint32_t meta) const { st_a(gp + i, vsum, visits, meta); }
+    __device__ __forceinline__ void stb(uint32_t i, double prior, double vsel) const { st_b(gp + i, prior, vsel); }
+    __device__ __forceinline__ void st_vsel(uint32_t i, double vsel) const { gp[i].b.vsel = vsel; }
+    __device__ __forceinline__ bool in_hbm(uint32_t) const { return true; }
+};
+// A game whose FIRST `sp_nodes` nodes (the blocks created first = the top of the tree, the records every simulation reads
+// and writes) live in shared memory for the length of a persistent launch ("shared-memory staging of the hot top of each
+// tree"; c4_split.cu copies them in at launch entry and back at exit).  Same functions, other addresses: the select /
+// expand / backup code below is templated on the game type, and with `Game` it compiles to what it was.  The shared copy
+// is addressed with 32-bit .shared addresses and explicit ld.shared / st.shared: a generic pointer costs a 64-bit select
+// plus the window-base arithmetic (S2UR) at every access, which measured slower than no staging at all.
+struct GameS : Game {
+    uint32_t sp32;       // .shared address of the copy of nodes 0 .. sp_nodes - 1
+    uint32_t sp_nodes;
+    // 16 bytes of node i (half 0 = A, half 1 = B).  Both addresses are computed up front and the two loads are predicated:
+    // as a branch, the compiler sank the 64-bit address arithmetic (with its constant-bank loads) under the predicate, onto the
+    // dependent chain of the descent
+    __device__ __forceinline__ uint4 ld16(uint32_t i, uint32_t half) const
+    {
+        const char *pg = reinterpret_cast<const char *>(gp + i) + half * 16u;
+        const uint32_t ps = sp32 + i * 32u + half * 16u;
+        uint4 v;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %6, %7;\n\t"
+                     "@p ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t"
+                     "@!p ld.global.v4.u32 {%0,%1,%2,%3}, [%5];\n\t}"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ps), "l"(pg), "r"(i), "r"(sp_nodes) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ C4NodeA lda(uint32_t i) const
+    {
+        const uint4 v = ld16(i, 0u);
+        C4NodeA a;
+        a.vsum = __hiloint2double((int)v.y, (int)v.x); a.visits = v.z; a.meta = v.w;
+        return a;
+    }
+    __device__ __forceinline__ C4NodeB ldb(uint32_t i) const
+    {
+        const uint4 v = ld16(i, 1u);
+        C4NodeB b;
+        b.prior = __hiloint2double((int)v.y, (int)v.x); b.vsel = __hiloint2double((int)v.w, (int)v.z);
+        return b;
+    }
+    __device__ __forceinline__ void sta(uint32_t i, double vsum, uint32_t visits, uint32_t meta) const
+    {
+        if (i >= sp_nodes) { st_a(gp + i, vsum, visits, meta); return; }
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(sp32 + i * 32u), "r"((uint32_t)__double2loint(vsum)),
+                     "r"((uint32_t)__double2hiint(vsum)), "r"(visits), "r"(meta) : "memory");
+    }
+    __device__ __forceinline__ void stb(uint32_t i, double prior, double vsel) const
+    {
+        if (i >= sp_nodes) { st_b(gp + i, prior, vsel); return; }
+        asm volatile("st.shared.v4.u32 [%0+16], {%1,%2,%3,%4};" :: "r"(sp32 + i * 32u), "r"((uint32_t)__double2loint(prior)),
+                     "r"((uint32_t)__double2hiint(prior)), "r"((uint32_t)__double2loint(vsel)), "r"((uint32_t)__double2hiint(vsel)) : "memory");
+    }
+    __device__ __forceinline__ void st_vsel(uint32_t i, double vsel) const
+    {
+        if (i >= sp_nodes) { gp[i].b.vsel = vsel; return; }
+        asm volatile("st.shared.f64 [%0+24], %1;" :: "r"(sp32 + i * 32u), "d"(vsel) : "memory");
+    }
+    __device__ __forceinline__ bool in_hbm(uint32_t block) const { return block * C4_SLOTS >= sp_nodes; }
 };
 
 // Evaluate node `node` (board c0,c1 at `age`): store the value, normalise the prior over the legal moves in its own
 // dtype (oinkoink/mcts.py:129-135,197-202), optionally mix root noise (mcts.py:171-181) and create the child block
 // (oinkoink/tree.py:119-132 -- one child per legal move, each with its terminal result).
 // p64 / p32: lane c (<7) holds the raw prior of column c.
-template <bool F32>
-__device__ __forceinline__ void apply_eval(const C4Dev &d, Game &G, uint32_t node, u64 c0, u64 c1, int age, double value,
+template <bool F32, class GAME>
+__device__ __forceinline__ void apply_eval(const C4Dev &d, GAME &G, uint32_t node, u64 c0, u64 c1, int age, double value,
                                            double p64, float p32, bool is_root, int ply)
 {
     const int lane = G.lane;
@@ -331,42 +394,42 @@ __device__ __forceinline__ void apply_eval(const C4Dev &d, Game &G, uint32_t nod
     const uint32_t blk = (uint32_t)G.n_blocks;
     C4_DEV_ASSERT((int)blk < d.blocks_per_game && node < blk * C4_SLOTS);
     G.n_blocks++;
-    C4Node *slot = G.gp + (size_t)blk * C4_SLOTS + lane;
+    const uint32_t slot = blk * C4_SLOTS + (uint32_t)lane;
     if (lane < 7) {
         int res = C4_RES_NONE;
         if (mine) { u64 a = c0, b = c1; res = c4_drop(a, b, age, lane); }
         const uint32_t m = c4_make_meta(mine, res);
-        st_a(slot, 0.0, 0u, m);
+        G.sta(slot, 0.0, 0u, m);
         // a terminal child is worth its result to the mover here; an unvisited one 0.0 ("assume lost", tree.py:42-44)
-        st_b(slot, mine ? p : 0.0, (m & C4_META_TERMINAL) ? c4_side_value(c4_meta_value(m), age) : 0.0);
+        G.stb(slot, mine ? p : 0.0, (m & C4_META_TERMINAL) ? c4_side_value(c4_meta_value(m), age) : 0.0);
     } else if (lane == 7) {
-        st_a(slot, value, 0u, 0u);                                    // block header: position value, #children, parent id
-        st_b(slot, 0.0, pack_header((uint32_t)__popc(legal), node));
+        G.sta(slot, value, 0u, 0u);                                    // block header: position value, #children, parent id
+        G.stb(slot, 0.0, pack_header((uint32_t)__popc(legal), node));
     }
     if (lane == 0) {
-        C4Node *n = G.gp + node;
         const double vs = __dadd_rn(0.0, value);                      // SearchEvaluation(): 0.0 + value, count 1
-        st_a(n, vs, 1u, C4_META_EXISTS | (blk << C4_META_CB_SHIFT));
-        if (node != 0u) n->b.vsel = c4_side_value(vs, age - 1);       // mean of one visit, seen by the parent's mover
+        G.sta(node, vs, 1u, C4_META_EXISTS | (blk << C4_META_CB_SHIFT));
+        if (node != 0u) G.st_vsel(node, c4_side_value(vs, age - 1));       // mean of one visit, seen by the parent's mover
     }
     __syncwarp();
 }
 
 // add `value` to one path node and refresh the side-relative mean select reads (depth = its distance from the root)
-__device__ __forceinline__ void backup_node(const Game &G, uint32_t id, int depth, double value)
+template <class GAME>
+__device__ __forceinline__ void backup_node(const GAME &G, uint32_t id, int depth, double value)
 {
-    C4Node *n = G.gp + id;
-    C4NodeA a = ld_a(n);
+    C4NodeA a = G.lda(id);
     const double vs = __dadd_rn(a.vsum, value);
     const uint32_t vis = a.visits + 1u;
-    st_a(n, vs, vis, a.meta);
+    G.sta(id, vs, vis, a.meta);
     // float(search_value) = value_sum / visit_count (mcts.py:56-57), flipped for the mover at the PARENT (age + depth - 1);
     // a terminal node keeps its result (NodeData.absolute_value, tree.py:27-38); the root is never selected
     if (depth > 0 && !(a.meta & C4_META_TERMINAL))
-        n->b.vsel = c4_side_value(__ddiv_rn(vs, (double)vis), G.age + depth - 1);
+        G.st_vsel(id, c4_side_value(__ddiv_rn(vs, (double)vis), G.age + depth - 1));
 }
 // add `value` to the first `count` path nodes (lane i owns path entry i / i+32): oinkoink/mcts.py:164-168
-__device__ __forceinline__ void backup(Game &G, uint32_t path_lo, uint32_t path_hi, int count, double value)
+template <class GAME>
+__device__ __forceinline__ void backup(GAME &G, uint32_t path_lo, uint32_t path_hi, int count, double value)
 {
     if (G.lane < count) backup_node(G, path_lo, G.lane, value);
     if (G.lane + 32 < count) backup_node(G, path_hi, G.lane + 32, value);
@@ -394,27 +457,28 @@ __device__ __forceinline__ u64 score_key(double x)
 // expand-then-select step, merged by eager expansion) with select_child / ucb_score (mcts.py:138-161).
 // The per-level dependent chain is what bounds the tree pass (profiles/README.md), so it is kept short:
 //   load {A,B} of the own child -> sqrt(N)/(n+1) -> two multiplies, one add -> 64-bit key -> two REDUX.MAX + one vote.
-__device__ __forceinline__ Leaf descend(const C4Dev &d, const Game &G)
+template <class GAME>
+__device__ __forceinline__ Leaf descend(const C4Dev &d, const GAME &G)
 {
     const int lane = G.lane;
     Leaf L;
     L.c0 = G.c0; L.c1 = G.c1; L.age = G.age; L.depth = 0;
     L.path_lo = 0u; L.path_hi = 0u; L.node = 0u;
-    C4NodeA ra = ld_a(G.gp);
+    C4NodeA ra = G.lda(0u);
     uint32_t visits = ra.visits, meta = ra.meta;
     while (!(meta & C4_META_TERMINAL) && visits > 0u) {
         const uint32_t blk = c4_meta_child_block(meta);
         C4_DEV_ASSERT(blk > 0u && (int)blk < G.n_blocks && L.depth < PATH_CAP - 1);
-        const C4Node *cn = G.gp + (size_t)blk * C4_SLOTS + (lane & 7);
-        C4NodeA a = ld_a(cn);
-        C4NodeB b = ld_b(cn);
+        const uint32_t cn = blk * C4_SLOTS + (uint32_t)(lane & 7);
+        C4NodeA a = G.lda(cn);
+        C4NodeB b = G.ldb(cn);
         // exploration factor of the parent: log((N+base+1)/base)+init and sqrt(N) from host-built tables (glibc log / sqrt)
         const double pbc = d.pbc[visits];
         const double sq = d.sqt[visits];
         const bool exists = (lane < 7) && (a.meta & C4_META_EXISTS);
         // speculative prefetch: every lane pulls ITS child's block (two 128-byte lines) towards L2 while the warp decides;
         // HBM bandwidth is nowhere near a limit for this kernel (profiles/README.md)
-        if (exists && c4_meta_child_block(a.meta) != 0u) {
+        if (exists && c4_meta_child_block(a.meta) != 0u && G.in_hbm(c4_meta_child_block(a.meta))) {
             const char *pf = reinterpret_cast<const char *>(G.gp + (size_t)c4_meta_child_block(a.meta) * C4_SLOTS);
             asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
             asm volatile("prefetch.global.L2 [%0];" :: "l"(pf + 128));
@@ -553,12 +617,13 @@ __device__ __forceinline__ void emit_request(const C4Dev &d, Game &G, int pool, 
 
 // End of a search inside a self-play game: pick the move, log the position, play it, finish / re-seed the game.
 // oinkoink/mcts.py:78-88 (MCTS.make_move) + neural/training_game.py:8-19 (training_game).  Returns the new status.
-__device__ __forceinline__ int finalize_move(const C4Dev &d, Game &G)
+template <class GAME>
+__device__ __forceinline__ int finalize_move(const C4Dev &d, GAME &G)
 {
     const int lane = G.lane;
     const int side = G.age & 1;
-    const uint32_t blk = c4_meta_child_block(ld_a(G.gp).meta);
-    C4NodeA a = ld_a(G.gp + (size_t)blk * C4_SLOTS + (lane & 7));
+    const uint32_t blk = c4_meta_child_block(G.lda(0u).meta);
+    C4NodeA a = G.lda(blk * C4_SLOTS + (uint32_t)(lane & 7));
     const bool exists = lane < 7 && (a.meta & C4_META_EXISTS);
     double v_side, v_abs;
     child_values(a, exists, side, v_side, v_abs);

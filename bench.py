@@ -27,7 +27,8 @@ A "step" = one such generation: fresh pool, empty memo, until `--games` games ha
           bf16 peak; `roofline_other`).  Fused engine: ONE kernel (k_fused) holds both roles; its tensor-side
           figure is `roofline`, its HBM-side figure `roofline_other`.  Lock-step engine: the tree pass / the network
           kernel from launch durations sampled with CUDA events.
-          `traffic` is null: no DRAM counter is read inside this run (ncu captures are under profiles/).
+          `traffic` = DRAM bytes per launch from the committed ncu capture of the same command and launch shape
+          (profiles/r02_split_traffic.csv; split engine, default workload), else null: no DRAM counter is read inside a run.
   cpu_baseline = the oracle port (oracle/selfplay_port.py) on the box's host cores, bounded sample (rank 0, N=1 only).
 --impl reference: the CPU port alone, all host cores, same metric / config.
 """
@@ -158,6 +159,21 @@ def digest_records(rec):
     for f in rec.dtype.names:
         h.update(np.ascontiguousarray(rec[f]).tobytes())
     return h.hexdigest()[:16]
+
+
+def ncu_traffic(path):
+    """mean over the launches in an ncu --csv metrics file of dram__bytes_read.sum + dram__bytes_write.sum (bytes), or None"""
+    import csv
+    try:
+        per = {}
+        with open(path) as f:
+            rows = [r for r in csv.reader(f) if len(r) > 14 and r[0].isdigit()]
+        for r in rows:
+            if r[12] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                per[r[0]] = per.get(r[0], 0.0) + float(r[14].replace(",", ""))
+        return sum(per.values()) / len(per) if per else None
+    except OSError:
+        return None
 
 
 def main():
@@ -357,6 +373,15 @@ def main():
                       "algorithmic_bytes_per_launch": tree_bytes / n_launch, "sims_per_launch": positions * SIMS / n_launch,
                       "ms_per_launch": step_ms, "share_of_step": 1.0,
                       "note": "1.28 KB per simulation (SURVEY.md 8d) + 64 B per memo probe; dependent-load latency bound" + where_h}
+            if engine == "split" and args.games == 4096 and "C4_SP_NET_CTAS" not in os.environ:
+                # DRAM bytes of this very launch shape from the ncu capture of the same command (profiles/r02_split_traffic.csv:
+                # `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:k_sp_one python bench.py --steps 1 --warmup 1
+                # --no-e2e --no-cpu --no-extras`); whole kernel = both roles; no counter is read inside this run
+                t = ncu_traffic(os.path.join(ROOT, "profiles", "r02_split_traffic.csv"))
+                if t:
+                    roof_h["traffic"] = t
+                    roof_h["traffic_source"] = ("profiles/r02_split_traffic.csv: dram__bytes_read.sum + dram__bytes_write.sum per k_sp_one "
+                                                "launch (whole kernel, both roles), ncu capture of the same workload, not this run")
             if engine == "split":
                 roof_t, roof_h = roof_h, roof_t                       # `roofline` = the tree kernel: it bounds the step (tower CTAs have slack)
         else:

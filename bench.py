@@ -30,6 +30,8 @@ A "step" = one such generation: fresh pool, empty memo, until `--games` games ha
           `traffic` = DRAM bytes per launch from the committed ncu capture of the same command and launch shape
           (profiles/r02_split_traffic.csv; split engine, default workload), else null: no DRAM counter is read inside a run.
   cpu_baseline = the oracle port (oracle/selfplay_port.py) on the box's host cores, bounded sample (rank 0, N=1 only).
+  cpu_baseline_reference = the unmodified reference package (baseline/_ref, copied by build()) on the same cores: its
+          multiprocess game_pool + InferenceServer path, a bounded sample of whole games -- context for how conservative the port is.
 --impl reference: the CPU port alone, all host cores, same metric / config.
 """
 import argparse
@@ -118,6 +120,26 @@ def cpu_port(seconds, warm=2.0, procs=None):
     return r, pp.procs
 
 
+def reference_python(timeout_s=240):
+    """second stated CPU baseline: the UNMODIFIED reference's multiprocess self-play (TrainingLoop._generate_games,
+    oinkoink/neural/training.py:99-133) from baseline/_ref on the host cores, CPU inference, a bounded sample of whole games"""
+    procs = max(1, (os.cpu_count() or 2) - 1)                              # + the InferenceServer process = all cores
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_reference.py"), "--procs", str(procs), "--threads", "2",
+           "--games-per-proc", "2", "--sims", str(SIMS)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    try:
+        out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=timeout_s).stdout
+        r = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    except Exception as e:                                                 # context only: never fails the bench line
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:120])}
+    if "unavailable" in r:
+        return r
+    return {"value": r["positions_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+            "sample": "unmodified reference package (baseline/_ref), its own checkpoint example_net.pth on CPU: %d game_pool "
+                      "processes x %d game threads + 1 InferenceServer process, %d whole games (%d positions) at %d sims/move "
+                      "in %.1f s" % (r["procs"], r["threads"], r["games"], r["positions"], SIMS, r["seconds"])}
+
+
 def run_reference(args, rank):
     """the reference arm: the CPU port of the reference path on all host cores (the reference itself is pure Python
     and is not present on the GPU box)."""
@@ -190,6 +212,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref-python", action="store_true", help="skip the unmodified-reference CPU sample (about 40 s)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip generation_1200 / steady_state / engine A-B")
     args = ap.parse_args()
@@ -442,6 +465,8 @@ def main():
                           "Evaluator.position_table); the unmodified Python reference measured 13 positions/s on 8 cores "
                           "(BASELINE.md)" % (cores, args.cpu_seconds),
                 "evals_per_sec": r["evals_per_sec"]}
+            if not args.no_ref_python:
+                line["cpu_baseline_reference"] = reference_python()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -14,8 +14,8 @@ A "step" = one such generation: fresh pool, empty memo, until `--games` games ha
   value = positions (root moves played) of all ranks / device time (CUDA events, max over ranks), inputs resident.
   e2e   = the same metric through the public API with HOST buffers: a whole generation of `--e2e-games` games per GPU
           (4 pool-fulls, drain of the last games included) from pinned host start positions to host records, memo
-          cold; with N > 1 through dist.generate_sharded, i.e. the NCCL all-gather of every rank's records and the
-          device-side sort are inside the timed region.
+          cold; with N > 1 through dist.generate_sharded(dst=0), i.e. the NCCL all-gather of every rank's records, the
+          device-side sort and the copy of the whole generation to rank 0's host are inside the timed region.
   generation_1200 = BASELINE.json configs[3]: the reference's example_config generation (1200 games, 64f/6r/6fc
           network) sharded over the N GPUs incl. the all-gather; seconds and the digest of the gathered records
           (identical for every N).
@@ -290,30 +290,40 @@ def main():
         start = (torch.zeros(args.e2e_games, dtype=torch.int64).pin_memory(),               # host-resident (pinned) inputs:
                  torch.zeros(args.e2e_games, dtype=torch.int64).pin_memory())               # every game from the empty board
         pool2 = SelfPlayPool(model, cfg, concurrent_games=args.games, seed=5000)
-        pool2.generate_records(min(64, args.e2e_games), start=(start[0][:64], start[1][:64]))   # warm the path
-        pool2.engine.clear_memo()
-        barrier()
-        t0 = time.perf_counter()
         if world == 1:
-            rec = pool2.generate_records(args.e2e_games, start=start)
+            pool2.generate_records(min(64, args.e2e_games), start=(start[0][:64], start[1][:64]))   # warm the path
         else:
-            # every rank plays its share (global game ids, so the generation does not depend on N), then the NCCL
-            # all-gather of the records and the device-side sort: every rank ends with the whole generation on the host
-            rec = generate_sharded(pool2, n_e2e)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        (_,), (dt_max,) = reduce_sum_max([0.0], [dt])
-        n_rec = len(rec)                                                     # N > 1: already the whole job's records
+            generate_sharded(pool2, 64 * world, dst=0)                       # (incl. the communicator and the sort kernels)
+        first = None
+        for rep in range(2):                                                 # the first run warms every kernel at full size (sort, gather, copy)
+            pool2.engine.clear_memo()
+            barrier()
+            t0 = time.perf_counter()
+            if world == 1:
+                rec = pool2.generate_records(args.e2e_games, start=start)
+            else:
+                # every rank plays its share (global game ids, so the generation does not depend on N), then the NCCL
+                # all-gather of the records and the device-side sort: every GPU ends with the whole generation in HBM and rank 0
+                # (the reference collects the games in one process, neural/training.py:112-133) with the whole generation on its host
+                rec = generate_sharded(pool2, n_e2e, dst=0)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            (n_rec,), (dt_max,) = reduce_sum_max([len(rec) if rec is not None else 0], [dt])
+            if first is None:
+                first = dt_max
+                del rec
+        n_rec = int(n_rec)                                                   # N > 1: rank 0 holds the whole job's records
         e2e = {"value": n_rec / dt_max, "unit": UNIT,
                "h2d_bytes_per_step": int(2 * 8 * args.e2e_games) if world == 1 else 0,
                "d2h_bytes_per_step": int(n_rec * 64),
                "what": ("SelfPlayPool.generate_records(%d games on %d slots, pinned host start positions) -> host records; "
-                        "cold memo; wall clock of the whole generation incl. the drain of the last games" % (
+                        "cold memo; wall clock of the whole generation incl. the drain of the last games; second of two such generations" % (
                             args.e2e_games, args.games)) if world == 1 else
                        ("dist.generate_sharded(%d games = %d per GPU on %d slots): generation + NCCL all-gather of all "
-                        "records + device-side sort + copy to the host on every rank; cold memo; wall clock, max over "
-                        "ranks" % (n_e2e, args.e2e_games, args.games)),
-               "records": n_rec, "seconds": dt_max, "records_sha256_16": digest_records(rec) if world > 1 else None}
+                        "records to every GPU + device-side sort + copy of the whole generation to rank 0's host; cold memo; wall "
+                        "clock, max over ranks; second of two such generations" % (n_e2e, args.e2e_games, args.games)),
+               "records": n_rec, "seconds": dt_max, "seconds_first_run": first,
+               "records_sha256_16": digest_records(rec) if world > 1 and rec is not None else None}
         pool2.engine.close()
         del rec
 
@@ -329,16 +339,18 @@ def main():
             pool3.engine.clear_memo()
             barrier()
             t0 = time.perf_counter()
-            rec = generate_sharded(pool3, args.gen_games)
+            rec = generate_sharded(pool3, args.gen_games, dst=0)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             (_,), (dt_max,) = reduce_sum_max([0.0], [dt])
             best = dt_max
-        extras["generation_1200"] = {
-            "games": args.gen_games, "n_gpus": world, "net": "example_config 64f/6r/6fc (random init, torch.manual_seed(0))",
-            "seconds": best, "positions": int(len(rec)), "positions_per_sec": len(rec) / best,
-            "records_sha256_16": digest_records(rec), "scaling": "strong",
-            "what": "dist.generate_sharded: games g -> rank g % N, NCCL all-gather of the records, device-side sort, host copy"}
+        if rank == 0:
+            extras["generation_1200"] = {
+                "games": args.gen_games, "n_gpus": world, "net": "example_config 64f/6r/6fc (random init, torch.manual_seed(0))",
+                "seconds": best, "positions": int(len(rec)), "positions_per_sec": len(rec) / best,
+                "records_sha256_16": digest_records(rec), "scaling": "strong",
+                "what": "dist.generate_sharded(dst=0): games g -> rank g % N, NCCL all-gather of the records, device-side sort, "
+                        "copy of the generation to rank 0's host"}
         pool3.engine.close()
         # warm regime, context only: continue one pool for a few seconds so the memo holds millions of positions
         step()

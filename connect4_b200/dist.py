@@ -14,7 +14,8 @@ def shard_games(n_games, rank, world):
 
 def all_gather_records(records, group=None):
     """records: uint8 tensor [n_local, 64] (CUDA for the NCCL backend, CPU for gloo). Returns every rank's records
-    concatenated in rank order: one all-gather of the counts, one all-gather of the padded payloads."""
+    concatenated in rank order: one all-gather of the counts, one all-gather of the payloads padded to the largest share
+    into ONE buffer, and one index_select that drops the padding."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -22,15 +23,18 @@ def all_gather_records(records, group=None):
         return records
     dev = records.device
     n = torch.tensor([records.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, n, group=group)
+    counts = counts.tolist()
     m = max(max(counts), 1)
     padded = torch.zeros((m, 64), dtype=torch.uint8, device=dev)
     padded[:records.shape[0]] = records
-    out = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(out, padded, group=group)
-    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+    out = torch.empty((world * m, 64), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    if all(c == m for c in counts):
+        return out
+    keep = torch.cat([torch.arange(r * m, r * m + c, device=dev) for r, c in enumerate(counts)])
+    return out.index_select(0, keep)
 
 
 def sort_records_device(rec):
@@ -45,15 +49,22 @@ def sort_records_device(rec):
     return rec.index_select(0, order)
 
 
-def generate_sharded(pool, n_games, group=None):
-    """Play this rank's share of `n_games` on `pool` (SelfPlayPool) and all-gather the records of all ranks.
-    Returns a numpy record array sorted by (game_id, ply) -- identical on every rank."""
+def generate_sharded(pool, n_games, group=None, dst=None):
+    """Play this rank's share of `n_games` on `pool` (SelfPlayPool) and all-gather the records of all ranks (every GPU ends
+    with the whole generation in HBM: `pool.engine.last_generation_device`, sorted by (game_id, ply)).
+    Returns them as a numpy record array -- identical on every rank; with `dst` = a rank, only that rank copies the
+    generation to its host (the reference collects the games in ONE process, neural/training.py:112-133) and the other
+    ranks return None."""
     import torch.distributed as dist
-    from .engine import RECORD_DTYPE
+    from .engine import records_to_host
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
     n_local, base, stride = shard_games(n_games, rank, world)
     pool.generate_records(n_local, game_id_base=base, game_id_stride=stride, to_host=False)
     rec = pool.engine.last_records_device
     if world > 1:
         rec = all_gather_records(rec, group)
-    return sort_records_device(rec).cpu().numpy().view(RECORD_DTYPE).reshape(-1)
+    rec = sort_records_device(rec)
+    pool.engine.last_generation_device = rec
+    if dst is not None and rank != dst:
+        return None
+    return records_to_host(rec)

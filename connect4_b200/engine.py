@@ -215,7 +215,7 @@ class Engine():
         self.last_records_device = rec[:n.value]
         if not to_host:
             return n.value
-        return rec[:n.value].cpu().numpy().view(RECORD_DTYPE).reshape(-1)
+        return records_to_host(rec[:n.value])
 
     @_on_device
     def bench(self, iterations, kind):
@@ -256,6 +256,18 @@ class Engine():
     @_on_device
     def reset_pool(self):
         _lib.check(self.lib.c4_selfplay_reset(self.h, _lib.stream_ptr()))
+
+
+def records_to_host(rec):
+    """records (uint8 tensor [n, 64]) -> numpy record array on the host.  CUDA records go through page-locked memory from
+    torch's caching host allocator: the buffer of one generation is reused by the next, and the copy runs at PCIe speed
+    instead of the ~2 GB/s of a pageable first-touch copy (267 MB per generation at 8 GPUs)."""
+    import torch
+    if rec.is_cuda:
+        host = torch.empty(rec.shape, dtype=rec.dtype, pin_memory=True)
+        host.copy_(rec)
+        rec = host
+    return rec.numpy().view(RECORD_DTYPE).reshape(-1)
 
 
 def augment_pack(records_device):

@@ -305,7 +305,8 @@ def main():
                 # every rank plays its share (global game ids, so the generation does not depend on N), then the NCCL
                 # all-gather of the records and the device-side sort: every GPU ends with the whole generation in HBM and rank 0
                 # (the reference collects the games in one process, neural/training.py:112-133) with the whole generation on its host
-                rec = generate_sharded(pool2, n_e2e, dst=0)
+                phases = {}
+                rec = generate_sharded(pool2, n_e2e, dst=0, timing=phases)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             (n_rec,), (dt_max,) = reduce_sum_max([len(rec) if rec is not None else 0], [dt])
@@ -323,6 +324,7 @@ def main():
                         "records to every GPU + device-side sort + copy of the whole generation to rank 0's host; cold memo; wall "
                         "clock, max over ranks; second of two such generations" % (n_e2e, args.e2e_games, args.games)),
                "records": n_rec, "seconds": dt_max, "seconds_first_run": first,
+               "rank0_phase_seconds": {k: round(v, 4) for k, v in phases.items()} if world > 1 else None,
                "records_sha256_16": digest_records(rec) if world > 1 and rec is not None else None}
         pool2.engine.close()
         del rec

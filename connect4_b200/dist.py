@@ -49,22 +49,41 @@ def sort_records_device(rec):
     return rec.index_select(0, order)
 
 
-def generate_sharded(pool, n_games, group=None, dst=None):
+def generate_sharded(pool, n_games, group=None, dst=None, timing=None):
     """Play this rank's share of `n_games` on `pool` (SelfPlayPool) and all-gather the records of all ranks (every GPU ends
     with the whole generation in HBM: `pool.engine.last_generation_device`, sorted by (game_id, ply)).
     Returns them as a numpy record array -- identical on every rank; with `dst` = a rank, only that rank copies the
     generation to its host (the reference collects the games in ONE process, neural/training.py:112-133) and the other
-    ranks return None."""
+    ranks return None.  `timing`: a dict that receives this rank's seconds per phase (adds a device synchronisation
+    after each phase)."""
+    import time
+    import torch
     import torch.distributed as dist
     from .engine import records_to_host
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+
+    def mark(name, t0):
+        if timing is None:
+            return t0
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        timing[name] = t1 - t0
+        return t1
+
+    t = time.perf_counter()
     n_local, base, stride = shard_games(n_games, rank, world)
     pool.generate_records(n_local, game_id_base=base, game_id_stride=stride, to_host=False)
     rec = pool.engine.last_records_device
+    t = mark("generate", t)
     if world > 1:
         rec = all_gather_records(rec, group)
+    t = mark("all_gather", t)
     rec = sort_records_device(rec)
     pool.engine.last_generation_device = rec
+    t = mark("sort", t)
     if dst is not None and rank != dst:
         return None
-    return records_to_host(rec)
+    out = records_to_host(rec)
+    mark("host_copy", t)
+    return out

@@ -47,6 +47,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <chrono>
 #include <mutex>
 #include <thread>
@@ -81,6 +82,8 @@ struct SpParams {
     int n_net;                          // tower CTAs = rings
     unsigned ring_cap;                  // entries per ring (power of two >= game slots)
     int stage_nodes;                    // node records per game that a tree CTA keeps in shared memory (multiple of 8; 0 = none)
+    int table_entries;                  // entries of each PUCT table (log / sqrt / reciprocal) a tree CTA of the ONE-launch form keeps in
+                                        // the shared memory it carries anyway (0: read them through L1 from HBM)
 };
 
 // tree CTA control block (shared memory)
@@ -105,11 +108,15 @@ __device__ __forceinline__ unsigned long long *sp_ring(SpGlobal *G, unsigned cap
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(G) + sp_rings_off()) + (size_t)r * cap * 2;
 }
 __device__ __forceinline__ void st_volu(unsigned *p, unsigned v) { *reinterpret_cast<volatile unsigned *>(p) = v; }
+// PUCT tables in a tree CTA's dynamic shared memory (one-launch form): behind the control block, SP_TAB_STRIDE entries apart
+#define SP_TAB_OFF ((uint32_t)((sizeof(SpCtl) + 127) & ~(size_t)127))
+#define SP_TAB_STRIDE 4096u
 
 #define SP_PROF(i, v) do { if (P.prof) atomicAdd(&G->prof[i], (unsigned long long)(v)); } while (0)
 
 // the split engine's port: the answer comes from the game's answer slot in HBM / L2 (written by a tower CTA), the request goes
 // to the ring of the tower its ticket names
+template <bool TAB>
 struct SpPort {
     static constexpr int GC_MAX = SP_GC_MAX;
     static constexpr bool DEDUP = true;
@@ -121,7 +128,7 @@ struct SpPort {
     uint32_t stage_nodes;
     __device__ __forceinline__ void stage(GameS &g, int gl) const { g.sp32 = stage_base32 + (uint32_t)gl * stage_nodes * 32u; g.sp_nodes = stage_nodes; }
 #else
-    typedef Game GameType;
+    typedef typename std::conditional<TAB, GameTab<SP_TAB_OFF, SP_TAB_STRIDE>, Game>::type GameType;
     __device__ __forceinline__ void stage(Game &, int) const {}
 #endif
     const uint32_t *memo;
@@ -170,7 +177,8 @@ struct SpPort {
 
 // ------------------------------------------------------------------------------------------------ tree CTAs
 // (body of a tree CTA: CTAs 0 .. n_tree - 1 of the launch)
-template <bool SELFPLAY>
+// (TAB: the PUCT tables are read from the CTA's dynamic shared memory -- one-launch form only)
+template <bool SELFPLAY, bool TAB>
 __device__ __forceinline__ void sp_tree_body(const C4Dev &dg, SpGlobal *G, const SpParams &P, SpCtl *S)
 {
     const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -182,6 +190,14 @@ __device__ __forceinline__ void sp_tree_body(const C4Dev &dg, SpGlobal *G, const
     for (int i = threadIdx.x; i < (int)(sizeof(SpCtl) / 4); i += blockDim.x) reinterpret_cast<uint32_t *>(S)[i] = 0u;
     __syncthreads();
     for (int i = threadIdx.x; i < SP_GC_MAX; i += blockDim.x) S->status[i] = (i < Gc) ? fz_entry_status(dg, g0 + i) : (int)ST_IDLE;
+    if (TAB) {
+        // PUCT tables (19 KB at 800 simulations; every level of every descent reads all three): a tree CTA of the one-launch form
+        // carries the tower's 200 KB of shared memory and has only ~28 KB of L1, which the tables would share with the node records
+        double *tab = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(S) + SP_TAB_OFF);
+        for (int i = threadIdx.x; i < P.table_entries; i += blockDim.x) {
+            tab[i] = dg.pbc[i]; tab[SP_TAB_STRIDE + i] = dg.sqt[i]; tab[2 * SP_TAB_STRIDE + i] = dg.rcp[i];
+        }
+    }
 #ifdef C4_SP_STAGE_TOP
     // shared-memory staging of the top of each tree: the first stage_nodes node records of every game of this CTA (the blocks
     // created first: root, its children, the first expansions) are copied in here, live in shared memory while the launch
@@ -243,9 +259,9 @@ __device__ __forceinline__ void sp_tree_body(const C4Dev &dg, SpGlobal *G, const
 #ifdef C4_SP_STAGE_TOP
         uint32_t stage_base32;                                                // (volatile: computed once, not re-derived from the window base at every access)
         asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(stage_base32) : "l"(stage_base));
-        const SpPort port{S, G, stage_base32, (uint32_t)P.stage_nodes, dg.memo, dg.memo_mask, dg.memo_epoch, (unsigned)P.n_net, P.ring_cap};
+        const SpPort<false> port{S, G, stage_base32, (uint32_t)P.stage_nodes, dg.memo, dg.memo_mask, dg.memo_epoch, (unsigned)P.n_net, P.ring_cap};
 #else
-        const SpPort port{S, G, dg.memo, dg.memo_mask, dg.memo_epoch, (unsigned)P.n_net, P.ring_cap};
+        const SpPort<TAB> port{S, G, dg.memo, dg.memo_mask, dg.memo_epoch, (unsigned)P.n_net, P.ring_cap};
 #endif
         int rot = (warp * 9) % Gc;
         bool idle = false;
@@ -673,7 +689,7 @@ __global__ void __launch_bounds__(SP_TREE_THREADS, 1)
 k_sp_tree(const C4Dev dg, SpGlobal *G, SpParams P)
 {
     __shared__ SpCtl Sm;
-    sp_tree_body<SELFPLAY>(dg, G, P, &Sm);
+    sp_tree_body<SELFPLAY, false>(dg, G, P, &Sm);
 }
 template <typename OP, int F>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -689,7 +705,13 @@ __global__ void __launch_bounds__(SP_TREE_THREADS, 1)
 k_sp_one(const C4Dev dg, const unsigned char *__restrict__ image, int R, SpGlobal *G, SpParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    if ((int)blockIdx.x < P.n_tree) sp_tree_body<SELFPLAY>(dg, G, P, reinterpret_cast<SpCtl *>(smem));
+    if ((int)blockIdx.x < P.n_tree) {
+#ifndef C4_SP_STAGE_TOP
+        if (P.table_entries) sp_tree_body<SELFPLAY, true>(dg, G, P, reinterpret_cast<SpCtl *>(smem));
+        else
+#endif
+        sp_tree_body<SELFPLAY, false>(dg, G, P, reinterpret_cast<SpCtl *>(smem));
+    }
     else sp_net_body<OP, F, 0, 16, 17, true>(image, R, G, dg.ctr, P, smem, blockIdx.x - (unsigned)P.n_tree);
 }
 
@@ -819,7 +841,6 @@ bool c4_split_eligible(const c4_net *net, int max_games, long long live_games)
 int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulations, bool selfplay,
                  unsigned long long stop_games, double stop_ms, cudaStream_t stream)
 {
-    (void)simulations;
     const int sms = sp_sms();
     C4_REQUIRE(c4_split_supported(net, max_games), "split engine: network, pool size or device not supported");
     SpDevice &pd = *sp_device();
@@ -855,6 +876,15 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     }
 #endif
     const bool two = sp_two_launches(pd);                                 // (may run the probe, which uses the control block: before the reset)
+    // PUCT tables in the tree CTAs' shared memory (one-launch form only; env C4_SP_SMEM_TABLES=0/1 overrides the default)
+    P.table_entries = 0;
+#ifndef C4_SP_STAGE_TOP
+    {
+        const bool want = getenv("C4_SP_SMEM_TABLES") ? atoi(getenv("C4_SP_SMEM_TABLES")) != 0 : true;
+        const size_t need = SP_TAB_OFF + (size_t)3 * 8 * SP_TAB_STRIDE;
+        if (want && !two && simulations + 2 <= (int)SP_TAB_STRIDE && need <= (size_t)smem) P.table_entries = simulations + 2;
+    }
+#endif
     if (two) P.stage_nodes = 0;                                           // (the tree kernel of the two-launch form has no dynamic shared memory)
     // ticket counter, flags, answer slots and the rings' stamps all start from zero
     C4_CUDA(cudaMemsetAsync(pd.G, 0, sp_rings_off() + (size_t)n_net * cap * 16, stream));

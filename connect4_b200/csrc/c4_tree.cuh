@@ -280,6 +280,7 @@ struct Game {
     int sims_done;
     u64 c0, c1;          // root board
     int age;             // root age
+    static constexpr bool SMEM_TABLES = false;   // the PUCT tables are read from HBM (through L1) via C4Dev::pbc / sqt / rcp
     // node accessors (node i of this game): every read / write of the tree goes through these
     __device__ __forceinline__ C4NodeA lda(uint32_t i) const { return ld_a(gp + i); }
     __device__ __forceinline__ C4NodeB ldb(uint32_t i) const { return ld_b(gp + i); }
@@ -287,6 +288,19 @@ struct Game {
     __device__ __forceinline__ void stb(uint32_t i, double prior, double vsel) const { st_b(gp + i, prior, vsel); }
     __device__ __forceinline__ void st_vsel(uint32_t i, double vsel) const { gp[i].b.vsel = vsel; }
     __device__ __forceinline__ bool in_hbm(uint32_t) const { return true; }
+};
+// A game of a CTA that keeps the three PUCT tables (C4Dev::pbc / sqt / rcp) in its DYNAMIC shared memory, table k at byte
+// OFF + k * 8 * STRIDE: compile-time offsets from the dynamic shared-memory base, so a table read is one LDS with an immediate
+// and costs no pointer register (three generic pointers instead spilled the 64-register tree warps).  Used by the tree CTAs
+// of the one-launch split engine (c4_split.cu), which carry the tower's shared memory and have little L1.
+template <uint32_t OFF, uint32_t STRIDE>
+struct GameTab : Game {
+    static constexpr bool SMEM_TABLES = true;
+    static __device__ __forceinline__ const double *table(int k)
+    {
+        extern __shared__ __align__(16) unsigned char c4_dyn_smem[];
+        return reinterpret_cast<const double *>(c4_dyn_smem + OFF) + (size_t)k * STRIDE;
+    }
 };
 // A game whose FIRST `sp_nodes` nodes (the blocks created first = the top of the tree, the records every simulation reads
 // and writes) live in shared memory for the length of a persistent launch ("shared-memory staging of the hot top of each
@@ -473,8 +487,9 @@ __device__ __forceinline__ Leaf descend(const C4Dev &d, const GAME &G)
         C4NodeA a = G.lda(cn);
         C4NodeB b = G.ldb(cn);
         // exploration factor of the parent: log((N+base+1)/base)+init and sqrt(N) from host-built tables (glibc log / sqrt)
-        const double pbc = d.pbc[visits];
-        const double sq = d.sqt[visits];
+        double pbc, sq;
+        if constexpr (GAME::SMEM_TABLES) { pbc = GAME::table(0)[visits]; sq = GAME::table(1)[visits]; }
+        else { pbc = d.pbc[visits]; sq = d.sqt[visits]; }
         const bool exists = (lane < 7) && (a.meta & C4_META_EXISTS);
         // speculative prefetch: every lane pulls ITS child's block (two 128-byte lines) towards L2 while the warp decides;
         // HBM bandwidth is nowhere near a limit for this kernel (profiles/README.md)
@@ -489,7 +504,8 @@ __device__ __forceinline__ Leaf descend(const C4Dev &d, const GAME &G)
         if (d.fastdiv) {
             // correctly rounded sqrt(N)/(n+1) from the correctly rounded reciprocal and two FMAs (Markstein's
             // sequence); upload_config checked it against IEEE division for EVERY (N, n) pair this context can meet
-            const double y = d.rcp[a.visits + 1u];
+            double y;
+            if constexpr (GAME::SMEM_TABLES) y = GAME::table(2)[a.visits + 1u]; else y = d.rcp[a.visits + 1u];
             const double q0 = __dmul_rn(sq, y);
             q = __fma_rn(__fma_rn(-den, q0, sq), y, q0);
         } else {

@@ -1,0 +1,89 @@
+"""split engine, cold benchmark generation (4,096 slots until 4,096 games are done), three measurements in one process:
+ 1. PUCT tables in the tree CTAs' shared memory off / on (C4_SP_SMEM_TABLES), alternating;
+ 2. the time profile of one generation in slices of --slice-ms (positions/s, network evaluations/s, memo hit rate per slice);
+ 3. a PHASED tower count: the first T1 ms with n1 tower CTAs, the rest with n2 (the engine reads C4_SP_NET_CTAS per launch and a
+    launch continues the pool the previous one left), against the constant tower counts.
+usage: phase_ab.py [--games N] [--slice-ms 25] [--reps 2]"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+os.environ.setdefault("C4_FZ_TIMEOUT_S", "30")
+os.environ["C4_ENGINE"] = "split"
+from connect4_b200.mcts import MCTSConfig
+from connect4_b200.neural.game_pool import SelfPlayPool
+from connect4_b200.neural.model import ModelWrapper
+
+
+def arg(name, default):
+    return type(default)(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
+
+
+slots = arg("--games", 4096)
+slice_ms = arg("--slice-ms", 25.0)
+reps = arg("--reps", 2)
+z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests/golden/example_net_state.npz"))
+model = ModelWrapper(state_dict={k: z[k] for k in z.files})
+pool = SelfPlayPool(model, MCTSConfig(800, 19652, 1.25, 0.3, 0.25, 6), concurrent_games=slots, seed=1)
+
+
+def generation(phases):
+    """phases = [(tower CTAs, ms or None), ...]; the last phase runs until `slots` games are done.  -> positions/s, hit rate"""
+    pos = ms = ev = hit = games = 0
+    for i, (n, t) in enumerate(phases):
+        os.environ["C4_SP_NET_CTAS"] = str(n)
+        last = i == len(phases) - 1
+        r = pool.stream(stop_games=slots - games if last else 0, max_ms=0.0 if last else float(t), reset=(i == 0), cold_memo=(i == 0))
+        pos += r["positions"]; ms += r["device_ms"]; ev += r["evals"]; hit += r["memo_hits"]; games += r["games"]
+        if games >= slots:
+            break
+    return pos / ms * 1e3, hit / max(1, hit + ev), ms
+
+
+pool.stream(stop_games=slots, reset=True, cold_memo=True)          # warm-up (module load, allocator)
+print("== 1. PUCT tables in shared memory (72 towers)", flush=True)
+best = {}
+for rep in range(reps + 1):
+    for tab in ("0", "1"):
+        os.environ["C4_SP_SMEM_TABLES"] = tab
+        v, h, ms = generation([(72, None)])
+        best[tab] = max(best.get(tab, 0.0), v)
+        print("tables %s: %.0f positions/s  hit %.3f  %.1f ms" % (tab, v, h, ms), flush=True)
+tab = "1" if best["1"] > best["0"] else "0"
+os.environ["C4_SP_SMEM_TABLES"] = tab
+print("-> tables %s for the rest" % tab, flush=True)
+
+print("== 2. time profile of one generation, 72 towers, slices of %.0f ms" % slice_ms, flush=True)
+os.environ["C4_SP_NET_CTAS"] = "72"
+games = 0
+t = 0.0
+first = True
+while games < slots:
+    r = pool.stream(max_ms=slice_ms, reset=first, cold_memo=first)
+    first = False
+    games += r["games"]; t += r["device_ms"]
+    print("t %6.1f ms: %7.0f positions/s  %8.0f evals/s  hit %.3f  games done %d" % (
+        t, r["positions"] / r["device_ms"] * 1e3, r["evals"] / r["device_ms"] * 1e3,
+        r["memo_hits"] / max(1, r["memo_hits"] + r["evals"]), games), flush=True)
+
+print("== 3. constant and phased tower counts", flush=True)
+plans = [[(72, None)]]
+if "--early" in sys.argv:                                            # more towers at the cold start: measured worse than constant 72
+    for n1 in (88, 104):
+        for t1 in (25.0, 50.0, 100.0):
+            for n2 in (56, 64, 72):
+                plans.append([(n1, t1), (n2, None)])
+# the time profile says: towers saturated (42 M evaluations/s) from ~60 to ~270 ms, trees the limit after that
+for t1 in (250.0, 275.0, 300.0):
+    for n2 in (48, 56, 64):
+        plans.append([(72, t1), (n2, None)])
+for n_mid in (80, 88):
+    for n2 in (56, 64):
+        plans.append([(72, 50.0), (n_mid, 225.0), (n2, None)])
+plans += [[(64, 50.0), (80, 225.0), (56, None)], [(56, 50.0), (72, 225.0), (56, None)], [(72, None)]]
+for plan in plans:
+    res = [generation(plan) for _ in range(reps)]
+    v = max(x[0] for x in res)
+    print("%-40s best %.0f positions/s (all: %s)  hit %.3f" % (
+        " -> ".join("%d%s" % (n, "" if t is None else " for %.0f ms" % t) for n, t in plan), v,
+        ", ".join("%.0f" % x[0] for x in res), res[0][1]), flush=True)
+pool.engine.close()

@@ -41,6 +41,7 @@ int c4_fused_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
                  unsigned long long stop_games, double stop_ms, cudaStream_t stream);
 // c4_split.cu: the persistent engine with tree CTAs and tower CTAs on separate SMs (same contract)
 bool c4_split_eligible(const c4_net *net, int max_games, long long live_games);
+int c4_split_last_launches();
 int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulations, bool selfplay,
                  unsigned long long stop_games, double stop_ms, cudaStream_t stream);
 
@@ -1229,7 +1230,7 @@ extern "C" int c4_selfplay_stream(c4_ctx *ctx, int eval_kind, int reset, int64_t
     float tree_sum = 0.f, net_sum = 0.f;
     if (fused) {
         if ((rc = persistent_run(ctx, ctx->max_games, true, games_goal, max_ms, s))) return rc;
-        ctx->last_launches += eng == 3 ? 2 : 1;
+        ctx->last_launches += eng == 3 ? c4_split_last_launches() : 1;
     } else {
         // lock-step engine: chunks of passes with a host look at the counters in between
         for (long long it = 0;; it++) {

@@ -62,10 +62,14 @@
 #define SP_PATIENCE 4                                     // watch time-outs after which a parked game asks for itself
 #define SP_WATCH_SWEEPS 2048                              // mail-warp sweeps (~150 ns each) until a watch times out
 
-struct SpGlobal {
+struct SpHeader {                                         // (what the host reads back after a launch)
     unsigned ticket; unsigned pad0[31];                   // requests issued so far (dealt round-robin to the towers)
-    int quit, abort, trees_exited; int pad2[29];
+    int quit, abort, trees_exited, sliced; int pad2[28];  // sliced: a tree CTA ended this launch because its time slice was over
     unsigned long long prof[32];
+    unsigned long long sig[16];                           // load signals of the launch (always on): [0] strips, [1] boards in them,
+                                                          // [2] tree-warp cycles in runs, [3] tree-warp cycles idle between runs
+};
+struct SpGlobal : SpHeader {
     unsigned long long ans[SP_GMAX][8];                   // per game slot: {float bits | tag << 32} x {prior[7], value}
     // followed by the rings: [n_net][ring_cap][2] words
 };
@@ -75,6 +79,8 @@ struct SpParams {
     int n_slots;                        // game slots of the pool
     unsigned long long stop_games;      // leave once ctr->games_finished reaches this (0 = never)
     unsigned long long stop_ns;         // leave after this much run time (0 = never)
+    unsigned long long slice_ns;        // leave after this much run time AND tell the host (SpGlobal::sliced) that the launch is to be
+                                        // continued by another one, possibly with another tower count (0 = no slices)
     const int *host_abort;              // mapped host word: non-zero = the host gave up waiting, leave at once
     int prof;                           // accumulate cycle / event sums in SpGlobal::prof (C4_FZ_DEBUG)
     int batch_ns;                       // a dispatcher that finds less than a strip waits up to this long for more
@@ -223,6 +229,7 @@ __device__ __forceinline__ void sp_tree_body(const C4Dev &dg, SpGlobal *G, const
                     bool stop = false;
                     if (P.stop_games && __ldcg(&dg.ctr->games_finished) >= P.stop_games) stop = true;
                     if (P.stop_ns && fz_globaltimer() - t_begin > P.stop_ns) stop = true;
+                    if (!stop && P.slice_ns && fz_globaltimer() - t_begin > P.slice_ns) { stop = true; st_vol(&G->sliced, 1); }
                     if (stop) { st_vol(&S->stop, 1); atomicAdd(&S->wake, 1); }
                 }
                 if ((it & 8191u) == 0u && *reinterpret_cast<const volatile int *>(P.host_abort)) st_vol(&G->abort, 1);
@@ -324,6 +331,7 @@ __device__ __forceinline__ void sp_tree_body(const C4Dev &dg, SpGlobal *G, const
         __syncwarp();
         if (lane == 0) {
             if (P.prof) { SP_PROF(8, n_run); SP_PROF(9, t_run); SP_PROF(10, t_idle); }
+            atomicAdd(&G->sig[2], (unsigned long long)t_run); atomicAdd(&G->sig[3], (unsigned long long)t_idle);
             __threadfence_block();
             atomicAdd(&S->tree_exited, 1);
         }
@@ -539,6 +547,7 @@ __device__ __forceinline__ void sp_net_body(const unsigned char *__restrict__ im
         E.calib = nullptr;
         int c = 0;                                                           // global (strip, layer, tile) counter
         unsigned ring_head = 0u;                                             // dispatcher: entries of this tower's ring consumed
+        unsigned sig_strips = 0u;                                            // dispatcher: strips served (boards = ring_head)
         const unsigned long long *ring = sp_ring(G, P.ring_cap, (int)tower);
         for (;;) {
             const long long t_d0 = clock64();
@@ -590,11 +599,12 @@ __device__ __forceinline__ void sp_net_body(const unsigned char *__restrict__ im
                         S->strip_tag[lane] = (unsigned)((b >> 48) & 0x3FFFu);
                     }
                     ring_head += (unsigned)k;
+                    sig_strips++;
                     break;
                 }
                 __syncwarp();
                 if (lane == 0) {
-                    if (k == 0) st_vol(&S->quit, 1);
+                    if (k == 0) { st_vol(&S->quit, 1); atomicAdd(&G->sig[0], (unsigned long long)sig_strips); atomicAdd(&G->sig[1], (unsigned long long)ring_head); }
                     __threadfence_block();
                     st_vol(&S->strip_nb, k);
                 }
@@ -741,6 +751,8 @@ struct SpDevice {
     cudaStream_t side = nullptr, side2 = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     int coresident = 0;                 // 0 = not probed yet, 1 = two kernels on two streams run side by side, -1 = they do not
+    int adapt_n_net = 0;                // adaptive tower count: where the last sliced run ended (0 = no such run yet)
+    int last_launches = 0;              // kernels launched by the last run
     std::mutex run;                     // one run per device at a time: the rings and answer slots are per device
 };
 static SpDevice g_sp_device[64];
@@ -803,6 +815,49 @@ static bool sp_coresident(SpDevice &pd)
     return pd.coresident == 1;
 }
 
+// ---- adaptive tower count.  The best split of the SMs between trees and towers moves with the state of a generation (time profile
+// in profiles/README.md: a cold generation at 4,096 games goes through a cold start with hardly any evaluations, a middle phase at
+// ~81 % memo hits in which 72 saturated towers hold the trees back -- best constant count there: 80 -- and a tail at > 90 % hits
+// in which 56 towers are enough and every further tree SM counts).  A constant count (72) is a compromise; the hand-made
+// schedule 64 -> 80 -> 56 towers measured +5 %.  So a run is cut into slices (SpParams::slice_ns): a slice ends like any stop (tree
+// warps finish the answers in flight, every game's state is in HBM), the host reads the slice's load signals and launches the
+// next slice with the tower count they ask for.  Signals: boards per strip b (a tower takes what its ring holds, so b says how
+// far from saturated the towers are: capacity use u = throughput(b) / throughput(NB), strip time ~ 1 + gamma b) and the share i
+// of their time the tree warps found no runnable game.  Balance: evaluations asked per busy tree SM = evaluations a saturated
+// tower serves, n_net' / n_tree' = n_net u / (n_tree (1 - i)).  Records do not depend on any of this (tests/test_gpu_split.py).
+struct SpAdapt {
+    bool on = false;
+    int lo = 0, hi = 0;
+    double slice_ms = 25.0;
+};
+static SpAdapt sp_adapt_config(const c4_net *net, int max_games, int sms, bool two)
+{
+    SpAdapt a;
+    const char *e = getenv("C4_SP_ADAPT");                                // "0" = off, "1" = on, "<ms>" = on with this slice length
+    if (e && atof(e) <= 0.0) return a;
+    if (two || getenv("C4_SP_NET_CTAS") || net->F != 32 || max_games < 1024) return a;    // (measured for 32-filter networks only)
+    a.on = true;
+    if (e && atof(e) > 1.0) a.slice_ms = atof(e);
+    a.lo = (sms * 40 + 74) / 148;
+    a.hi = std::min((sms * 96 + 74) / 148, sms - (max_games + SP_GC_MAX - 1) / SP_GC_MAX);
+    if (a.hi < a.lo) a.on = false;
+    return a;
+}
+static int sp_adapt_next(const SpAdapt &a, int sms, int n_net, int n_tree, const unsigned long long *sig)
+{
+    const double NB = SP_NB, gamma = 0.145;                               // strip time ~ T0 (1 + gamma b): 16.5k cycles at 1 board, 47k at 16
+    const double b = sig[0] ? (double)sig[1] / (double)sig[0] : 0.0;
+    const double u = b >= NB - 1.0 ? 1.0 : b * (1.0 + gamma * NB) / (NB * (1.0 + gamma * b));
+    const double idle = (sig[2] + sig[3]) ? (double)sig[3] / (double)(sig[2] + sig[3]) : 0.0;
+    const double rho = std::max(1e-3, n_net * u) / std::max(1e-3, n_tree * (1.0 - idle));
+    double target = sms * rho / (1.0 + rho);
+    if (target < n_net && idle > 0.05) target = n_net;                    // trees wait although the towers are not full: latency, not capacity
+    target = std::max((double)n_net - 16.0, std::min((double)n_net + 16.0, target));
+    int n = (int)(target / 4.0 + 0.5) * 4;
+    n = std::max(a.lo, std::min(a.hi, n));
+    return n;
+}
+
 static bool c4_split_supported(const c4_net *net, int max_games)
 {
     if (!net || (net->F != 32 && net->F != 64) || !net->use_tc || !net->image_tc) return false;
@@ -836,6 +891,13 @@ bool c4_split_eligible(const c4_net *net, int max_games, long long live_games)
     return c4_split_supported(net, max_games);
 }
 
+// kernels launched by the last c4_split_run on the current device (one per slice; two in the two-launch form)
+int c4_split_last_launches()
+{
+    SpDevice *pd = sp_device();
+    return pd ? pd->last_launches : 0;
+}
+
 // Run the pool until every game slot is idle / done, `stop_games` games have finished (counter in d.ctr) or `stop_ms` have
 // passed, and wait for it (same contract as c4_fused_run).
 int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulations, bool selfplay,
@@ -846,6 +908,7 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     SpDevice &pd = *sp_device();
     std::lock_guard<std::mutex> run_lock(pd.run);
     static const bool debug = getenv("C4_FZ_DEBUG") != nullptr;
+    const bool adapt_log = getenv("C4_SP_ADAPT_LOG") != nullptr;
     *reinterpret_cast<volatile int *>(pd.h_abort) = 0;
     SpParams P;
     P.n_slots = max_games;
@@ -854,94 +917,124 @@ int c4_split_run(const C4Dev &d, const c4_net *net, int max_games, int simulatio
     P.host_abort = pd.d_abort;
     P.prof = debug ? 1 : 0;
     P.batch_ns = getenv("C4_SP_BATCH_NS") ? atoi(getenv("C4_SP_BATCH_NS")) : 0;
-    const int n_net = sp_net_ctas(sms, net->F);
-    const int n_tree = std::min(sms - n_net, max_games);
     unsigned cap = 64;
     while ((int)cap < max_games) cap <<= 1;
-    P.n_net = n_net;
     P.ring_cap = cap;
-    P.n_tree = n_tree;
     const int smem = net->F == 32 ? sp_net_smem<32>(net->R) : sp_net_smem<64>(net->R);
-    P.stage_nodes = 0;
-#ifdef C4_SP_STAGE_TOP
-    // ONE launch: every CTA has the tower's shared memory; a tree CTA uses it for the top of its games' trees (env
-    // C4_SP_STAGE=0 turns that off; C4_SP_STAGE=n caps the node records per game).  Compiled in with -DC4_SP_STAGE_TOP only:
-    // measured slower than no staging (profiles/README.md, "shared-memory staging of the tree top")
-    {
-        const int gc_max = (max_games + n_tree - 1) / n_tree;
-        const int avail = smem - (int)((sizeof(SpCtl) + 127) & ~(size_t)127);
-        int nodes = std::min(avail / (gc_max * 32), std::min(512, d.blocks_per_game * C4_SLOTS)) & ~7;
-        if (getenv("C4_SP_STAGE")) nodes = std::min(nodes, atoi(getenv("C4_SP_STAGE")) & ~7);
-        P.stage_nodes = std::max(0, nodes);
-    }
-#endif
     const bool two = sp_two_launches(pd);                                 // (may run the probe, which uses the control block: before the reset)
-    // PUCT tables in the tree CTAs' shared memory (one-launch form only; env C4_SP_SMEM_TABLES=0/1 overrides the default)
-    P.table_entries = 0;
-#ifndef C4_SP_STAGE_TOP
-    {
-        const bool want = getenv("C4_SP_SMEM_TABLES") ? atoi(getenv("C4_SP_SMEM_TABLES")) != 0 : true;
-        const size_t need = SP_TAB_OFF + (size_t)3 * 8 * SP_TAB_STRIDE;
-        if (want && !two && simulations + 2 <= (int)SP_TAB_STRIDE && need <= (size_t)smem) P.table_entries = simulations + 2;
-    }
-#endif
-    if (two) P.stage_nodes = 0;                                           // (the tree kernel of the two-launch form has no dynamic shared memory)
-    // ticket counter, flags, answer slots and the rings' stamps all start from zero
-    C4_CUDA(cudaMemsetAsync(pd.G, 0, sp_rings_off() + (size_t)n_net * cap * 16, stream));
-    if (two) {
-        auto kn = net->F == 32 ? (net->fp16 ? k_sp_net<OpFP16, 32> : k_sp_net<OpBF16, 32>) : (net->fp16 ? k_sp_net<OpFP16, 64> : k_sp_net<OpBF16, 64>);
-        auto kt = selfplay ? k_sp_tree<true> : k_sp_tree<false>;
-        C4_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        // Both kernels must be LOADED before the first of them starts: with lazy module loading (the CUDA 12 default) the
-        // first launch of a function loads it, and that load can wait for running kernels -- here for a tower kernel that
-        // itself waits for the tree kernel: a deadlock, and it was the first thing the bring-up hit.
-        {
-            cudaFuncAttributes fa;
-            C4_CUDA(cudaFuncGetAttributes(&fa, kn));
-            C4_CUDA(cudaFuncGetAttributes(&fa, kt));
-        }
-        C4_CUDA(cudaEventRecord(pd.ev_a, stream));
-        C4_CUDA(cudaStreamWaitEvent(pd.side, pd.ev_a, 0));
-        kn<<<n_net, TC_THREADS, smem, pd.side>>>((const unsigned char *)net->image_tc, net->R, pd.G, d.ctr, P);
-        C4_CUDA(cudaGetLastError());
-        kt<<<n_tree, SP_TREE_THREADS, 0, stream>>>(d, pd.G, P);
-        C4_CUDA(cudaGetLastError());
-        C4_CUDA(cudaEventRecord(pd.ev_b, pd.side));
-        C4_CUDA(cudaStreamWaitEvent(stream, pd.ev_b, 0));
-    } else {
-        void (*k1)(const C4Dev, const unsigned char *, int, SpGlobal *, SpParams);
-        if (net->F == 32) k1 = selfplay ? (net->fp16 ? k_sp_one<OpFP16, 32, true> : k_sp_one<OpBF16, 32, true>)
-                                        : (net->fp16 ? k_sp_one<OpFP16, 32, false> : k_sp_one<OpBF16, 32, false>);
-        else k1 = selfplay ? (net->fp16 ? k_sp_one<OpFP16, 64, true> : k_sp_one<OpBF16, 64, true>)
-                           : (net->fp16 ? k_sp_one<OpFP16, 64, false> : k_sp_one<OpBF16, 64, false>);
-        C4_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k1<<<n_tree + n_net, SP_TREE_THREADS, smem, stream>>>(d, (const unsigned char *)net->image_tc, net->R, pd.G, P);
-        C4_CUDA(cudaGetLastError());
-    }
+    const SpAdapt adapt = sp_adapt_config(net, max_games, sms, two);
+    int n_net = sp_net_ctas(sms, net->F);
+    if (adapt.on) n_net = std::max(adapt.lo, std::min(adapt.hi, pd.adapt_n_net ? pd.adapt_n_net : (sms * 64 + 74) / 148));
     const double limit_s = getenv("C4_FZ_TIMEOUT_S") ? atof(getenv("C4_FZ_TIMEOUT_S")) : 900.0;
-    const auto t0 = std::chrono::steady_clock::now();
+    const auto t_call = std::chrono::steady_clock::now();
     bool asked = false;
-    for (long long it = 0;; it++) {
-        cudaError_t q = cudaStreamQuery(stream);
-        if (q == cudaSuccess) break;
-        if (q != cudaErrorNotReady) { C4_CUDA(q); }
-        const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (!asked && el > limit_s) { *reinterpret_cast<volatile int *>(pd.h_abort) = 1; asked = true; }
-        if (asked && el > limit_s + 5.0) {
-            fprintf(stderr, "[split] the launches did not end %.0f s after the abort request; giving up\n", 5.0);
-            fflush(stderr);
-            _exit(86);
+    pd.last_launches = 0;
+    for (int slice = 0;; slice++) {
+        const int n_tree = std::min(sms - n_net, max_games);
+        P.n_net = n_net;
+        P.n_tree = n_tree;
+        // time limits of this launch: what is left of the caller's limit, and the slice of the adaptive tower count
+        P.slice_ns = 0ULL;
+        if (stop_ms > 0.0) {
+            const double left_ms = stop_ms - std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+            if (slice > 0 && left_ms <= 0.0) break;
+            P.stop_ns = (unsigned long long)(std::max(left_ms, 0.01) * 1e6);
+            if (adapt.on && left_ms > adapt.slice_ms) P.slice_ns = (unsigned long long)(adapt.slice_ms * 1e6);
+        } else if (adapt.on) P.slice_ns = (unsigned long long)(adapt.slice_ms * 1e6);
+        P.stage_nodes = 0;
+#ifdef C4_SP_STAGE_TOP
+        // ONE launch: every CTA has the tower's shared memory; a tree CTA uses it for the top of its games' trees (env
+        // C4_SP_STAGE=0 turns that off; C4_SP_STAGE=n caps the node records per game).  Compiled in with -DC4_SP_STAGE_TOP only:
+        // measured slower than no staging (profiles/README.md, "shared-memory staging of the tree top")
+        {
+            const int gc_max = (max_games + n_tree - 1) / n_tree;
+            const int avail = smem - (int)((sizeof(SpCtl) + 127) & ~(size_t)127);
+            int nodes = std::min(avail / (gc_max * 32), std::min(512, d.blocks_per_game * C4_SLOTS)) & ~7;
+            if (getenv("C4_SP_STAGE")) nodes = std::min(nodes, atoi(getenv("C4_SP_STAGE")) & ~7);
+            P.stage_nodes = std::max(0, nodes);
         }
-        if (it > 2000) std::this_thread::sleep_for(std::chrono::microseconds(el > 1.0 ? 2000 : 50));
-    }
-    if (debug) {
-        unsigned long long h[32];
-        C4_CUDA(cudaMemcpy(h, pd.G->prof, sizeof(h), cudaMemcpyDeviceToHost));
-        const double ns = (double)std::max(1ULL, h[0]), nr = (double)std::max(1ULL, h[8]);
-        fprintf(stderr, "[split prof] %d tree CTAs + %d tower CTAs, %s | strips %llu boards/strip %.2f | tower cycles per strip: idle %.0f busy %.0f "
-                        "(busy share %.2f) = claim %.0f + input %.0f + layers %.0f + heads %.0f | tree runs %llu cycles/run %.0f tree-warp idle share %.2f\n",
-                n_tree, n_net, two ? "two launches" : "one launch", h[0], h[1] / ns, h[2] / ns, h[3] / ns, h[3] / (double)std::max(1ULL, h[2] + h[3]),
-                h[4] / ns, h[5] / ns, h[6] / ns, h[7] / ns, h[8], h[9] / nr, h[10] / (double)std::max(1ULL, h[9] + h[10]));
+#endif
+        // PUCT tables in the tree CTAs' shared memory (one-launch form only; env C4_SP_SMEM_TABLES=0/1 overrides the default)
+        P.table_entries = 0;
+#ifndef C4_SP_STAGE_TOP
+        {
+            const bool want = getenv("C4_SP_SMEM_TABLES") ? atoi(getenv("C4_SP_SMEM_TABLES")) != 0 : true;
+            const size_t need = SP_TAB_OFF + (size_t)3 * 8 * SP_TAB_STRIDE;
+            if (want && !two && simulations + 2 <= (int)SP_TAB_STRIDE && need <= (size_t)smem) P.table_entries = simulations + 2;
+        }
+#endif
+        if (two) P.stage_nodes = 0;                                           // (the tree kernel of the two-launch form has no dynamic shared memory)
+        // ticket counter, flags, answer slots and the rings' stamps all start from zero
+        C4_CUDA(cudaMemsetAsync(pd.G, 0, sp_rings_off() + (size_t)n_net * cap * 16, stream));
+        if (two) {
+            auto kn = net->F == 32 ? (net->fp16 ? k_sp_net<OpFP16, 32> : k_sp_net<OpBF16, 32>) : (net->fp16 ? k_sp_net<OpFP16, 64> : k_sp_net<OpBF16, 64>);
+            auto kt = selfplay ? k_sp_tree<true> : k_sp_tree<false>;
+            C4_CUDA(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            // Both kernels must be LOADED before the first of them starts: with lazy module loading (the CUDA 12 default) the
+            // first launch of a function loads it, and that load can wait for running kernels -- here for a tower kernel that
+            // itself waits for the tree kernel: a deadlock, and it was the first thing the bring-up hit.
+            {
+                cudaFuncAttributes fa;
+                C4_CUDA(cudaFuncGetAttributes(&fa, kn));
+                C4_CUDA(cudaFuncGetAttributes(&fa, kt));
+            }
+            C4_CUDA(cudaEventRecord(pd.ev_a, stream));
+            C4_CUDA(cudaStreamWaitEvent(pd.side, pd.ev_a, 0));
+            kn<<<n_net, TC_THREADS, smem, pd.side>>>((const unsigned char *)net->image_tc, net->R, pd.G, d.ctr, P);
+            C4_CUDA(cudaGetLastError());
+            kt<<<n_tree, SP_TREE_THREADS, 0, stream>>>(d, pd.G, P);
+            C4_CUDA(cudaGetLastError());
+            C4_CUDA(cudaEventRecord(pd.ev_b, pd.side));
+            C4_CUDA(cudaStreamWaitEvent(stream, pd.ev_b, 0));
+            pd.last_launches += 2;
+        } else {
+            void (*k1)(const C4Dev, const unsigned char *, int, SpGlobal *, SpParams);
+            if (net->F == 32) k1 = selfplay ? (net->fp16 ? k_sp_one<OpFP16, 32, true> : k_sp_one<OpBF16, 32, true>)
+                                            : (net->fp16 ? k_sp_one<OpFP16, 32, false> : k_sp_one<OpBF16, 32, false>);
+            else k1 = selfplay ? (net->fp16 ? k_sp_one<OpFP16, 64, true> : k_sp_one<OpBF16, 64, true>)
+                               : (net->fp16 ? k_sp_one<OpFP16, 64, false> : k_sp_one<OpBF16, 64, false>);
+            C4_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k1<<<n_tree + n_net, SP_TREE_THREADS, smem, stream>>>(d, (const unsigned char *)net->image_tc, net->R, pd.G, P);
+            C4_CUDA(cudaGetLastError());
+            pd.last_launches += 1;
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        for (long long it = 0;; it++) {
+            cudaError_t q = cudaStreamQuery(stream);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) { C4_CUDA(q); }
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call).count();
+            if (!asked && el > limit_s) { *reinterpret_cast<volatile int *>(pd.h_abort) = 1; asked = true; }
+            if (asked && el > limit_s + 5.0) {
+                fprintf(stderr, "[split] the launches did not end %.0f s after the abort request; giving up\n", 5.0);
+                fflush(stderr);
+                _exit(86);
+            }
+            if (it > 2000) std::this_thread::sleep_for(std::chrono::microseconds(
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 1.0 ? 2000 : 50));
+        }
+        if (debug) {
+            unsigned long long h[32];
+            C4_CUDA(cudaMemcpy(h, pd.G->prof, sizeof(h), cudaMemcpyDeviceToHost));
+            const double ns = (double)std::max(1ULL, h[0]), nr = (double)std::max(1ULL, h[8]);
+            fprintf(stderr, "[split prof] %d tree CTAs + %d tower CTAs, %s | strips %llu boards/strip %.2f | tower cycles per strip: idle %.0f busy %.0f "
+                            "(busy share %.2f) = claim %.0f + input %.0f + layers %.0f + heads %.0f | tree runs %llu cycles/run %.0f tree-warp idle share %.2f\n",
+                    n_tree, n_net, two ? "two launches" : "one launch", h[0], h[1] / ns, h[2] / ns, h[3] / ns, h[3] / (double)std::max(1ULL, h[2] + h[3]),
+                    h[4] / ns, h[5] / ns, h[6] / ns, h[7] / ns, h[8], h[9] / nr, h[10] / (double)std::max(1ULL, h[9] + h[10]));
+        }
+        if (!adapt.on || asked) break;
+        // the slice's flags and load signals; a launch that no CTA ended for its slice is the last one
+        SpHeader hd;
+        C4_CUDA(cudaMemcpy(&hd, pd.G, sizeof(hd), cudaMemcpyDeviceToHost));
+        if (!hd.sliced || hd.abort) break;
+        const unsigned long long *sig = hd.sig;
+        const int n_prev = n_net;
+        n_net = sp_adapt_next(adapt, sms, n_net, n_tree, sig);
+        if (adapt_log)
+            fprintf(stderr, "[split adapt] slice %d: %d towers, boards/strip %.2f, tree-warp idle share %.3f -> %d towers\n", slice, n_prev,
+                    sig[0] ? (double)sig[1] / (double)sig[0] : 0.0, (sig[2] + sig[3]) ? (double)sig[3] / (double)(sig[2] + sig[3]) : 0.0, n_net);
+        pd.adapt_n_net = n_net;
+        C4_REQUIRE(slice < (1 << 24), "split engine: did not terminate");
     }
     if (asked) { c4_set_error("split engine: host deadline passed (C4_FZ_TIMEOUT_S); the launches were aborted"); return -4; }
     return 0;

@@ -84,6 +84,36 @@ def test_split_generation_does_not_depend_on_towers_memo_or_deduplication(monkey
         _same(recs[0], r)
 
 
+def test_adaptive_tower_count_and_shared_memory_tables_change_work_not_results(monkeypatch):
+    """from 1,024 game slots a run of the split engine is cut into time slices and every slice is launched with the tower count
+    the previous slice's load signals ask for (C4_SP_ADAPT = slice length in ms; 0 = constant count); the tree CTAs read the
+    PUCT tables from shared memory (C4_SP_SMEM_TABLES).  A game may be stopped and continued by another launch, on another
+    tree CTA, any number of times: the records stay those of the lock-step engine"""
+    from connect4_b200.neural.game_pool import SelfPlayPool
+    model = _model()
+    knobs = ("C4_SP_ADAPT", "C4_SP_SMEM_TABLES", "C4_SP_NET_CTAS")
+    recs, launches = [], []
+    for env in ({"C4_SP_ADAPT": "0"}, {"C4_SP_ADAPT": "2"}, {}, {"C4_SP_ADAPT": "2", "C4_SP_SMEM_TABLES": "0"}):
+        for k in knobs:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        recs.append(_generate(monkeypatch, "split", model, _cfg(64), 1100, 2600, seed=5))
+        # the stream interface reports the kernels it launched: one per slice (+ two bookkeeping kernels)
+        monkeypatch.setenv("C4_ENGINE", "split")
+        pool = SelfPlayPool(model, _cfg(64), concurrent_games=1100, seed=5)
+        r = pool.stream(max_ms=40.0, reset=True, cold_memo=True)
+        pool.engine.close()
+        assert r["engine"] == "split" and 30.0 <= r["device_ms"] < 400.0
+        launches.append(r["launches"])
+    for k in knobs:
+        monkeypatch.delenv(k, raising=False)
+    assert launches[0] == 3 and launches[1] >= 10 and launches[3] >= 10, launches
+    for r in recs[1:]:
+        _same(recs[0], r)
+    _same(recs[0], _generate(monkeypatch, "lockstep", model, _cfg(64), 1100, 2600, seed=5))
+
+
 def test_split_search_batch_equals_lockstep_and_oracle(monkeypatch, oracle):
     """stand-alone searches (MCTS.make_move protocol, c4_search_run NET): the whole batch in one persistent launch pair"""
     from connect4_b200.engine import Engine

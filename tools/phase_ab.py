@@ -65,6 +65,60 @@ while games < slots:
         t, r["positions"] / r["device_ms"] * 1e3, r["evals"] / r["device_ms"] * 1e3,
         r["memo_hits"] / max(1, r["memo_hits"] + r["evals"]), games), flush=True)
 
+if "--signals" in sys.argv:
+    # per slice and tower count: throughput next to the engine's own cycle accounting (run with C4_FZ_DEBUG=1: the engine
+    # prints boards per strip, tower busy share and tree-warp idle share of every launch to stderr)
+    for n in (56, 64, 72, 80, 88):
+        os.environ["C4_SP_NET_CTAS"] = str(n)
+        games, t, first = 0, 0.0, True
+        while games < slots:
+            r = pool.stream(max_ms=slice_ms, reset=first, cold_memo=first)
+            first = False
+            games += r["games"]; t += r["device_ms"]
+            print("towers %d t %6.1f ms: %7.0f positions/s  %8.0f evals/s  hit %.3f  games done %d" % (
+                n, t, r["positions"] / r["device_ms"] * 1e3, r["evals"] / r["device_ms"] * 1e3,
+                r["memo_hits"] / max(1, r["memo_hits"] + r["evals"]), games), flush=True)
+    sys.exit(0)
+if "--adapt" in sys.argv:
+    # adaptive tower count (the engine's default for 32-filter networks from 1,024 games) against the constant 72
+    import time
+    def run(label, env):
+        for k in ("C4_SP_NET_CTAS", "C4_SP_ADAPT", "C4_SP_ADAPT_LOG"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        res = []
+        for _ in range(max(1, reps)):
+            r = pool.stream(stop_games=slots, reset=True, cold_memo=True)
+            res.append(r["positions"] / r["device_ms"] * 1e3)
+        print("%-34s cold generation %s positions/s  (launches %d)" % (label, ", ".join("%.0f" % v for v in res), r["launches"]), flush=True)
+    run("constant 72 (C4_SP_ADAPT=0)", {"C4_SP_ADAPT": "0"})
+    for ms in ("10", "15", "25", "40", "60"):
+        run("adaptive, slices of %s ms" % ms, {"C4_SP_ADAPT": ms})
+    run("adaptive, default", {})
+    run("constant 72 (C4_SP_ADAPT=0)", {"C4_SP_ADAPT": "0"})
+    os.environ.pop("C4_SP_ADAPT", None)
+    os.environ["C4_SP_ADAPT_LOG"] = "1"
+    pool.stream(stop_games=slots, reset=True, cold_memo=True)
+    os.environ.pop("C4_SP_ADAPT_LOG", None)
+    # a whole generation of 4 pool-fulls from host start positions to host records (the bench's e2e leg)
+    for label, env in (("constant 72", {"C4_SP_ADAPT": "0"}), ("adaptive", {}), ("constant 72", {"C4_SP_ADAPT": "0"}), ("adaptive", {})):
+        os.environ.pop("C4_SP_ADAPT", None)
+        os.environ.update(env)
+        pool.engine.clear_memo()
+        t0 = time.perf_counter()
+        rec = pool.generate_records(4 * slots)
+        dt = time.perf_counter() - t0
+        print("%-12s generate_records(%d): %d records in %.3f s = %.0f positions/s" % (label, 4 * slots, len(rec), dt, len(rec) / dt), flush=True)
+    # warm steady state
+    for label, env in (("constant 72", {"C4_SP_ADAPT": "0"}), ("adaptive", {})):
+        os.environ.pop("C4_SP_ADAPT", None)
+        os.environ.update(env)
+        pool.stream(stop_games=slots, reset=True, cold_memo=True)
+        for _ in range(3):
+            r = pool.stream(max_ms=500.0)
+            print("%-12s warm 0.5 s: %.0f positions/s  hit %.3f" % (label, r["positions"] / r["device_ms"] * 1e3,
+                  r["memo_hits"] / max(1, r["memo_hits"] + r["evals"])), flush=True)
+    sys.exit(0)
 print("== 3. constant and phased tower counts", flush=True)
 plans = [[(72, None)]]
 if "--early" in sys.argv:                                            # more towers at the cold start: measured worse than constant 72

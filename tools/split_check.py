@@ -25,7 +25,7 @@ def gen(engine, slots, sims, n_games, seed=3):
 
 
 if "--perf-only" not in sys.argv:
-    for slots, sims, n in ((8, 16, 8), (64, 64, 200), (300, 200, 700), (1000, 100, 1500)):
+    for slots, sims, n in ((8, 16, 8), (64, 64, 200), (300, 200, 700), (1000, 100, 1500), (1024, 64, 3000)):
         a, ta = gen("split", slots, sims, n)
         b, tb = gen("lockstep", slots, sims, n)
         same = len(a) == len(b) and a.tobytes() == b.tobytes()

@@ -28,7 +28,7 @@ A "step" = one such generation: fresh pool, empty memo, until `--games` games ha
           figure is `roofline`, its HBM-side figure `roofline_other`.  Lock-step engine: the tree pass / the network
           kernel from launch durations sampled with CUDA events.
           `traffic` = DRAM bytes per launch from the committed ncu capture of the same command and launch shape
-          (profiles/r02_split_traffic.csv; split engine, default workload), else null: no DRAM counter is read inside a run.
+          (profiles/r02_split_adapt_launches.csv; split engine, default workload), else null: no DRAM counter is read inside a run.
   cpu_baseline = the oracle port (oracle/selfplay_port.py) on the box's host cores, bounded sample (rank 0, N=1 only).
   cpu_baseline_reference = the unmodified reference package (baseline/_ref, copied by build()) on the same cores: its
           multiprocess game_pool + InferenceServer path, a bounded sample of whole games -- context for how conservative the port is.
@@ -384,7 +384,11 @@ def main():
         peak_tf, peak_hbm, peak_src = peaks()
         flops = model.flops_per_position
         step_ms = 1000.0 * secs / args.steps
-        n_launch = args.steps * world
+        # kernels of the engine per step: the split engine cuts a step into time slices (adaptive tower count), one launch each;
+        # every c4_selfplay_stream call reports its launches (2 of them are the k_sum_stats bookkeeping kernels)
+        eng_launches = max(args.steps, int(tot["launches"]) - 2 * args.steps) if engine == "split" else args.steps
+        n_launch = eng_launches * world
+        launch_ms = 1000.0 * secs / eng_launches
         tf = evals * flops / secs / 1e12 / world                              # per GPU
         tree_bytes = positions * SIMS * 1280.0 + (evals + hits) * 64.0
         gbs = tree_bytes / secs / 1e9 / world
@@ -395,29 +399,34 @@ def main():
                 where_t = where_h = ""
             else:
                 sms = torch.cuda.get_device_properties(local).multi_processor_count
-                n_net = int(os.environ.get("C4_SP_NET_CTAS", (sms * 72 + 74) // 148))
-                kname_h = "k_sp_one<OpFP16,32,selfplay>, tree CTAs (%d of %d SMs: 31 game warps + 1 mail warp each)" % (sms - n_net, sms)
-                kname_t = "k_sp_one<OpFP16,32,selfplay>, tower CTAs (%d of %d SMs: tcgen05/TMEM tower, one leaf ring each)" % (n_net, sms)
-                where_h = "; runs on %d of %d SMs for the whole step, peak = whole device" % (sms - n_net, sms)
-                where_t = "; runs on %d of %d SMs for the whole step, peak = whole device" % (n_net, sms)
+                if "C4_SP_NET_CTAS" in os.environ or os.environ.get("C4_SP_ADAPT") == "0":
+                    n_net = int(os.environ.get("C4_SP_NET_CTAS", (sms * 72 + 74) // 148))
+                    n_t, n_h = "%d" % n_net, "%d" % (sms - n_net)
+                else:                                                 # adaptive: chosen per 25 ms slice from the previous slice's load
+                    n_t = "%d..%d (adaptive, per slice)" % ((sms * 40 + 74) // 148, (sms * 96 + 74) // 148)
+                    n_h = "%d..%d (adaptive, per slice)" % (sms - (sms * 96 + 74) // 148, sms - (sms * 40 + 74) // 148)
+                kname_h = "k_sp_one<OpFP16,32,selfplay>, tree CTAs (%s of %d SMs: 31 game warps + 1 mail warp each)" % (n_h, sms)
+                kname_t = "k_sp_one<OpFP16,32,selfplay>, tower CTAs (%s of %d SMs: tcgen05/TMEM tower, one leaf ring each)" % (n_t, sms)
+                where_h = "; runs on %s of %d SMs, %.1f launches (time slices) per step back to back, peak = whole device" % (n_h, sms, eng_launches / args.steps)
+                where_t = "; runs on %s of %d SMs, %.1f launches (time slices) per step back to back, peak = whole device" % (n_t, sms, eng_launches / args.steps)
             roof_t = {"kernel": kname_t, "bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                       "traffic": None, "peak_source": peak_src, "flops_per_eval": flops, "evals_per_launch": evals / n_launch,
-                      "ms_per_launch": step_ms, "share_of_step": 1.0,
+                      "ms_per_launch": launch_ms, "share_of_step": 1.0,
                       "note": "network FLOPs of the step / step time; the towers run short strips (latency over fill), bound by the "
                               "per-tile issue / epilogue chain, not by the tensor pipe" + where_t}
             roof_h = {"kernel": kname_h, "bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
                       "traffic": None, "peak_source": peak_src.replace("sustained bf16", "copy bandwidth"),
                       "algorithmic_bytes_per_launch": tree_bytes / n_launch, "sims_per_launch": positions * SIMS / n_launch,
-                      "ms_per_launch": step_ms, "share_of_step": 1.0,
+                      "ms_per_launch": launch_ms, "share_of_step": 1.0,
                       "note": "1.28 KB per simulation (SURVEY.md 8d) + 64 B per memo probe; dependent-load latency bound" + where_h}
             if engine == "split" and args.games == 4096 and "C4_SP_NET_CTAS" not in os.environ:
-                # DRAM bytes of this very launch shape from the ncu capture of the same command (profiles/r02_split_traffic.csv:
+                # DRAM bytes of this very launch shape from the ncu capture of the same command (profiles/r02_split_adapt_launches.csv:
                 # `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:k_sp_one python bench.py --steps 1 --warmup 1
                 # --no-e2e --no-cpu --no-extras`); whole kernel = both roles; no counter is read inside this run
-                t = ncu_traffic(os.path.join(ROOT, "profiles", "r02_split_traffic.csv"))
+                t = ncu_traffic(os.path.join(ROOT, "profiles", "r02_split_adapt_launches.csv"))
                 if t:
                     roof_h["traffic"] = t
-                    roof_h["traffic_source"] = ("profiles/r02_split_traffic.csv: dram__bytes_read.sum + dram__bytes_write.sum per k_sp_one "
+                    roof_h["traffic_source"] = ("profiles/r02_split_adapt_launches.csv: dram__bytes_read.sum + dram__bytes_write.sum per k_sp_one "
                                                 "launch (whole kernel, both roles), ncu capture of the same workload, not this run")
             if engine == "split":
                 roof_t, roof_h = roof_h, roof_t                       # `roofline` = the tree kernel: it bounds the step (tower CTAs have slack)

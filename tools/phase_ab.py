@@ -52,6 +52,8 @@ tab = "1" if best["1"] > best["0"] else "0"
 os.environ["C4_SP_SMEM_TABLES"] = tab
 print("-> tables %s for the rest" % tab, flush=True)
 
+if "--only-tables" in sys.argv:
+    sys.exit(0)
 print("== 2. time profile of one generation, 72 towers, slices of %.0f ms" % slice_ms, flush=True)
 os.environ["C4_SP_NET_CTAS"] = "72"
 games = 0
@@ -78,6 +80,23 @@ if "--signals" in sys.argv:
             print("towers %d t %6.1f ms: %7.0f positions/s  %8.0f evals/s  hit %.3f  games done %d" % (
                 n, t, r["positions"] / r["device_ms"] * 1e3, r["evals"] / r["device_ms"] * 1e3,
                 r["memo_hits"] / max(1, r["memo_hits"] + r["evals"]), games), flush=True)
+    sys.exit(0)
+if "--tune" in sys.argv:
+    # controller variants (C4_SP_ADAPT_TUNE = fast_ms,gain_up,gain_down,max_step): cold generation, 16,384-game generation
+    import time
+    for tune in ("25,1,1,16", "10,1,1,16", "25,1,1.5,16", "10,1,1.5,16", "10,1,1.5,24", "10,1.25,1.5,24", "12,1,2,24", "25,1,1,16"):
+        os.environ.pop("C4_SP_NET_CTAS", None)
+        os.environ["C4_SP_ADAPT_TUNE"] = tune
+        res = []
+        for _ in range(3):
+            r = pool.stream(stop_games=slots, reset=True, cold_memo=True)
+            res.append(r["positions"] / r["device_ms"] * 1e3)
+        pool.engine.clear_memo()
+        t0 = time.perf_counter()
+        rec = pool.generate_records(4 * slots)
+        dt = time.perf_counter() - t0
+        print("tune %-16s cold generation %s (launches %d) | generate_records(%d) %.0f positions/s" % (
+            tune, ", ".join("%.0f" % v for v in res), r["launches"], 4 * slots, len(rec) / dt), flush=True)
     sys.exit(0)
 if "--adapt" in sys.argv:
     # adaptive tower count (the engine's default for 32-filter networks from 1,024 games) against the constant 72

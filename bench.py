@@ -183,15 +183,15 @@ def digest_records(rec):
     return h.hexdigest()[:16]
 
 
-def ncu_traffic(path):
-    """mean over the launches in an ncu --csv metrics file of dram__bytes_read.sum + dram__bytes_write.sum (bytes), or None"""
+def ncu_traffic(path, kernel="k_sp_one"):
+    """mean over the launches of `kernel` in an ncu --csv metrics file of dram__bytes_read.sum + dram__bytes_write.sum (bytes), or None"""
     import csv
     try:
         per = {}
         with open(path) as f:
             rows = [r for r in csv.reader(f) if len(r) > 14 and r[0].isdigit()]
         for r in rows:
-            if r[12] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if r[12] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and kernel in r[4]:
                 per[r[0]] = per.get(r[0], 0.0) + float(r[14].replace(",", ""))
         return sum(per.values()) / len(per) if per else None
     except OSError:

@@ -134,7 +134,7 @@ struct SpPort {
     uint32_t stage_nodes;
     __device__ __forceinline__ void stage(GameS &g, int gl) const { g.sp32 = stage_base32 + (uint32_t)gl * stage_nodes * 32u; g.sp_nodes = stage_nodes; }
 #else
-    typedef typename std::conditional<TAB, GameTab<SP_TAB_OFF, SP_TAB_STRIDE>, Game>::type GameType;
+    typedef typename std::conditional<TAB, GameTab<SP_TAB_OFF, SP_TAB_STRIDE>, GameNP>::type GameType;
     __device__ __forceinline__ void stage(Game &, int) const {}
 #endif
     const uint32_t *memo;

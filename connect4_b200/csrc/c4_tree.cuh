@@ -281,9 +281,14 @@ struct Game {
     u64 c0, c1;          // root board
     int age;             // root age
     static constexpr bool SMEM_TABLES = false;   // the PUCT tables are read from HBM (through L1) via C4Dev::pbc / sqt / rcp
+    static constexpr bool PREFETCH = true;       // descend() pulls every child's own block towards L2 while the warp decides
     // node accessors (node i of this game): every read / write of the tree goes through these
     __device__ __forceinline__ C4NodeA lda(uint32_t i) const { return ld_a(gp + i); }
     __device__ __forceinline__ C4NodeB ldb(uint32_t i) const { return ld_b(gp + i); }
+    // both halves of node i (what select reads of a child): two 128-bit loads through L1.  Measured in the split engine and not
+    // kept (profiles/README.md): ONE 256-bit load (`ld.global.v4.u64` = LDG.E.ENL2.256 on sm_100a) 446.7k against 450k positions/s,
+    // two `ld.global.cg` loads 442k -- the 28 KB of L1 the tree CTAs have left still serve 37-41 % of the node reads
+    __device__ __forceinline__ void ldab(uint32_t i, C4NodeA &a, C4NodeB &b) const { a = ld_a(gp + i); b = ld_b(gp + i); }
     __device__ __forceinline__ void sta(uint32_t i, double vsum, uint32_t visits, uint32_t meta) const { st_a(gp + i, vsum, visits, meta); }
     __device__ __forceinline__ void stb(uint32_t i, double prior, double vsel) const { st_b(gp + i, prior, vsel); }
     __device__ __forceinline__ void st_vsel(uint32_t i, double vsel) const { gp[i].b.vsel = vsel; }
@@ -293,8 +298,12 @@ struct Game {
 // OFF + k * 8 * STRIDE: compile-time offsets from the dynamic shared-memory base, so a table read is one LDS with an immediate
 // and costs no pointer register (three generic pointers instead spilled the 64-register tree warps).  Used by the tree CTAs
 // of the one-launch split engine (c4_split.cu), which carry the tower's shared memory and have little L1.
+// (no speculative prefetch of the grandchildren's blocks: tuned in round 1 for the lock-step pass, where a warp's lines have to come
+//  back from L2 / HBM at every pass; in the persistent split engine a game stays on its SM and the 14 prefetch instructions per level
+//  only take issue slots and L1 / L2 request bandwidth from the 31 tree warps: 434k -> 449k positions/s without them)
+struct GameNP : Game { static constexpr bool PREFETCH = false; };
 template <uint32_t OFF, uint32_t STRIDE>
-struct GameTab : Game {
+struct GameTab : GameNP {
     static constexpr bool SMEM_TABLES = true;
     static __device__ __forceinline__ const double *table(int k)
     {
@@ -332,6 +341,7 @@ struct GameS : Game {
         a.vsum = __hiloint2double((int)v.y, (int)v.x); a.visits = v.z; a.meta = v.w;
         return a;
     }
+    __device__ __forceinline__ void ldab(uint32_t i, C4NodeA &a, C4NodeB &b) const { a = lda(i); b = ldb(i); }
     __device__ __forceinline__ C4NodeB ldb(uint32_t i) const
     {
         const uint4 v = ld16(i, 1u);
@@ -484,8 +494,9 @@ __device__ __forceinline__ Leaf descend(const C4Dev &d, const GAME &G)
         const uint32_t blk = c4_meta_child_block(meta);
         C4_DEV_ASSERT(blk > 0u && (int)blk < G.n_blocks && L.depth < PATH_CAP - 1);
         const uint32_t cn = blk * C4_SLOTS + (uint32_t)(lane & 7);
-        C4NodeA a = G.lda(cn);
-        C4NodeB b = G.ldb(cn);
+        C4NodeA a;
+        C4NodeB b;
+        G.ldab(cn, a, b);
         // exploration factor of the parent: log((N+base+1)/base)+init and sqrt(N) from host-built tables (glibc log / sqrt)
         double pbc, sq;
         if constexpr (GAME::SMEM_TABLES) { pbc = GAME::table(0)[visits]; sq = GAME::table(1)[visits]; }
@@ -493,7 +504,7 @@ __device__ __forceinline__ Leaf descend(const C4Dev &d, const GAME &G)
         const bool exists = (lane < 7) && (a.meta & C4_META_EXISTS);
         // speculative prefetch: every lane pulls ITS child's block (two 128-byte lines) towards L2 while the warp decides;
         // HBM bandwidth is nowhere near a limit for this kernel (profiles/README.md)
-        if (exists && c4_meta_child_block(a.meta) != 0u && G.in_hbm(c4_meta_child_block(a.meta))) {
+        if (GAME::PREFETCH && exists && c4_meta_child_block(a.meta) != 0u && G.in_hbm(c4_meta_child_block(a.meta))) {
             const char *pf = reinterpret_cast<const char *>(G.gp + (size_t)c4_meta_child_block(a.meta) * C4_SLOTS);
             asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
             asm volatile("prefetch.global.L2 [%0];" :: "l"(pf + 128));

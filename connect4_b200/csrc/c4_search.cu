@@ -582,7 +582,7 @@ extern "C" int c4_ctx_create(int device, int32_t max_games, const c4_mcts_config
         int lg = 14;
         while (lg < 28 && (1LL << lg) < (long long)max_games * 65536) lg++;
         if (getenv("C4_MEMO_LOG2")) lg = atoi(getenv("C4_MEMO_LOG2"));
-        ctx->memo_log2 = (lg >= 10 && lg <= 28) ? lg : 0;
+        ctx->memo_log2 = (lg >= 10 && lg <= 30) ? lg : 0;   // (29 and 30 through the environment only: 34 / 69 GB)
     }
     const size_t G = (size_t)max_games;
     d.blocks_per_game = cfg->simulations + 2;

@@ -114,6 +114,34 @@ def test_adaptive_tower_count_and_shared_memory_tables_change_work_not_results(m
     _same(recs[0], _generate(monkeypatch, "lockstep", model, _cfg(64), 1100, 2600, seed=5))
 
 
+def test_large_search_batch_in_slices_and_searches_beyond_the_shared_memory_tables(monkeypatch):
+    """(a) a stand-alone search batch of more than 1,024 positions runs in time slices with the adaptive tower count like a
+    generation does; (b) searches of more simulations than the shared-memory PUCT tables hold (4,096 entries) fall back to the
+    tables in HBM.  Root read-outs / records equal to the lock-step engine's"""
+    from connect4_b200.engine import Engine
+    model = _model()
+    c0, c1 = random_positions(23, 1100)
+    outs = {}
+    for engine, adapt in (("split", "1.5"), ("split", "0"), ("lockstep", "0")):
+        monkeypatch.setenv("C4_ENGINE", engine)
+        monkeypatch.setenv("C4_SP_ADAPT", adapt)                       # "1.5" = slices of 1.5 ms
+        eng = Engine(1100, _cfg(120, 0.0, 0.0, 0))
+        eng.set_net(model)
+        eng.begin(c0, c1)
+        eng.run("net")
+        outs[(engine, adapt)] = eng.readout()
+        eng.close()
+    monkeypatch.delenv("C4_SP_ADAPT", raising=False)
+    ref = outs[("lockstep", "0")]
+    assert (ref["root_visits"] == 121).all()
+    for k in ref:
+        assert outs[("split", "1.5")][k].tobytes() == ref[k].tobytes(), k
+        assert outs[("split", "0")][k].tobytes() == ref[k].tobytes(), k
+    a = _generate(monkeypatch, "split", model, _cfg(4200), 2, 2, seed=9)
+    b = _generate(monkeypatch, "lockstep", model, _cfg(4200), 2, 2, seed=9)
+    _same(a, b)
+
+
 def test_split_search_batch_equals_lockstep_and_oracle(monkeypatch, oracle):
     """stand-alone searches (MCTS.make_move protocol, c4_search_run NET): the whole batch in one persistent launch pair"""
     from connect4_b200.engine import Engine

@@ -30,6 +30,11 @@
 // bounded (tree-warp watchdog -> abort flag -> all CTAs leave; host deadline through a mapped word), so a protocol bug ends
 // in an error code, not in a hung device.
 //
+// Last part of round 2: the tree CTAs of the one-launch form keep the PUCT tables in the shared memory they
+// carry anyway (GameTab, c4_tree.cuh: compile-time offsets, plain LDS) and descend without the lock-step pass's speculative prefetch
+// (GameNP); and the split of the SMs between the roles is ADAPTIVE: a run is cut into time slices (SpParams::slice_ns), each slice is
+// one launch, and the host picks the next slice's tower count from the load signals of the last one (sp_adapt_next).
+//
 // NO gpu-scope fence on the data path: __threadfence() invalidates the SM's whole L1 (CCTL.IVALL) -- in a tree CTA that
 // is the cache of the node records, and the first version paid it on every request and every answer.  Instead every
 // cross-SM message is made of self-validating 8-byte words (aligned 8-byte stores and loads are single transactions):

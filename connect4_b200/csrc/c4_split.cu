@@ -835,6 +835,12 @@ struct SpAdapt {
     int lo = 0, hi = 0;
     double slice_ms = 25.0;
 };
+// 40..96 of 148 SMs as towers, and never so many that a tree CTA would own more than SP_GC_MAX game slots
+static void sp_adapt_bounds(SpAdapt &a, int max_games, int sms)
+{
+    a.lo = (sms * 40 + 74) / 148;
+    a.hi = std::min((sms * 96 + 74) / 148, sms - (max_games + SP_GC_MAX - 1) / SP_GC_MAX);
+}
 static SpAdapt sp_adapt_config(const c4_net *net, int max_games, int sms, bool two)
 {
     SpAdapt a;
@@ -843,8 +849,7 @@ static SpAdapt sp_adapt_config(const c4_net *net, int max_games, int sms, bool t
     if (two || getenv("C4_SP_NET_CTAS") || net->F != 32 || max_games < 1024) return a;    // (measured for 32-filter networks only)
     a.on = true;
     if (e && atof(e) > 1.0) a.slice_ms = atof(e);
-    a.lo = (sms * 40 + 74) / 148;
-    a.hi = std::min((sms * 96 + 74) / 148, sms - (max_games + SP_GC_MAX - 1) / SP_GC_MAX);
+    sp_adapt_bounds(a, max_games, sms);
     if (a.hi < a.lo) a.on = false;
     return a;
 }
@@ -861,6 +866,19 @@ static int sp_adapt_next(const SpAdapt &a, int sms, int n_net, int n_tree, const
     int n = (int)(target / 4.0 + 0.5) * 4;
     n = std::max(a.lo, std::min(a.hi, n));
     return n;
+}
+
+// Test hook (tests/test_host_logic.py; host arithmetic only, no GPU): the tower count the controller picks after a slice with
+// `n_net` towers on a device of `sms` SMs that served `boards` boards in `strips` strips while the tree warps spent
+// `run_cycles` in runs and `idle_cycles` without a runnable game.
+extern "C" int c4_split_adapt_next(int sms, int max_games, int n_net, unsigned long long strips, unsigned long long boards,
+                                   unsigned long long run_cycles, unsigned long long idle_cycles)
+{
+    SpAdapt a;
+    a.on = true;
+    sp_adapt_bounds(a, max_games, sms);
+    const unsigned long long sig[4] = {strips, boards, run_cycles, idle_cycles};
+    return sp_adapt_next(a, sms, n_net, std::min(sms - n_net, max_games), sig);
 }
 
 static bool c4_split_supported(const c4_net *net, int max_games)

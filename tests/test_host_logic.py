@@ -207,3 +207,37 @@ def test_match_chooses_the_lock_step_path_only_for_deterministic_device_players(
     assert all(g._player_o.evaluator is centre.evaluator for g in m.games[:7])
     assert all(g._player_o.evaluator is net.evaluator for g in m.games[7:])
     assert all(g.player_to_move() is g._player_x for g in m.games)      # after one ply x is to move
+
+
+def test_adaptive_tower_count_decisions():
+    """the split engine's controller (csrc/c4_split.cu, sp_adapt_next) on load signals measured on a B200 (profiles/README.md,
+    time profile of a generation): host arithmetic only, reached through a test hook of the library"""
+    import ctypes
+    from connect4_b200 import _build
+    L = ctypes.CDLL(_build.build())
+    f = L.c4_split_adapt_next
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int] * 3 + [ctypes.c_ulonglong] * 4
+
+    def nxt(n_net, boards_per_strip, idle_share, games=4096, sms=148):
+        strips = 10000
+        return f(sms, games, n_net, strips, int(round(boards_per_strip * strips)), int(round((1.0 - idle_share) * 1e9)), int(round(idle_share * 1e9)))
+
+    # middle game: saturated towers (15+ boards per strip) hold the trees back -> more towers, at most 16 at a time
+    assert nxt(56, 15.33, 0.34) == 72
+    assert nxt(64, 15.6, 0.43) == 80
+    assert nxt(72, 15.5, 0.25) in (80, 84)
+    # balanced: towers full, tree warps idle ~5 % -> stays within one step of 4
+    assert abs(nxt(80, 15.1, 0.062) - 80) <= 4
+    # tail: short strips, trees never wait -> towers become tree SMs
+    assert nxt(72, 5.0, 0.0) == 56
+    assert nxt(80, 3.7, 0.0) == 64                                   # (wants ~54: one step of 16)
+    assert nxt(56, 12.6, 0.027) == 56
+    # cold start: the trees wait although the strips are short -- latency, not capacity: no tower is taken away
+    assert nxt(56, 4.18, 0.10) == 56
+    assert nxt(56, 1.0, 0.069) == 56
+    # bounds: 40..96 of 148 SMs, and a tree CTA owns at most 256 game slots (16,384 games -> at least 64 tree CTAs)
+    assert nxt(96, 16.0, 0.6) == 96
+    assert nxt(40, 1.0, 0.0) == 40
+    assert nxt(84, 16.0, 0.5, games=16384) == 84
+    assert nxt(66, 16.0, 0.5, sms=132) <= (132 * 96 + 74) // 148     # a smaller device scales the bounds

@@ -66,3 +66,66 @@ def test_sort_records_device_orders_by_game_and_ply():
     for f in ("game_id", "ply", "c0"):
         assert (out[f] == ref[f]).all()
     assert sort_records_device(raw[:0]).shape == (0, 64)
+
+
+class _FakeEngine:
+    last_records_device = None
+    last_generation_device = None
+
+
+class _FakePool:
+    """stands in for SelfPlayPool on a machine without a GPU: `plays` a rank's share by writing records whose game ids follow
+    the (base, stride) numbering and whose number of plies depends on the game (ragged shares)"""
+    def __init__(self):
+        self.engine = _FakeEngine()
+
+    def generate_records(self, n_games, game_id_base=0, game_id_stride=1, start=None, to_host=True):
+        from connect4_b200.engine import RECORD_DTYPE
+        gids = [game_id_base + i * game_id_stride for i in range(n_games)]
+        rows = [(g, p) for g in reversed(gids) for p in range(3 + g % 4)]          # games finish out of order
+        rec = np.zeros(len(rows), dtype=RECORD_DTYPE)
+        rec["game_id"] = [r[0] for r in rows]
+        rec["ply"] = [r[1] for r in rows]
+        rec["c0"] = [1000 * r[0] + r[1] for r in rows]
+        self.engine.last_records_device = torch.as_tensor(rec.view(np.uint8).reshape(len(rows), 64).copy())
+        assert not to_host
+
+
+def _worker_sharded(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from connect4_b200.dist import generate_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pool = _FakePool()
+    everyone = generate_sharded(pool, 11)                                           # every rank gets the generation
+    timing = {}
+    only0 = generate_sharded(pool, 11, dst=0, timing=timing)                        # only rank 0 copies it to its host
+    held = pool.engine.last_generation_device.shape[0]
+    q.put((rank, everyone.copy(), None if only0 is None else only0.copy(), sorted(timing), held))
+    dist.destroy_process_group()
+
+
+def test_generate_sharded_world2_dst_and_timing():
+    """dist.generate_sharded over two gloo ranks with a stand-in pool: game g is played by rank g % 2, the gathered generation
+    is complete, in (game_id, ply) order and identical on both ranks; with dst=0 only rank 0 gets a host copy while every
+    rank keeps the whole generation where its records live; the per-phase timing names the four phases"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    want = [(g, p) for g in range(11) for p in range(3 + g % 4)]
+    for rank, everyone, only0, phases, held in res:
+        assert list(zip(everyone["game_id"].tolist(), everyone["ply"].tolist())) == want
+        assert (everyone["c0"] == 1000 * everyone["game_id"].astype(np.int64) + everyone["ply"]).all()
+        assert phases == sorted(["generate", "all_gather", "sort"] + (["host_copy"] if rank == 0 else []))
+        assert held == len(want)
+        assert (only0 is None) == (rank != 0)
+    for f in res[0][1].dtype.names:                       # field by field (numpy leaves a record's padding bytes undefined)
+        assert res[0][1][f].tobytes() == res[1][1][f].tobytes() == res[0][2][f].tobytes(), f
